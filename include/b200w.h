@@ -1,0 +1,166 @@
+/* b200w — C ABI of the B200-native fine-tune / serve worker.
+ *
+ * The reference (substratusai/runbooks) is a Go operator with no FFI of its own: its boundary to
+ * the hot path is the container contract (docs/container-contract.md) and the Pod spec built by
+ * internal/controller/model_controller.go:286-395 (trainer Job) and
+ * internal/controller/server_controller.go:114-205 (server Deployment). The arithmetic lives in
+ * the un-vendored trainer image (examples/llama2-7b/finetuned-model.yaml:6). This header is the
+ * C boundary a Go host (cgo), the Python host in runbooks_b200/ (ctypes) or a C++ host binds to
+ * in order to run that arithmetic on a B200; INTEGRATION.md shows each binding.
+ *
+ * Conventions: extern "C"; opaque context; every function returns 0 on success
+ * and a negative b200w_status on failure, with b200w_last_error() giving the message; no C++
+ * exception crosses the boundary; the caller owns host buffers, the library owns device memory
+ * unless a function says "device pointer"; a context is bound to one CUDA device and is not
+ * thread-safe (one context per rank).
+ */
+#ifndef B200W_H_
+#define B200W_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200W_ABI_VERSION 1
+#if defined(__GNUC__)
+#define B200W_API __attribute__((visibility("default")))
+#else
+#define B200W_API
+#endif
+
+typedef enum {
+  B200W_OK = 0,
+  B200W_ERR_INVALID = -1, /* bad argument / unsupported shape */
+  B200W_ERR_CUDA = -2,    /* CUDA runtime or driver failure    */
+  B200W_ERR_NCCL = -3,    /* NCCL failure or libnccl missing   */
+  B200W_ERR_STATE = -4,   /* call order (e.g. step before init) */
+  B200W_ERR_OOM = -5
+} b200w_status;
+
+typedef enum { B200W_BF16 = 0, B200W_F32 = 1, B200W_I32 = 2 } b200w_dtype;
+
+/* Architecture of the causal LM. Llama family for this round (models/llama/modeling_llama.py in
+ * HF transformers 5.5.0 is the oracle: RMSNorm, rotate_half RoPE, SwiGLU, untied lm_head, no
+ * biases). head_dim must be 128. */
+typedef struct {
+  int32_t vocab_size;
+  int32_t hidden_size;
+  int32_t intermediate_size;
+  int32_t num_layers;
+  int32_t num_heads;
+  int32_t num_kv_heads;
+  int32_t head_dim;
+  int32_t max_seq_len; /* sequences are packed to exactly this many tokens */
+  float rms_norm_eps;
+  float rope_theta;
+} b200w_arch;
+
+/* Optimiser hyper-parameters; b200w_default_hparams() fills in the transformers.TrainingArguments
+ * defaults the reference's trainer image inherits. */
+typedef struct {
+  float lr;            /* 5e-5; the per-step value is passed to b200w_train_step            */
+  float beta1, beta2;  /* 0.9, 0.999                                                          */
+  float eps;           /* 1e-8                                                                */
+  float weight_decay;  /* 0.0                                                                 */
+  float max_grad_norm; /* 1.0 (<= 0 disables clipping)                                        */
+} b200w_hparams;
+
+typedef struct b200w_ctx b200w_ctx;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+B200W_API int b200w_abi_version(void);
+B200W_API int b200w_create(int device, b200w_ctx** out);
+B200W_API void b200w_destroy(b200w_ctx* ctx);
+B200W_API const char* b200w_last_error(const b200w_ctx* ctx); /* ctx may be NULL: last create() error */
+B200W_API int b200w_sync(b200w_ctx* ctx);
+B200W_API void b200w_default_hparams(b200w_hparams* hp);
+
+/* ---- model state -------------------------------------------------------------------------- */
+/* Allocates weights (bf16 compute copy + fp32 master), Adam moments, gradients and the
+ * activation arena for micro-batches of `micro_batch` sequences. training=0 skips optimiser
+ * state (inference / forward-only). */
+B200W_API int b200w_model_init(b200w_ctx* ctx, const b200w_arch* arch, const b200w_hparams* hp,
+                     int micro_batch, int training);
+/* Parameter names follow the HF checkpoint keys ("model.embed_tokens.weight",
+ * "model.layers.0.self_attn.q_proj.weight", ..., "lm_head.weight"). Host buffers. */
+B200W_API int b200w_param_count(b200w_ctx* ctx, int64_t* n_tensors, int64_t* n_elements);
+B200W_API int b200w_param_info(b200w_ctx* ctx, int64_t index, char* name, size_t name_cap, int64_t* rows,
+                     int64_t* cols);
+B200W_API int b200w_load_tensor(b200w_ctx* ctx, const char* name, const void* host, b200w_dtype dtype,
+                      int64_t n_elements);
+B200W_API int b200w_read_tensor(b200w_ctx* ctx, const char* name, void* host, b200w_dtype dtype,
+                      int64_t n_elements);
+/* kind: 0 = fp32 master weight, 1 = gradient (fp32), 2 = Adam m, 3 = Adam v */
+B200W_API int b200w_read_state(b200w_ctx* ctx, const char* name, int kind, float* host, int64_t n_elements);
+/* normal(0, std) init of every matrix, ones for norm weights (HF _init_weights), counter-based
+ * RNG seeded with `seed` — for benchmarks; parity tests load explicit tensors instead. */
+B200W_API int b200w_init_random(b200w_ctx* ctx, uint64_t seed, float std);
+
+/* ---- data-parallel communicator (NCCL over NVLink; libnccl is dlopen'ed on first use) ------ */
+B200W_API int b200w_comm_unique_id(void* id128); /* 128 bytes, call on rank 0, ship to the others */
+B200W_API int b200w_comm_init(b200w_ctx* ctx, int rank, int nranks, const void* id128);
+
+/* ---- the fine-tune step -------------------------------------------- */
+/* ids/labels: HOST int32 [n_seqs, max_seq_len]; n_seqs must be a multiple of micro_batch (the
+ * step runs n_seqs / micro_batch accumulation micro-steps, which equals one HF batch of n_seqs
+ * sequences: loss = sum(nll) / num_valid_tokens, HF loss_utils.py:28-42). labels follow the HF
+ * convention (unshifted; -100 ignored). With a communicator, gradients are averaged over ranks
+ * (DDP semantics) by a bucketed all-reduce overlapped with the last micro-step's backward.
+ * Order inside: fwd, loss, bwd, [all-reduce], global-norm clip, AdamW. loss_out / gnorm_out:
+ * HOST floats (this rank's mean loss; global pre-clip gradient norm). */
+B200W_API int b200w_train_step(b200w_ctx* ctx, const int32_t* ids, const int32_t* labels, int n_seqs, float lr,
+                     float* loss_out, float* gnorm_out);
+/* Forward + loss + backward only (no optimiser step): fills gradients for inspection. */
+B200W_API int b200w_forward_backward(b200w_ctx* ctx, const int32_t* ids, const int32_t* labels, int n_seqs,
+                           float* loss_out);
+/* Forward only; logits_out: HOST float [n_seqs * max_seq_len, vocab] or NULL; per-token nll
+ * (HOST float [n_seqs * max_seq_len], 0 where ignored) or NULL. n_seqs <= micro_batch. */
+B200W_API int b200w_forward(b200w_ctx* ctx, const int32_t* ids, const int32_t* labels, int n_seqs,
+                  float* logits_out, float* nll_out, float* loss_out);
+/* Number of kernels the library launched since the context was created (bench.py's
+ * gpu_launches) and device bytes currently allocated. */
+B200W_API int64_t b200w_launch_count(const b200w_ctx* ctx);
+B200W_API int64_t b200w_device_bytes(const b200w_ctx* ctx);
+
+/* ---- per-kernel hooks for the parity tests (DEVICE pointers, bf16 unless noted) ------------ */
+/* D[M,N] = opA[M,K] opB[N,K]^T (+C). a_mn / b_mn: operand stored [K,M] / [K,N] row-major.
+ * out_f32: D and C are fp32. C may be NULL or alias D. block_n: 0 auto, 128, 256. */
+B200W_API int b200w_op_gemm(b200w_ctx* ctx, const void* A, int a_mn, int lda, const void* B, int b_mn, int ldb,
+                  void* D, const void* C, int out_f32, int ldd, int M, int N, int K, int block_n);
+B200W_API int b200w_op_embed_fwd(b200w_ctx* ctx, const int32_t* ids, const void* table, void* out, int T, int d,
+                       int vocab);
+B200W_API int b200w_op_embed_bwd(b200w_ctx* ctx, const int32_t* ids, const void* dout, float* dtable, int T,
+                       int d, int vocab);
+B200W_API int b200w_op_rmsnorm_fwd(b200w_ctx* ctx, const void* x, const void* w, void* y, float* rstd, int T,
+                         int d, float eps);
+B200W_API int b200w_op_rmsnorm_bwd(b200w_ctx* ctx, const void* dy, const void* x, const void* w,
+                         const float* rstd, const void* dresid, void* dx, float* dw, int T, int d);
+/* in-place rotate_half RoPE on `nheads` heads of head_dim `dh` starting at column 0 of
+ * buf [T, ld]; position = t % S */
+B200W_API int b200w_op_rope(b200w_ctx* ctx, void* buf, int ld, int T, int S, int nheads, int dh, float theta,
+                  int inverse);
+B200W_API int b200w_op_swiglu_fwd(b200w_ctx* ctx, const void* gu, void* h, int T, int f);
+B200W_API int b200w_op_swiglu_bwd(b200w_ctx* ctx, const void* dh, const void* gu, void* dgu, int T, int f);
+/* labels (unshifted, int32 [T]) -> nll fp32 [T]; logits overwritten by dlogits * inv_n */
+B200W_API int b200w_op_ce(b200w_ctx* ctx, void* logits, const int32_t* labels, float* nll, int T, int S, int V,
+                float inv_n);
+B200W_API int b200w_op_attention_fwd(b200w_ctx* ctx, const void* qkv, int ld_qkv, int k_off, int v_off,
+                           void* out, int ld_out, float* lse2, int B, int S, int H, int Hkv,
+                           float scale);
+B200W_API int b200w_op_attention_bwd(b200w_ctx* ctx, const void* qkv, int ld_qkv, int k_off, int v_off,
+                           const void* out, const void* dout, int ld_out, const float* lse2,
+                           float* delta, float* dq32, void* dqkv, int B, int S, int H, int Hkv,
+                           float scale);
+B200W_API int b200w_op_adamw(b200w_ctx* ctx, float* master, float* m, float* v, const float* g, void* w_bf16,
+                   int64_t n, float lr, float beta1, float beta2, float eps, float wd, int step,
+                   float gscale);
+/* returns sqrt(sum g^2) in *norm_out (HOST) */
+B200W_API int b200w_op_grad_norm(b200w_ctx* ctx, const float* g, int64_t n, float* norm_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200W_H_ */

@@ -1,0 +1,878 @@
+// The fine-tune engine behind include/b200w.h: parameter / optimiser / activation memory for a
+// Llama-family causal LM, the forward-loss-backward-clip-AdamW step as a sequence of the
+// kernels in gemm.cu / attention.cu / ops.cu on one stream, and the data-parallel gradient
+// all-reduce (NCCL, dlopen'ed) on a second stream overlapped with the last backward.
+//
+// Oracle for every stage: HF transformers 5.5.0 LlamaForCausalLM + the hand-written HF-Trainer
+// step in oracle/ (SURVEY.md §8c): loss.backward(); clip_grad_norm_(1.0); AdamW.step().
+#include <dlfcn.h>
+#include <math.h>
+#include <string.h>
+
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/b200w.h"
+#include "host_common.h"
+#include "ops.h"
+#include "ptx.cuh"
+
+using namespace b200w;
+using bf16 = __nv_bfloat16;
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library must load (and export its symbols) on a box without NCCL.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Uid { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Uid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;
+
+NcclApi& nccl() {
+  static NcclApi api;
+  if (!api.lib) {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (!api.lib) throw Error(std::string("cannot dlopen libnccl: ") + dlerror());
+    auto sym = [&](const char* s) {
+      void* p = dlsym(api.lib, s);
+      if (!p) throw Error(std::string("libnccl lacks symbol ") + s);
+      return p;
+    };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+  }
+  return api;
+}
+#define B200W_NCCL(expr)                                                                  \
+  do {                                                                                    \
+    int _r = (expr);                                                                      \
+    if (_r != 0) throw NcclError(std::string(#expr) + ": " + nccl().GetErrorString(_r));  \
+  } while (0)
+struct NcclError : Error { using Error::Error; };
+
+std::string g_create_error;
+
+struct Param {
+  std::string name;
+  int64_t rows, cols;
+  size_t off;  // element offset into the flat parameter space
+  bool is_norm;
+};
+
+__global__ void init_normal_kernel(float* master, bf16* w, size_t n, uint64_t seed, float std) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // splitmix64 counter hash -> two uniforms -> Box-Muller
+    uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u1 = (static_cast<uint32_t>(z >> 32) + 1.0f) * (1.0f / 4294967296.0f);
+    const float u2 = static_cast<uint32_t>(z) * (1.0f / 4294967296.0f);
+    const float r = sqrtf(-2.f * __logf(u1)) * __cosf(6.2831853f * u2) * std;
+    if (master) master[i] = r;
+    w[i] = __float2bfloat16_rn(r);
+  }
+}
+__global__ void fill_kernel(float* master, bf16* w, size_t n, float val) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    if (master) master[i] = val;
+    w[i] = __float2bfloat16_rn(val);
+  }
+}
+}  // namespace
+
+struct b200w_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int64_t dev_bytes = 0;
+  std::vector<void*> allocs;
+
+  // ---- model ----
+  bool has_model = false, training = false;
+  b200w_arch arch{};
+  b200w_hparams hp{};
+  int micro_batch = 0;
+  int step = 0;
+  std::vector<Param> params;
+  std::unordered_map<std::string, int> index;
+  size_t n_elems = 0;       // all parameters
+  size_t n_zero_prefix = 0; // embed + norm weights: gradients accumulated with atomics
+  bf16* w = nullptr;
+  float *master = nullptr, *m = nullptr, *v = nullptr, *g = nullptr;
+  float2* rope_tab = nullptr;
+
+  struct LayerP { size_t ln1, ln2, wqkv, wo, wgu, wd; };
+  std::vector<LayerP> lp;
+  size_t p_embed = 0, p_norm = 0, p_lm = 0;
+
+  // ---- activations for one micro-batch ----
+  struct LayerA {
+    bf16 *h_in, *n1, *qkv, *attn, *h_mid, *n2, *gu, *act;
+    float *rstd1, *rstd2, *lse;
+  };
+  std::vector<LayerA> la;
+  bf16 *h_final = nullptr, *nf = nullptr, *logits = nullptr;
+  float *rstdf = nullptr, *nll = nullptr;
+  int32_t *ids_dev = nullptr, *labels_dev = nullptr, *targets = nullptr;
+  size_t ids_cap = 0;
+  int32_t* pinned = nullptr;
+  size_t pinned_cap = 0;
+  bf16 *dh_a = nullptr, *dh_b = nullptr, *dn = nullptr, *dact = nullptr, *dgu = nullptr,
+       *dattn = nullptr, *dqkv = nullptr;
+  float *dq32 = nullptr, *delta = nullptr;
+  float* scal = nullptr;    // [0] loss, [1] gscale, [2] gnorm
+  double* sumsq = nullptr;
+  float* host_scal = nullptr;  // pinned [4]
+  float* hook_scal = nullptr;
+
+  // ---- DP ----
+  void* comm = nullptr;
+  int rank = 0, nranks = 1;
+  cudaEvent_t ev_grad = nullptr, ev_comm = nullptr;
+
+  template <typename T>
+  T* alloc(size_t n) {
+    void* p = nullptr;
+    const size_t bytes = ((n * sizeof(T) + 255) / 256) * 256;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      throw std::bad_alloc();
+    }
+    allocs.push_back(p);
+    dev_bytes += static_cast<int64_t>(bytes);
+    return static_cast<T*>(p);
+  }
+  void free_all() {
+    for (void* p : allocs) cudaFree(p);
+    allocs.clear();
+    dev_bytes = 0;
+  }
+};
+
+namespace {
+
+int qkv_dim(const b200w_arch& a) { return (a.num_heads + 2 * a.num_kv_heads) * a.head_dim; }
+
+// device scalar scratch for the per-kernel hooks (exists without a model)
+float* ctx_scal(b200w_ctx* c) {
+  if (!c->hook_scal) c->hook_scal = c->alloc<float>(8);
+  return c->hook_scal;
+}
+
+template <typename F>
+int guarded(b200w_ctx* ctx, F&& f) {
+  if (!ctx) return B200W_ERR_INVALID;
+  try {
+    B200W_CUDA(cudaSetDevice(ctx->device));
+    f();
+    return B200W_OK;
+  } catch (const NcclError& e) {
+    ctx->err = e.what();
+    return B200W_ERR_NCCL;
+  } catch (const std::bad_alloc&) {
+    ctx->err = "device memory exhausted";
+    return B200W_ERR_OOM;
+  } catch (const Error& e) {
+    ctx->err = e.what();
+    return ctx->err.rfind("check failed", 0) == 0 ? B200W_ERR_INVALID : B200W_ERR_CUDA;
+  } catch (const std::exception& e) {
+    ctx->err = e.what();
+    return B200W_ERR_INVALID;
+  }
+}
+
+void add_param(b200w_ctx* c, const std::string& name, int64_t rows, int64_t cols, bool is_norm,
+               size_t* off_out) {
+  Param p{name, rows, cols, c->n_elems, is_norm};
+  *off_out = c->n_elems;
+  c->index[name] = static_cast<int>(c->params.size());
+  c->params.push_back(p);
+  c->n_elems += static_cast<size_t>(rows) * cols;
+}
+
+void build_params(b200w_ctx* c) {
+  const b200w_arch& a = c->arch;
+  const int d = a.hidden_size, f = a.intermediate_size, L = a.num_layers;
+  const int qd = a.num_heads * a.head_dim, kd = a.num_kv_heads * a.head_dim;
+  c->lp.resize(L);
+  // atomically-accumulated gradients first, so one memset clears them
+  add_param(c, "model.embed_tokens.weight", a.vocab_size, d, false, &c->p_embed);
+  for (int l = 0; l < L; ++l) {
+    const std::string pre = "model.layers." + std::to_string(l) + ".";
+    add_param(c, pre + "input_layernorm.weight", 1, d, true, &c->lp[l].ln1);
+    add_param(c, pre + "post_attention_layernorm.weight", 1, d, true, &c->lp[l].ln2);
+  }
+  add_param(c, "model.norm.weight", 1, d, true, &c->p_norm);
+  c->n_zero_prefix = c->n_elems;
+  size_t dummy;
+  for (int l = 0; l < L; ++l) {
+    const std::string pre = "model.layers." + std::to_string(l) + ".";
+    // q, k, v rows are contiguous: together they are the fused [qkv_dim, d] projection
+    add_param(c, pre + "self_attn.q_proj.weight", qd, d, false, &c->lp[l].wqkv);
+    add_param(c, pre + "self_attn.k_proj.weight", kd, d, false, &dummy);
+    add_param(c, pre + "self_attn.v_proj.weight", kd, d, false, &dummy);
+    add_param(c, pre + "self_attn.o_proj.weight", d, qd, false, &c->lp[l].wo);
+    // gate, up contiguous: the fused [2f, d] projection
+    add_param(c, pre + "mlp.gate_proj.weight", f, d, false, &c->lp[l].wgu);
+    add_param(c, pre + "mlp.up_proj.weight", f, d, false, &dummy);
+    add_param(c, pre + "mlp.down_proj.weight", d, f, false, &c->lp[l].wd);
+  }
+  add_param(c, "lm_head.weight", a.vocab_size, d, false, &c->p_lm);
+}
+
+void alloc_activations(b200w_ctx* c) {
+  const b200w_arch& a = c->arch;
+  const size_t T = static_cast<size_t>(c->micro_batch) * a.max_seq_len;
+  const size_t d = a.hidden_size, f = a.intermediate_size, qd = a.num_heads * a.head_dim,
+               qkvd = qkv_dim(a), H = a.num_heads;
+  const int L = a.num_layers;
+  c->la.resize(L);
+  const int Lsave = c->training ? L : 1;  // forward-only: every layer reuses one set
+  for (int l = 0; l < L; ++l) {
+    if (l < Lsave) {
+      auto& x = c->la[l];
+      x.h_in = c->alloc<bf16>(T * d);
+      x.n1 = c->alloc<bf16>(T * d);
+      x.qkv = c->alloc<bf16>(T * qkvd);
+      x.attn = c->alloc<bf16>(T * qd);
+      x.h_mid = c->alloc<bf16>(T * d);
+      x.n2 = c->alloc<bf16>(T * d);
+      x.gu = c->alloc<bf16>(T * 2 * f);
+      x.act = c->alloc<bf16>(T * f);
+      x.rstd1 = c->alloc<float>(T);
+      x.rstd2 = c->alloc<float>(T);
+      x.lse = c->alloc<float>(H * T);
+    } else {
+      c->la[l] = c->la[0];
+    }
+  }
+  c->h_final = c->alloc<bf16>(T * d);
+  if (!c->training) {
+    // forward-only ping-pong: layer l reads h_in, writes the next layer's h_in
+    // (la[0].h_in and h_final alternate)
+  }
+  c->nf = c->alloc<bf16>(T * d);
+  c->rstdf = c->alloc<float>(T);
+  c->logits = c->alloc<bf16>(T * a.vocab_size);
+  c->nll = c->alloc<float>(T);
+  c->targets = c->alloc<int32_t>(T);
+  c->scal = c->alloc<float>(8);
+  c->sumsq = c->alloc<double>(1);
+  if (c->training) {
+    c->dh_a = c->alloc<bf16>(T * d);
+    c->dh_b = c->alloc<bf16>(T * d);
+    c->dn = c->alloc<bf16>(T * d);
+    c->dact = c->alloc<bf16>(T * f);
+    c->dgu = c->alloc<bf16>(T * 2 * f);
+    c->dattn = c->alloc<bf16>(T * qd);
+    c->dqkv = c->alloc<bf16>(T * qkvd);
+    c->dq32 = c->alloc<float>(T * qd);
+    c->delta = c->alloc<float>(H * T);
+  }
+  c->rope_tab = c->alloc<float2>(static_cast<size_t>(a.max_seq_len) * (a.head_dim / 2));
+  rope_table(c->rope_tab, a.max_seq_len, a.head_dim, a.rope_theta, c->stream);
+}
+
+// ---- forward of one micro-batch (ids already on device) -------------------------------------
+void forward_micro(b200w_ctx* c, const int32_t* ids, int nseq) {
+  const b200w_arch& a = c->arch;
+  const int S = a.max_seq_len, T = nseq * S, d = a.hidden_size, f = a.intermediate_size;
+  const int H = a.num_heads, Hkv = a.num_kv_heads, dh = a.head_dim;
+  const int qd = H * dh, kd = Hkv * dh, qkvd = qkv_dim(a);
+  const float scale = 1.f / sqrtf(static_cast<float>(dh));
+  cudaStream_t s = c->stream;
+  int64_t& n = c->launches;
+  const int L = a.num_layers;
+
+  bf16* h = c->la[0].h_in;
+  embed_fwd(ids, c->w + c->p_embed, h, T, d, a.vocab_size, s); ++n;
+  for (int l = 0; l < L; ++l) {
+    auto& x = c->la[l];
+    const auto& p = c->lp[l];
+    bf16* h_in = c->training ? x.h_in : h;
+    bf16* h_next = c->training ? (l + 1 < L ? c->la[l + 1].h_in : c->h_final)
+                               : (h == c->la[0].h_in ? c->h_final : c->la[0].h_in);
+    rmsnorm_fwd(h_in, c->w + p.ln1, x.n1, x.rstd1, T, d, a.rms_norm_eps, s); ++n;
+    gemm_bf16(x.n1, false, d, c->w + p.wqkv, false, d, x.qkv, nullptr, false, qkvd, T, qkvd, d, 0, s); ++n;
+    rope_apply(x.qkv, qkvd, c->rope_tab, T, S, H + Hkv, dh, false, s); ++n;
+    attention_fwd(x.qkv, qkvd, qd, qd + kd, x.attn, qd, x.lse, nseq, S, H, Hkv, scale, s); ++n;
+    gemm_bf16(x.attn, false, qd, c->w + p.wo, false, qd, x.h_mid, h_in, false, d, T, d, qd, 0, s); ++n;
+    rmsnorm_fwd(x.h_mid, c->w + p.ln2, x.n2, x.rstd2, T, d, a.rms_norm_eps, s); ++n;
+    gemm_bf16(x.n2, false, d, c->w + p.wgu, false, d, x.gu, nullptr, false, 2 * f, T, 2 * f, d, 0, s); ++n;
+    swiglu_fwd(x.gu, x.act, T, f, s); ++n;
+    gemm_bf16(x.act, false, f, c->w + p.wd, false, f, h_next, x.h_mid, false, d, T, d, f, 0, s); ++n;
+    h = h_next;
+  }
+  // in training mode h == h_final; in forward-only mode h is whichever buffer came last
+  rmsnorm_fwd(h, c->w + c->p_norm, c->nf, c->rstdf, T, d, a.rms_norm_eps, s); ++n;
+  gemm_bf16(c->nf, false, d, c->w + c->p_lm, false, d, c->logits, nullptr, false, a.vocab_size, T,
+            a.vocab_size, d, 0, s); ++n;
+  if (c->training && h != c->h_final) throw Error("internal: residual stream bookkeeping");
+}
+
+// loss + dlogits (in place)
+void loss_micro(b200w_ctx* c, const int32_t* labels, int nseq, float inv_n) {
+  const b200w_arch& a = c->arch;
+  const int S = a.max_seq_len, T = nseq * S;
+  cudaStream_t s = c->stream;
+  ce_shift_targets(labels, c->targets, T, S, s); ++c->launches;
+  ce_loss_fwd_bwd(c->logits, c->targets, c->nll, T, a.vocab_size, inv_n, s); ++c->launches;
+  reduce_sum_f32(c->nll, c->scal + 0, T, inv_n, s); ++c->launches;
+}
+
+void allreduce_range(b200w_ctx* c, size_t off, size_t count) {
+  B200W_CUDA(cudaEventRecord(c->ev_grad, c->stream));
+  B200W_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_grad, 0));
+  B200W_NCCL(nccl().AllReduce(c->g + off, c->g + off, count, kNcclFloat32, kNcclSum, c->comm,
+                              c->comm_stream));
+  ++c->launches;
+}
+
+// backward of one micro-batch. first: overwrite gradients instead of accumulating.
+// overlap_ar: launch the per-layer all-reduce as soon as a layer's gradients are final.
+void backward_micro(b200w_ctx* c, const int32_t* ids, int nseq, bool first, bool overlap_ar) {
+  const b200w_arch& a = c->arch;
+  const int S = a.max_seq_len, T = nseq * S, d = a.hidden_size, f = a.intermediate_size;
+  const int H = a.num_heads, Hkv = a.num_kv_heads, dh = a.head_dim, V = a.vocab_size;
+  const int qd = H * dh, kd = Hkv * dh, qkvd = qkv_dim(a);
+  const float scale = 1.f / sqrtf(static_cast<float>(dh));
+  cudaStream_t s = c->stream;
+  int64_t& n = c->launches;
+  const int L = a.num_layers;
+  float* g = c->g;
+  auto acc = [&](size_t off) -> const void* { return first ? nullptr : g + off; };
+
+  // lm_head: dnf = dlogits W ; dW += dlogits^T nf
+  gemm_bf16(c->logits, false, V, c->w + c->p_lm, true, d, c->dn, nullptr, false, d, T, d, V, 0, s); ++n;
+  gemm_bf16(c->logits, true, V, c->nf, true, d, g + c->p_lm, acc(c->p_lm), true, d, V, d, T, 0, s); ++n;
+  if (overlap_ar) allreduce_range(c, c->p_lm, static_cast<size_t>(V) * d);
+  bf16* dh_cur = c->dh_a;
+  bf16* dh_alt = c->dh_b;
+  rmsnorm_bwd(c->dn, c->h_final, c->w + c->p_norm, c->rstdf, nullptr, dh_cur, g + c->p_norm, T, d, s); ++n;
+
+  for (int l = L - 1; l >= 0; --l) {
+    auto& x = c->la[l];
+    const auto& p = c->lp[l];
+    const size_t o_q = p.wqkv, o_o = p.wo, o_gu = p.wgu, o_d = p.wd;
+    // h_next = h_mid + act Wd^T
+    gemm_bf16(dh_cur, false, d, c->w + o_d, true, f, c->dact, nullptr, false, f, T, f, d, 0, s); ++n;
+    gemm_bf16(dh_cur, true, d, x.act, true, f, g + o_d, acc(o_d), true, f, d, f, T, 0, s); ++n;
+    swiglu_bwd(c->dact, x.gu, c->dgu, T, f, s); ++n;
+    gemm_bf16(c->dgu, false, 2 * f, c->w + o_gu, true, d, c->dn, nullptr, false, d, T, d, 2 * f, 0, s); ++n;
+    gemm_bf16(c->dgu, true, 2 * f, x.n2, true, d, g + o_gu, acc(o_gu), true, d, 2 * f, d, T, 0, s); ++n;
+    // dh_mid = dh + rmsnorm_bwd(dn2)
+    rmsnorm_bwd(c->dn, x.h_mid, c->w + p.ln2, x.rstd2, dh_cur, dh_alt, g + p.ln2, T, d, s); ++n;
+    std::swap(dh_cur, dh_alt);
+    // h_mid = h_in + attn Wo^T
+    gemm_bf16(dh_cur, false, d, c->w + o_o, true, qd, c->dattn, nullptr, false, qd, T, qd, d, 0, s); ++n;
+    gemm_bf16(dh_cur, true, d, x.attn, true, qd, g + o_o, acc(o_o), true, qd, d, qd, T, 0, s); ++n;
+    B200W_CUDA(cudaMemsetAsync(c->dq32, 0, static_cast<size_t>(T) * qd * sizeof(float), s));
+    attention_bwd(x.qkv, qkvd, qd, qd + kd, x.attn, c->dattn, qd, x.lse, c->delta, c->dq32, c->dqkv,
+                  nseq, S, H, Hkv, scale, s); n += 2;
+    cast_f32_to_bf16_2d(c->dq32, c->dqkv, qkvd, T, qd, s); ++n;
+    rope_apply(c->dqkv, qkvd, c->rope_tab, T, S, H + Hkv, dh, true, s); ++n;
+    gemm_bf16(c->dqkv, false, qkvd, c->w + o_q, true, d, c->dn, nullptr, false, d, T, d, qkvd, 0, s); ++n;
+    gemm_bf16(c->dqkv, true, qkvd, x.n1, true, d, g + o_q, acc(o_q), true, d, qkvd, d, T, 0, s); ++n;
+    rmsnorm_bwd(c->dn, x.h_in, c->w + p.ln1, x.rstd1, dh_cur, dh_alt, g + p.ln1, T, d, s); ++n;
+    std::swap(dh_cur, dh_alt);
+    if (overlap_ar) {
+      // the layer's matrices are contiguous: [wqkv .. wd + d*f)
+      allreduce_range(c, o_q, (o_d + static_cast<size_t>(d) * f) - o_q);
+    }
+  }
+  embed_bwd(ids, dh_cur, g + c->p_embed, T, d, V, s); ++n;
+  if (overlap_ar) allreduce_range(c, 0, c->n_zero_prefix);
+}
+
+void ensure_ids(b200w_ctx* c, size_t n_tok) {
+  if (c->ids_cap < n_tok) {
+    c->ids_dev = c->alloc<int32_t>(n_tok);
+    c->labels_dev = c->alloc<int32_t>(n_tok);
+    c->ids_cap = n_tok;
+  }
+  if (c->pinned_cap < 2 * n_tok) {
+    if (c->pinned) cudaFreeHost(c->pinned);
+    B200W_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->pinned), 2 * n_tok * sizeof(int32_t)));
+    c->pinned_cap = 2 * n_tok;
+  }
+}
+
+// counts HF's num_items_in_batch: shifted labels != -100
+long count_valid(const int32_t* labels, int n_seqs, int S) {
+  long nvalid = 0;
+  for (int b = 0; b < n_seqs; ++b)
+    for (int t = 1; t < S; ++t) nvalid += labels[static_cast<size_t>(b) * S + t] != -100;
+  return nvalid;
+}
+
+void upload_batch(b200w_ctx* c, const int32_t* ids, const int32_t* labels, size_t n_tok) {
+  ensure_ids(c, n_tok);
+  memcpy(c->pinned, ids, n_tok * sizeof(int32_t));
+  memcpy(c->pinned + n_tok, labels, n_tok * sizeof(int32_t));
+  B200W_CUDA(cudaMemcpyAsync(c->ids_dev, c->pinned, n_tok * sizeof(int32_t), cudaMemcpyHostToDevice,
+                             c->stream));
+  B200W_CUDA(cudaMemcpyAsync(c->labels_dev, c->pinned + n_tok, n_tok * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, c->stream));
+}
+
+void fwd_bwd_all(b200w_ctx* c, const int32_t* ids, const int32_t* labels, int n_seqs,
+                 bool allow_overlap) {
+  const int S = c->arch.max_seq_len, mb = c->micro_batch;
+  B200W_CHECK(c->has_model && c->training, "model not initialised for training");
+  B200W_CHECK(n_seqs > 0 && n_seqs % mb == 0, "n_seqs must be a positive multiple of micro_batch");
+  const size_t n_tok = static_cast<size_t>(n_seqs) * S;
+  const long nvalid = count_valid(labels, n_seqs, S);
+  B200W_CHECK(nvalid > 0, "batch has no valid target token");
+  const float inv_n = 1.f / static_cast<float>(nvalid);
+  upload_batch(c, ids, labels, n_tok);
+  B200W_CUDA(cudaMemsetAsync(c->scal, 0, 8 * sizeof(float), c->stream));
+  B200W_CUDA(cudaMemsetAsync(c->g, 0, c->n_zero_prefix * sizeof(float), c->stream));
+  const int n_micro = n_seqs / mb;
+  for (int mi = 0; mi < n_micro; ++mi) {
+    const int32_t* mids = c->ids_dev + static_cast<size_t>(mi) * mb * S;
+    const int32_t* mlab = c->labels_dev + static_cast<size_t>(mi) * mb * S;
+    forward_micro(c, mids, mb);
+    loss_micro(c, mlab, mb, inv_n);
+    const bool ar = allow_overlap && c->comm && mi == n_micro - 1;
+    backward_micro(c, mids, mb, mi == 0, ar);
+  }
+  if (allow_overlap && c->comm) {
+    B200W_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
+    B200W_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+  }
+}
+
+}  // namespace
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+extern "C" {
+
+int b200w_abi_version(void) { return B200W_ABI_VERSION; }
+
+int b200w_create(int device, b200w_ctx** out) {
+  if (!out) return B200W_ERR_INVALID;
+  *out = nullptr;
+  try {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+      cudaGetLastError();
+      g_create_error = "no usable CUDA device " + std::to_string(device) +
+                       " (b200w has no CPU fallback): " + cudaGetErrorString(e);
+      return B200W_ERR_CUDA;
+    }
+    B200W_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B200W_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+      g_create_error = std::string("b200w is built for sm_100a only; device is ") + prop.name;
+      return B200W_ERR_CUDA;
+    }
+    auto c = std::make_unique<b200w_ctx>();
+    c->device = device;
+    B200W_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    B200W_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    B200W_CUDA(cudaEventCreateWithFlags(&c->ev_grad, cudaEventDisableTiming));
+    B200W_CUDA(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+    B200W_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->host_scal), 8 * sizeof(float)));
+    *out = c.release();
+    return B200W_OK;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return B200W_ERR_CUDA;
+  }
+}
+
+void b200w_destroy(b200w_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (ctx->comm) nccl().CommDestroy(ctx->comm);
+  ctx->free_all();
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->host_scal) cudaFreeHost(ctx->host_scal);
+  if (ctx->ev_grad) cudaEventDestroy(ctx->ev_grad);
+  if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  delete ctx;
+}
+
+const char* b200w_last_error(const b200w_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int b200w_sync(b200w_ctx* ctx) {
+  return guarded(ctx, [&] {
+    B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    B200W_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+  });
+}
+
+void b200w_default_hparams(b200w_hparams* hp) {
+  if (!hp) return;
+  hp->lr = 5e-5f; hp->beta1 = 0.9f; hp->beta2 = 0.999f; hp->eps = 1e-8f;
+  hp->weight_decay = 0.0f; hp->max_grad_norm = 1.0f;
+}
+
+int b200w_model_init(b200w_ctx* ctx, const b200w_arch* arch, const b200w_hparams* hp,
+                     int micro_batch, int training) {
+  return guarded(ctx, [&] {
+    B200W_CHECK(arch != nullptr, "arch is NULL");
+    B200W_CHECK(!ctx->has_model, "model already initialised");
+    B200W_CHECK(arch->head_dim == 128, "head_dim must be 128");
+    B200W_CHECK(arch->num_heads % arch->num_kv_heads == 0, "heads must be a multiple of kv heads");
+    B200W_CHECK(arch->hidden_size % 8 == 0 && arch->intermediate_size % 8 == 0 &&
+                    arch->vocab_size % 8 == 0,
+                "sizes must be multiples of 8");
+    B200W_CHECK(arch->max_seq_len % 128 == 0, "max_seq_len must be a multiple of 128");
+    B200W_CHECK(micro_batch >= 1, "micro_batch must be >= 1");
+    ctx->arch = *arch;
+    if (hp) ctx->hp = *hp; else b200w_default_hparams(&ctx->hp);
+    ctx->micro_batch = micro_batch;
+    ctx->training = training != 0;
+    build_params(ctx);
+    ctx->w = ctx->alloc<bf16>(ctx->n_elems);
+    if (ctx->training) {
+      ctx->master = ctx->alloc<float>(ctx->n_elems);
+      ctx->m = ctx->alloc<float>(ctx->n_elems);
+      ctx->v = ctx->alloc<float>(ctx->n_elems);
+      ctx->g = ctx->alloc<float>(ctx->n_elems);
+      B200W_CUDA(cudaMemsetAsync(ctx->m, 0, ctx->n_elems * sizeof(float), ctx->stream));
+      B200W_CUDA(cudaMemsetAsync(ctx->v, 0, ctx->n_elems * sizeof(float), ctx->stream));
+      B200W_CUDA(cudaMemsetAsync(ctx->g, 0, ctx->n_elems * sizeof(float), ctx->stream));
+    }
+    alloc_activations(ctx);
+    B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->has_model = true;
+    ctx->step = 0;
+  });
+}
+
+int b200w_param_count(b200w_ctx* ctx, int64_t* n_tensors, int64_t* n_elements) {
+  return guarded(ctx, [&] {
+    B200W_CHECK(ctx->has_model, "no model");
+    if (n_tensors) *n_tensors = static_cast<int64_t>(ctx->params.size());
+    if (n_elements) *n_elements = static_cast<int64_t>(ctx->n_elems);
+  });
+}
+
+int b200w_param_info(b200w_ctx* ctx, int64_t index, char* name, size_t name_cap, int64_t* rows,
+                     int64_t* cols) {
+  return guarded(ctx, [&] {
+    B200W_CHECK(ctx->has_model && index >= 0 && index < (int64_t)ctx->params.size(), "bad index");
+    const Param& p = ctx->params[index];
+    if (name && name_cap) {
+      strncpy(name, p.name.c_str(), name_cap - 1);
+      name[name_cap - 1] = 0;
+    }
+    if (rows) *rows = p.rows;
+    if (cols) *cols = p.cols;
+  });
+}
+
+static const Param& find_param(b200w_ctx* ctx, const char* name, int64_t n_elements) {
+  B200W_CHECK(ctx->has_model && name, "no model / name");
+  auto it = ctx->index.find(name);
+  if (it == ctx->index.end()) throw Error(std::string("check failed: unknown parameter ") + name);
+  const Param& p = ctx->params[it->second];
+  B200W_CHECK(n_elements == p.rows * p.cols, "element count does not match the parameter shape");
+  return p;
+}
+
+int b200w_load_tensor(b200w_ctx* ctx, const char* name, const void* host, b200w_dtype dtype,
+                      int64_t n_elements) {
+  return guarded(ctx, [&] {
+    const Param& p = find_param(ctx, name, n_elements);
+    B200W_CHECK(host && (dtype == B200W_BF16 || dtype == B200W_F32), "bad host buffer / dtype");
+    const size_t n = static_cast<size_t>(n_elements);
+    if (dtype == B200W_F32) {
+      float* tmp = ctx->training ? ctx->master + p.off : nullptr;
+      void* scratch = nullptr;
+      if (!tmp) { B200W_CUDA(cudaMalloc(&scratch, n * 4)); tmp = static_cast<float*>(scratch); }
+      B200W_CUDA(cudaMemcpyAsync(tmp, host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+      cast_f32_to_bf16(tmp, ctx->w + p.off, n, ctx->stream);
+      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (scratch) cudaFree(scratch);
+    } else {
+      B200W_CUDA(cudaMemcpyAsync(ctx->w + p.off, host, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+      if (ctx->training) cast_bf16_to_f32(ctx->w + p.off, ctx->master + p.off, n, ctx->stream);
+      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+  });
+}
+
+int b200w_read_tensor(b200w_ctx* ctx, const char* name, void* host, b200w_dtype dtype,
+                      int64_t n_elements) {
+  return guarded(ctx, [&] {
+    const Param& p = find_param(ctx, name, n_elements);
+    B200W_CHECK(host && (dtype == B200W_BF16 || dtype == B200W_F32), "bad host buffer / dtype");
+    const size_t n = static_cast<size_t>(n_elements);
+    B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (dtype == B200W_BF16) {
+      B200W_CUDA(cudaMemcpy(host, ctx->w + p.off, n * 2, cudaMemcpyDeviceToHost));
+    } else if (ctx->training) {
+      B200W_CUDA(cudaMemcpy(host, ctx->master + p.off, n * 4, cudaMemcpyDeviceToHost));
+    } else {
+      void* scratch = nullptr;
+      B200W_CUDA(cudaMalloc(&scratch, n * 4));
+      cast_bf16_to_f32(ctx->w + p.off, static_cast<float*>(scratch), n, ctx->stream);
+      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+      B200W_CUDA(cudaMemcpy(host, scratch, n * 4, cudaMemcpyDeviceToHost));
+      cudaFree(scratch);
+    }
+  });
+}
+
+int b200w_read_state(b200w_ctx* ctx, const char* name, int kind, float* host, int64_t n_elements) {
+  return guarded(ctx, [&] {
+    const Param& p = find_param(ctx, name, n_elements);
+    B200W_CHECK(ctx->training && host && kind >= 0 && kind <= 3, "bad kind / not training");
+    const float* src[4] = {ctx->master, ctx->g, ctx->m, ctx->v};
+    B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    B200W_CUDA(cudaMemcpy(host, src[kind] + p.off, static_cast<size_t>(n_elements) * 4,
+                          cudaMemcpyDeviceToHost));
+  });
+}
+
+int b200w_init_random(b200w_ctx* ctx, uint64_t seed, float std) {
+  return guarded(ctx, [&] {
+    B200W_CHECK(ctx->has_model, "no model");
+    for (const Param& p : ctx->params) {
+      const size_t n = static_cast<size_t>(p.rows) * p.cols;
+      float* mp = ctx->training ? ctx->master + p.off : nullptr;
+      if (p.is_norm)
+        fill_kernel<<<64, 256, 0, ctx->stream>>>(mp, ctx->w + p.off, n, 1.0f);
+      else
+        init_normal_kernel<<<sm_count() * 8, 256, 0, ctx->stream>>>(mp, ctx->w + p.off, n,
+                                                                    seed + p.off, std);
+    }
+    B200W_CUDA(cudaGetLastError());
+    B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int b200w_comm_unique_id(void* id128) {
+  if (!id128) return B200W_ERR_INVALID;
+  try {
+    int r = nccl().GetUniqueId(id128);
+    if (r != 0) { g_create_error = nccl().GetErrorString(r); return B200W_ERR_NCCL; }
+    return B200W_OK;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return B200W_ERR_NCCL;
+  }
+}
+
+int b200w_comm_init(b200w_ctx* ctx, int rank, int nranks, const void* id128) {
+  return guarded(ctx, [&] {
+    B200W_CHECK(id128 && nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / id");
+    B200W_CHECK(!ctx->comm, "communicator already initialised");
+    Uid uid;
+    memcpy(&uid, id128, sizeof(uid));
+    try {
+      B200W_NCCL(nccl().CommInitRank(&ctx->comm, nranks, uid, rank));
+    } catch (const Error& e) {
+      throw NcclError(e.what());
+    }
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+  });
+}
+
+int b200w_forward_backward(b200w_ctx* ctx, const int32_t* ids, const int32_t* labels, int n_seqs,
+                           float* loss_out) {
+  return guarded(ctx, [&] {
+    B200W_CHECK(ids && labels, "NULL batch");
+    fwd_bwd_all(ctx, ids, labels, n_seqs, /*allow_overlap=*/false);
+    B200W_CUDA(cudaMemcpyAsync(ctx->host_scal, ctx->scal, 4 * sizeof(float), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+    B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (loss_out) *loss_out = ctx->host_scal[0];
+  });
+}
+
+int b200w_train_step(b200w_ctx* ctx, const int32_t* ids, const int32_t* labels, int n_seqs, float lr,
+                     float* loss_out, float* gnorm_out) {
+  return guarded(ctx, [&] {
+    B200W_CHECK(ids && labels, "NULL batch");
+    fwd_bwd_all(ctx, ids, labels, n_seqs, /*allow_overlap=*/true);
+    cudaStream_t s = ctx->stream;
+    B200W_CUDA(cudaMemsetAsync(ctx->sumsq, 0, sizeof(double), s));
+    grad_sumsq(ctx->g, ctx->n_elems, ctx->sumsq, s); ++ctx->launches;
+    // all-reduce summed the ranks: DDP averages, so fold 1/nranks into the gradient scale
+    clip_coef(ctx->sumsq, ctx->hp.max_grad_norm, 1.f / static_cast<float>(ctx->nranks),
+              ctx->scal + 1, ctx->scal + 2, s); ++ctx->launches;
+    ctx->step += 1;
+    adamw_step(ctx->master, ctx->m, ctx->v, ctx->g, ctx->w, ctx->n_elems, lr, ctx->hp.beta1,
+               ctx->hp.beta2, ctx->hp.eps, ctx->hp.weight_decay, ctx->step, ctx->scal + 1, s);
+    ++ctx->launches;
+    B200W_CUDA(cudaMemcpyAsync(ctx->host_scal, ctx->scal, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B200W_CUDA(cudaStreamSynchronize(s));
+    if (loss_out) *loss_out = ctx->host_scal[0];
+    if (gnorm_out) *gnorm_out = ctx->host_scal[2];
+  });
+}
+
+int b200w_forward(b200w_ctx* ctx, const int32_t* ids, const int32_t* labels, int n_seqs,
+                  float* logits_out, float* nll_out, float* loss_out) {
+  return guarded(ctx, [&] {
+    B200W_CHECK(ctx->has_model && ids, "no model / NULL ids");
+    B200W_CHECK(n_seqs >= 1 && n_seqs <= ctx->micro_batch, "n_seqs must be <= micro_batch");
+    const int S = ctx->arch.max_seq_len, V = ctx->arch.vocab_size;
+    const size_t T = static_cast<size_t>(n_seqs) * S;
+    std::vector<int32_t> dummy;
+    if (!labels) { dummy.assign(T, -100); }
+    upload_batch(ctx, ids, labels ? labels : dummy.data(), T);
+    forward_micro(ctx, ctx->ids_dev, n_seqs);
+    if (logits_out) {
+      void* scratch = nullptr;
+      B200W_CUDA(cudaMalloc(&scratch, T * V * 4));
+      cast_bf16_to_f32(ctx->logits, static_cast<float*>(scratch), T * V, ctx->stream);
+      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+      B200W_CUDA(cudaMemcpy(logits_out, scratch, T * V * 4, cudaMemcpyDeviceToHost));
+      cudaFree(scratch);
+    }
+    if (labels && (nll_out || loss_out)) {
+      const long nvalid = count_valid(labels, n_seqs, S);
+      const float inv_n = nvalid > 0 ? 1.f / static_cast<float>(nvalid) : 0.f;
+      B200W_CUDA(cudaMemsetAsync(ctx->scal, 0, 8 * sizeof(float), ctx->stream));
+      loss_micro(ctx, ctx->labels_dev, n_seqs, inv_n);
+      B200W_CUDA(cudaMemcpyAsync(ctx->host_scal, ctx->scal, 4 * sizeof(float),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (nll_out) B200W_CUDA(cudaMemcpy(nll_out, ctx->nll, T * 4, cudaMemcpyDeviceToHost));
+      if (loss_out) *loss_out = ctx->host_scal[0];
+    }
+    B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int64_t b200w_launch_count(const b200w_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t b200w_device_bytes(const b200w_ctx* ctx) { return ctx ? ctx->dev_bytes : 0; }
+
+// ---- per-kernel hooks ---------------------------------------------------------------------
+#define HOOK(body)                                              \
+  return guarded(ctx, [&] {                                     \
+    body;                                                       \
+    ++ctx->launches;                                            \
+    B200W_CUDA(cudaStreamSynchronize(ctx->stream));             \
+  })
+
+int b200w_op_gemm(b200w_ctx* ctx, const void* A, int a_mn, int lda, const void* B, int b_mn, int ldb,
+                  void* D, const void* C, int out_f32, int ldd, int M, int N, int K, int block_n) {
+  HOOK(gemm_bf16(A, a_mn != 0, lda, B, b_mn != 0, ldb, D, C, out_f32 != 0, ldd, M, N, K, block_n,
+                 ctx->stream));
+}
+int b200w_op_embed_fwd(b200w_ctx* ctx, const int32_t* ids, const void* table, void* out, int T, int d,
+                       int vocab) {
+  HOOK(embed_fwd(ids, table, out, T, d, vocab, ctx->stream));
+}
+int b200w_op_embed_bwd(b200w_ctx* ctx, const int32_t* ids, const void* dout, float* dtable, int T,
+                       int d, int vocab) {
+  HOOK(embed_bwd(ids, dout, dtable, T, d, vocab, ctx->stream));
+}
+int b200w_op_rmsnorm_fwd(b200w_ctx* ctx, const void* x, const void* w, void* y, float* rstd, int T,
+                         int d, float eps) {
+  HOOK(rmsnorm_fwd(x, w, y, rstd, T, d, eps, ctx->stream));
+}
+int b200w_op_rmsnorm_bwd(b200w_ctx* ctx, const void* dy, const void* x, const void* w,
+                         const float* rstd, const void* dresid, void* dx, float* dw, int T, int d) {
+  HOOK(rmsnorm_bwd(dy, x, w, rstd, dresid, dx, dw, T, d, ctx->stream));
+}
+int b200w_op_rope(b200w_ctx* ctx, void* buf, int ld, int T, int S, int nheads, int dh, float theta,
+                  int inverse) {
+  return guarded(ctx, [&] {
+    float2* tab = nullptr;
+    B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&tab), static_cast<size_t>(S) * (dh / 2) * sizeof(float2)));
+    try {
+      rope_table(tab, S, dh, theta, ctx->stream);
+      rope_apply(buf, ld, tab, T, S, nheads, dh, inverse != 0, ctx->stream);
+      ++ctx->launches;
+      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    } catch (...) { cudaFree(tab); throw; }
+    cudaFree(tab);
+  });
+}
+int b200w_op_swiglu_fwd(b200w_ctx* ctx, const void* gu, void* h, int T, int f) {
+  HOOK(swiglu_fwd(gu, h, T, f, ctx->stream));
+}
+int b200w_op_swiglu_bwd(b200w_ctx* ctx, const void* dh, const void* gu, void* dgu, int T, int f) {
+  HOOK(swiglu_bwd(dh, gu, dgu, T, f, ctx->stream));
+}
+int b200w_op_ce(b200w_ctx* ctx, void* logits, const int32_t* labels, float* nll, int T, int S, int V,
+                float inv_n) {
+  return guarded(ctx, [&] {
+    int32_t* tg = nullptr;
+    B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&tg), static_cast<size_t>(T) * 4));
+    try {
+      ce_shift_targets(labels, tg, T, S, ctx->stream);
+      ce_loss_fwd_bwd(logits, tg, nll, T, V, inv_n, ctx->stream);
+      ctx->launches += 2;
+      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    } catch (...) { cudaFree(tg); throw; }
+    cudaFree(tg);
+  });
+}
+int b200w_op_attention_fwd(b200w_ctx* ctx, const void* qkv, int ld_qkv, int k_off, int v_off,
+                           void* out, int ld_out, float* lse2, int B, int S, int H, int Hkv,
+                           float scale) {
+  HOOK(attention_fwd(qkv, ld_qkv, k_off, v_off, out, ld_out, lse2, B, S, H, Hkv, scale, ctx->stream));
+}
+int b200w_op_attention_bwd(b200w_ctx* ctx, const void* qkv, int ld_qkv, int k_off, int v_off,
+                           const void* out, const void* dout, int ld_out, const float* lse2,
+                           float* delta, float* dq32, void* dqkv, int B, int S, int H, int Hkv,
+                           float scale) {
+  HOOK(attention_bwd(qkv, ld_qkv, k_off, v_off, out, dout, ld_out, lse2, delta, dq32, dqkv, B, S, H,
+                     Hkv, scale, ctx->stream));
+}
+int b200w_op_adamw(b200w_ctx* ctx, float* master, float* m, float* v, const float* g, void* w_bf16,
+                   int64_t n, float lr, float beta1, float beta2, float eps, float wd, int step,
+                   float gscale) {
+  return guarded(ctx, [&] {
+    B200W_CUDA(cudaMemcpyAsync(ctx_scal(ctx), &gscale, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    adamw_step(master, m, v, g, w_bf16, static_cast<size_t>(n), lr, beta1, beta2, eps, wd, step,
+               ctx_scal(ctx), ctx->stream);
+    ++ctx->launches;
+    B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+int b200w_op_grad_norm(b200w_ctx* ctx, const float* g, int64_t n, float* norm_out) {
+  return guarded(ctx, [&] {
+    double* ss = nullptr;
+    B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss), sizeof(double)));
+    B200W_CUDA(cudaMemsetAsync(ss, 0, sizeof(double), ctx->stream));
+    grad_sumsq(g, static_cast<size_t>(n), ss, ctx->stream);
+    ++ctx->launches;
+    double h = 0;
+    B200W_CUDA(cudaMemcpyAsync(&h, ss, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ss);
+    if (norm_out) *norm_out = static_cast<float>(sqrt(h));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,326 @@
+// bf16 x bf16 -> fp32-accumulate GEMM on tcgen05 tensor cores (sm_100a), TMA-fed.
+//
+//   D[M,N] = op(A)[M,K] * op(B)[N,K]^T  (+ C[M,N])
+//
+// This one kernel family covers the three contractions of the fine-tune step
+// (SURVEY.md §2b `gemm_bf16`, oracle: torch.nn.Linear fwd / autograd):
+//   forward   Y  = X  W^T   : A = X  [T,in]  K-major,  B = W  [out,in] K-major
+//   dgrad     dX = dY W     : A = dY [T,out] K-major,  B = W  [out,in] read MN-major (K = out)
+//   wgrad     dW = dY^T X   : A = dY [T,out] read MN-major, B = X [T,in] read MN-major (K = T)
+// so no operand is ever transposed through HBM.
+//
+// Structure: persistent CTAs (one per SM), 128 x BLOCK_N output tiles, K in 64-element
+// (= one 128-byte swizzle atom) blocks; warp 0 = TMA producer, warp 1 = tcgen05.mma issuer
+// (single elected thread), warp 2 = TMEM allocator, warps 4..7 = epilogue. Two TMEM accumulator
+// stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace b200w {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B atom row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <typename OutT>
+__device__ __forceinline__ void store_chunk32(OutT* drow, const OutT* crow, const float (&v)[32],
+                                              int ncols_valid, bool has_c);
+
+template <>
+__device__ __forceinline__ void store_chunk32<__nv_bfloat16>(__nv_bfloat16* drow,
+                                                             const __nv_bfloat16* crow,
+                                                             const float (&v)[32], int ncols_valid,
+                                                             bool has_c) {
+  if (ncols_valid >= 32) {
+    uint4 out[4];
+    uint32_t* o = reinterpret_cast<uint32_t*>(out);
+    if (has_c) {
+      const uint4* c4 = reinterpret_cast<const uint4*>(crow);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 c = c4[i];
+        const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = unpack_bf16x2(cw[j]);
+          o[i * 4 + j] = pack_bf16x2(v[i * 8 + j * 2] + f.x, v[i * 8 + j * 2 + 1] + f.y);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    }
+    uint4* d4 = reinterpret_cast<uint4*>(drow);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d4[i] = out[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i < ncols_valid) {
+        float x = v[i];
+        if (has_c) x += __bfloat162float(crow[i]);
+        drow[i] = __float2bfloat16_rn(x);
+      }
+    }
+  }
+}
+
+template <>
+__device__ __forceinline__ void store_chunk32<float>(float* drow, const float* crow,
+                                                     const float (&v)[32], int ncols_valid,
+                                                     bool has_c) {
+  if (ncols_valid >= 32) {
+    float4* d4 = reinterpret_cast<float4*>(drow);
+    const float4* c4 = reinterpret_cast<const float4*>(crow);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      if (has_c) {
+        float4 c = c4[i];
+        o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+      }
+      d4[i] = o;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < ncols_valid) drow[i] = v[i] + (has_c ? crow[i] : 0.f);
+  }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 OutT* D, const OutT* C, int M, int N, int K, int ldd) {
+  using cfg = Cfg<BLOCK_N>;
+  constexpr int STAGES = cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready for the epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % num_m) * BLOCK_M;  // M fastest: concurrent CTAs share B tiles via L2
+        const int n0 = (tile / num_m) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * cfg::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], cfg::STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box [128 rows(m), 64 k]
+          } else {
+            // global is [K rows, M cols]; one box = [64 k-rows, 64 m] = one MN atom column
+#pragma unroll
+            for (int a = 0; a < BLOCK_M / 64; ++a)
+              tma_load_2d(sa + a * (BLOCK_K * 128), &tmA, &full_bar[stage], m0 + a * 64, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);  // box [BLOCK_N rows(n), 64 k]
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_N / 64; ++a)
+              tma_load_2d(sb + a * (BLOCK_K * 128), &tmB, &full_bar[stage], n0 + a * 64, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      // K-major: next UMMA_K = +32 B inside the atom row. MN-major: next 16 K-rows = +2048 B.
+      constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+      constexpr uint32_t b_kstep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+      constexpr uint32_t a_lbo = A_MN ? (BLOCK_K * 128) : 16;
+      constexpr uint32_t b_lbo = B_MN ? (BLOCK_K * 128) : 16;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * cfg::STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t da = make_smem_desc(sa, a_lbo, 1024);
+          const uint64_t db = make_smem_desc(sb, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            tc_mma_bf16(tmem_d, desc_advance(da, k * a_kstep), desc_advance(db, k * b_kstep), idesc,
+                        (kb | k) != 0);
+          tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % num_m) * BLOCK_M;
+      const int n0 = (tile / num_m) * BLOCK_N;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      __syncwarp();
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      OutT* drow = D + static_cast<size_t>(row) * ldd + n0;
+      const OutT* crow = C ? C + static_cast<size_t>(row) * ldd + n0 : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_addr(tmem_base, q * 32, acc * BLOCK_N + c * 32), r);
+        tmem_ld_wait();
+        const int ncols = N - (n0 + c * 32);
+        if (row_ok && ncols > 0) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          store_chunk32<OutT>(drow + c * 32, crow ? crow + c * 32 : nullptr, v, ncols,
+                              crow != nullptr);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, cfg::TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT>
+void launch(const void* A, const void* B, OutT* D, const OutT* C, int M, int N, int K, int lda,
+            int ldb, int ldd, cudaStream_t stream) {
+  using cfg = Cfg<BLOCK_N>;
+  // A: K-major => global [M rows, K cols]; MN-major => global [K rows, M cols]
+  CUtensorMap tmA = A_MN ? make_tmap_bf16_2d(A, K, M, lda, BLOCK_K, 64)
+                         : make_tmap_bf16_2d(A, M, K, lda, BLOCK_M, BLOCK_K);
+  CUtensorMap tmB = B_MN ? make_tmap_bf16_2d(B, K, N, ldb, BLOCK_K, 64)
+                         : make_tmap_bf16_2d(B, N, K, ldb, BLOCK_N, BLOCK_K);
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OutT>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    B200W_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, cfg::SMEM_BYTES, stream>>>(tmA, tmB, D, C, M, N, K, ldd);
+  B200W_CUDA(cudaGetLastError());
+}
+
+template <int BLOCK_N, typename OutT>
+void dispatch_major(bool a_mn, bool b_mn, const void* A, const void* B, OutT* D, const OutT* C,
+                    int M, int N, int K, int lda, int ldb, int ldd, cudaStream_t s) {
+  if (!a_mn && !b_mn) launch<BLOCK_N, false, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
+  else if (!a_mn && b_mn) launch<BLOCK_N, false, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
+  else if (a_mn && b_mn) launch<BLOCK_N, true, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
+  else launch<BLOCK_N, true, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
+}
+
+}  // namespace
+
+// Public launcher (C++). out_fp32: D/C are float, else bf16. C may alias D (accumulate in place).
+// block_n: 0 = auto, else 128 or 256.
+void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int ldb, void* D,
+               const void* C, bool out_fp32, int ldd, int M, int N, int K, int block_n,
+               cudaStream_t stream) {
+  B200W_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
+  B200W_CHECK(lda % 8 == 0 && ldb % 8 == 0, "TMA needs 16-byte aligned row strides");
+  B200W_CHECK(ldd % (out_fp32 ? 4 : 8) == 0, "output rows must be 16-byte aligned");
+  B200W_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(D) & 15) == 0,
+              "operands must be 16-byte aligned");
+  if (block_n == 0) {
+    // 256-wide tiles halve A re-reads; fall back to 128 when that would leave SMs idle.
+    const long tiles256 = static_cast<long>((M + 127) / 128) * ((N + 255) / 256);
+    block_n = (N >= 256 && tiles256 >= sm_count()) ? 256 : 128;
+  }
+  B200W_CHECK(block_n == 128 || block_n == 256, "block_n must be 128 or 256");
+  if (out_fp32) {
+    if (block_n == 256)
+      dispatch_major<256, float>(a_mn, b_mn, A, B, static_cast<float*>(D),
+                                 static_cast<const float*>(C), M, N, K, lda, ldb, ldd, stream);
+    else
+      dispatch_major<128, float>(a_mn, b_mn, A, B, static_cast<float*>(D),
+                                 static_cast<const float*>(C), M, N, K, lda, ldb, ldd, stream);
+  } else {
+    if (block_n == 256)
+      dispatch_major<256, __nv_bfloat16>(a_mn, b_mn, A, B, static_cast<__nv_bfloat16*>(D),
+                                         static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb,
+                                         ldd, stream);
+    else
+      dispatch_major<128, __nv_bfloat16>(a_mn, b_mn, A, B, static_cast<__nv_bfloat16*>(D),
+                                         static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb,
+                                         ldd, stream);
+  }
+}
+
+}  // namespace b200w

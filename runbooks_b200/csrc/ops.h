@@ -1,0 +1,78 @@
+// C++ launchers for every kernel on the fine-tune hot path.
+// All pointers are DEVICE pointers; bf16 unless said otherwise; everything is enqueued on `s`.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200w {
+
+// ---- gemm.cu -------------------------------------------------------------------------------
+// D[M,N] = opA[M,K] * opB[N,K]^T (+ C). a_mn/b_mn: operand stored with the M/N index contiguous
+// (i.e. global memory is [K, M] / [K, N] row-major) instead of K contiguous.
+void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int ldb, void* D,
+               const void* C, bool out_fp32, int ldd, int M, int N, int K, int block_n,
+               cudaStream_t s);
+
+// ---- attention.cu --------------------------------------------------------------------------
+// Causal self-attention over packed sequences. qkv: [T, ld_qkv] with q at column 0, k at
+// column k_off, v at column v_off (head h at +h*128); T = B*S; head_dim fixed at 128.
+// out: [T, ld_out] (head h at column h*128); lse2: [H, T] fp32 (log2-domain logsumexp).
+void attention_fwd(const void* qkv, int ld_qkv, int k_off, int v_off, void* out, int ld_out,
+                   float* lse2, int B, int S, int H, int Hkv, float scale, cudaStream_t s);
+// dqkv gets dk, dv (bf16) at k_off / v_off; dq is accumulated in fp32 into dq32 [T, H*128]
+// (must be zero on entry). delta: [H, T] fp32 scratch.
+void attention_bwd(const void* qkv, int ld_qkv, int k_off, int v_off, const void* out,
+                   const void* dout, int ld_out, const float* lse2, float* delta, float* dq32,
+                   void* dqkv, int B, int S, int H, int Hkv, float scale, cudaStream_t s);
+
+// ---- ops.cu --------------------------------------------------------------------------------
+void embed_fwd(const int32_t* ids, const void* table, void* out, int T, int d, int vocab,
+               cudaStream_t s);
+void embed_bwd(const int32_t* ids, const void* dout, float* dtable, int T, int d, int vocab,
+               cudaStream_t s);
+
+void rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int T, int d, float eps,
+                 cudaStream_t s);
+// dx = (dresid ? dresid : 0) + d(rmsnorm)/dx ; dw (fp32) += sum_t dy * xhat
+void rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd,
+                 const void* dresid, void* dx, float* dw, int T, int d, cudaStream_t s);
+
+// cos/sin table for rotate_half RoPE: tab[pos*(dh/2) + i] = {cos, sin}(pos * theta^(-2i/dh))
+void rope_table(float2* tab, int S, int dh, float theta, cudaStream_t s);
+// in-place rotation of `nheads` consecutive heads starting at column 0 of buf [T, ld];
+// position = t % S. inverse=true applies the transpose (backward pass).
+void rope_apply(void* buf, int ld, const float2* tab, int T, int S, int nheads, int dh,
+                bool inverse, cudaStream_t s);
+
+// gu: [T, 2f] (gate | up); h: [T, f] = silu(gate) * up
+void swiglu_fwd(const void* gu, void* h, int T, int f, cudaStream_t s);
+void swiglu_bwd(const void* dh, const void* gu, void* dgu, int T, int f, cudaStream_t s);
+
+// targets[t] = labels[t+1] within each length-S sequence, -100 at the last position.
+void ce_shift_targets(const int32_t* labels, int32_t* targets, int T, int S, cudaStream_t s);
+// logits [T,V] bf16 -> per-token nll (fp32, 0 where target == -100); logits are overwritten IN
+// PLACE by dlogits = (softmax - onehot) * inv_n (bf16).
+void ce_loss_fwd_bwd(void* logits, const int32_t* targets, float* nll, int T, int V, float inv_n,
+                     cudaStream_t s);
+// out[0] += scale * sum(x[0..n)) ; deterministic single-block reduction
+void reduce_sum_f32(const float* x, float* out, int n, float scale, cudaStream_t s);
+
+// sumsq[0] += sum(g^2) in double
+void grad_sumsq(const float* g, size_t n, double* sumsq, cudaStream_t s);
+// torch.optim.AdamW step over a flat parameter range; g is pre-multiplied by *gscale (device
+// scalar: the clip coefficient); writes the bf16 compute copy.
+void adamw_step(float* master, float* m, float* v, const float* g, void* w_bf16, size_t n,
+                float lr, float beta1, float beta2, float eps, float wd, int step,
+                const float* gscale, cudaStream_t s);
+// gscale[0] = min(1, max_norm / (sqrt(sumsq * div^2) + 1e-6)) * div ; gnorm_out[0] = sqrt(sumsq)*div
+void clip_coef(const double* sumsq, float max_norm, float div, float* gscale, float* gnorm_out,
+               cudaStream_t s);
+
+void attn_bwd_delta(const void* out, const void* dout, int ld, float* delta, int T, int H,
+                    cudaStream_t s);
+// dst[t, c] (bf16, row stride ld_dst) = src[t, c] (fp32, dense [T, ncols])
+void cast_f32_to_bf16_2d(const float* src, void* dst, int ld_dst, int T, int ncols, cudaStream_t s);
+void cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t s);
+void cast_bf16_to_f32(const void* src, float* dst, size_t n, cudaStream_t s);
+
+}  // namespace b200w

@@ -1,0 +1,93 @@
+"""tcgen05 GEMM vs an fp32 torch reference of the same op (bf16 inputs, fp32 accumulate).
+Tolerances: fp32 output 2e-5 relative Frobenius (accumulation order only); bf16 output 3e-3
+(one round-to-nearest bf16 per element: rms 2^-9/sqrt(3) = 1.1e-3)."""
+import pytest
+import torch
+
+from util import call, dev, rel_err
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(256, 512, 256), (384, 768, 192), (200, 328, 136), (128, 128, 64), (1024, 256, 2048)]
+
+
+def _operands(M, N, K, a_mn, b_mn, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(M, K, generator=g).bfloat16()
+    B = torch.randn(N, K, generator=g).bfloat16()
+    ref = A.float() @ B.float().T
+    Ad = dev(A.T if a_mn else A)  # MN-major operands are stored [K, M] / [K, N]
+    Bd = dev(B.T if b_mn else B)
+    return Ad, Bd, ref
+
+
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_f32_out(engine, M, N, K, a_mn, b_mn, block_n):
+    Ad, Bd, ref = _operands(M, N, K, a_mn, b_mn)
+    D = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
+    call(engine, "b200w_op_gemm", Ad, a_mn, Ad.shape[1], Bd, b_mn, Bd.shape[1], D, None, 1, N, M, N, K,
+         block_n)
+    err = rel_err(D, ref)
+    print(f"gemm f32 M{M} N{N} K{K} a_mn{a_mn} b_mn{b_mn} bn{block_n}: rel_err {err:.3e}")
+    assert err < 2e-5
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
+def test_gemm_bf16_out_with_residual(engine, a_mn, b_mn):
+    M, N, K = 384, 512, 320
+    Ad, Bd, ref = _operands(M, N, K, a_mn, b_mn, seed=1)
+    Cres = torch.randn(M, N, generator=torch.Generator().manual_seed(2)).bfloat16()
+    D = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    call(engine, "b200w_op_gemm", Ad, a_mn, Ad.shape[1], Bd, b_mn, Bd.shape[1], D, dev(Cres), 0, N, M, N,
+         K, 0)
+    err = rel_err(D.float(), ref + Cres.float())
+    print(f"gemm bf16+residual a_mn{a_mn} b_mn{b_mn}: rel_err {err:.3e}")
+    assert err < 3e-3
+
+
+def test_gemm_f32_accumulate_in_place(engine):
+    """wgrad pattern: D (fp32) += A^T B over two micro-batches, both operands MN-major."""
+    M, N, K = 256, 384, 512
+    Ad, Bd, ref = _operands(M, N, K, 1, 1, seed=3)
+    D = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    call(engine, "b200w_op_gemm", Ad, 1, M, Bd, 1, N, D, None, 1, N, M, N, K, 0)
+    call(engine, "b200w_op_gemm", Ad, 1, M, Bd, 1, N, D, D, 1, N, M, N, K, 0)
+    err = rel_err(D, 2 * ref)
+    print(f"gemm f32 accumulate: rel_err {err:.3e}")
+    assert err < 2e-5
+
+
+def test_gemm_strided_output(engine):
+    """ldd > N: writes a column slice of a wider row-major buffer and leaves the rest alone."""
+    M, N, K = 256, 256, 128
+    Ad, Bd, ref = _operands(M, N, K, 0, 0, seed=4)
+    D = torch.full((M, 3 * N), 7.0, device="cuda", dtype=torch.bfloat16)
+    call(engine, "b200w_op_gemm", Ad, 0, K, Bd, 0, K, D[:, N:], None, 0, 3 * N, M, N, K, 0)
+    assert rel_err(D[:, N:2 * N].float(), ref) < 3e-3
+    assert bool((D[:, :N] == 7).all()) and bool((D[:, 2 * N:] == 7).all())
+
+
+def test_gemm_llama_shapes(engine):
+    """One forward, one dgrad and one wgrad GEMM at Llama-2-7B layer width, T = 1024."""
+    T, d = 1024, 4096
+    for (M, N, K, a_mn, b_mn) in [(T, 3 * d, d, 0, 0), (T, d, 3 * d, 0, 1), (d, d, T, 1, 1)]:
+        Ad, Bd, _ = _operands(M, N, K, a_mn, b_mn, seed=5)
+        A32 = (Ad.T if a_mn else Ad).float()
+        B32 = (Bd.T if b_mn else Bd).float()
+        ref = A32 @ B32.T
+        D = torch.empty(M, N, device="cuda", dtype=torch.float32)
+        call(engine, "b200w_op_gemm", Ad, a_mn, Ad.shape[1], Bd, b_mn, Bd.shape[1], D, None, 1, N, M, N,
+             K, 0)
+        err = rel_err(D, ref)
+        print(f"gemm llama M{M} N{N} K{K}: rel_err {err:.3e}")
+        assert err < 2e-5
+
+
+def test_gemm_rejects_bad_arguments(engine):
+    from runbooks_b200._lib import B200WError
+    A = torch.zeros(128, 60, device="cuda", dtype=torch.bfloat16)  # lda not a multiple of 8
+    D = torch.zeros(128, 128, device="cuda", dtype=torch.float32)
+    with pytest.raises(B200WError):
+        call(engine, "b200w_op_gemm", A, 0, 60, A, 0, 60, D, None, 1, 128, 128, 128, 60, 0)

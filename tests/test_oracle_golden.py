@@ -1,0 +1,115 @@
+"""Pins the oracle restatement (oracle/llama_oracle.py) against numbers produced by the real
+HuggingFace LlamaForCausalLM + torch.optim.AdamW path (tests/golden/, made by
+oracle/make_golden.py). CPU only. fp32 vs fp32, so the bar is 2e-5 relative (reassociation)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import llama_oracle as O
+
+CASES = ["llama_tiny_mha", "llama_tiny_gqa"]
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _load(case):
+    fx = np.load(f"tests/golden/{case}.npz")
+    v = [int(x) for x in fx["arch"]]
+    eps, theta = (float(x) for x in fx["arch_f"])
+    return fx, O.Arch(*v, rms_norm_eps=eps, rope_theta=theta), int(fx["batch"][1])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_two_steps_match_hf(case):
+    fx, a, seed = _load(case)
+    params = O.seeded_params(a, seed)
+    r1 = O.train_step(params, fx["ids"], fx["labels"], a, lr=5e-5, step=1)
+    assert abs(r1["loss"] - float(fx["loss"])) < 2e-5 * float(fx["loss"])
+    assert abs(r1["gnorm"] - float(fx["gnorm"])) < 2e-5 * float(fx["gnorm"])
+    assert rel(r1["logits"], fx["logits"]) < 2e-5
+    for k in params:
+        assert rel(r1["grads"][k].reshape(-1)[::61], fx["grad/" + k]) < 1e-4, k
+    r2 = O.train_step(r1["params"], fx["ids2"], fx["labels2"], a, lr=2.5e-5,
+                      state=dict(m=r1["m"], v=r1["v"]), step=2)
+    assert abs(r2["loss"] - float(fx["loss2"])) < 2e-5 * float(fx["loss2"])
+    assert abs(r2["gnorm"] - float(fx["gnorm2"])) < 2e-5 * float(fx["gnorm2"])
+    for k in params:
+        w0 = params[k].reshape(-1)[::61]
+        assert rel(r2["params"][k].reshape(-1)[::61], fx["param2/" + k]) < 1e-6, k
+        # the update itself (w2 - w0), which is ~1e-3 of the weights
+        assert rel(r2["params"][k].reshape(-1)[::61] - w0, fx["param2/" + k] - w0) < 2e-3, k
+
+
+def test_ops_match_hf_modules():
+    fx = np.load("tests/golden/llama_ops.npz")
+    y = O.rmsnorm(torch.tensor(fx["rms_x"]), torch.tensor(fx["rms_w"]), 1e-5)
+    assert rel(y, fx["rms_y"]) < 1e-6
+    pos = fx["rope_pos"]
+    cos, sin = O.rope_cos_sin(512, 128, 10000.0)
+    assert rel(cos[pos], fx["rope_cos"]) < 1e-6 and rel(sin[pos], fx["rope_sin"]) < 1e-6
+    qe = O.apply_rope(torch.tensor(fx["rope_q"]), cos[pos], sin[pos])
+    ke = O.apply_rope(torch.tensor(fx["rope_k"]), cos[pos], sin[pos])
+    assert rel(qe, fx["rope_qe"]) < 1e-6 and rel(ke, fx["rope_ke"]) < 1e-6
+    o = O.causal_attention(*(torch.tensor(fx[n]) for n in ("att_q", "att_k", "att_v")))
+    assert rel(o, fx["att_o"]) < 1e-5
+    loss, nll = O.causal_lm_loss(torch.tensor(fx["ce_logits"]), torch.tensor(fx["ce_labels"]))
+    assert abs(float(loss) - float(fx["ce_loss"])) < 1e-6 * float(fx["ce_loss"])
+    assert abs(float(nll.sum()) / 40 - float(fx["ce_loss_items40"])) < 1e-6 * float(fx["ce_loss_items40"])
+
+
+def test_loss_edge_cases():
+    """all-ignored rows contribute nothing; the final position never has a target."""
+    lg = torch.randn(2, 8, 16, generator=torch.Generator().manual_seed(0))
+    lb = torch.randint(0, 16, (2, 8), generator=torch.Generator().manual_seed(1))
+    lb[1] = -100
+    loss, nll = O.causal_lm_loss(lg, lb)
+    assert float(nll.view(2, 8)[1].abs().sum()) == 0 and float(nll.view(2, 8)[0, -1]) == 0
+    ref = torch.nn.functional.cross_entropy(lg[0, :-1], lb[0, 1:])
+    assert abs(float(loss) - float(ref)) < 1e-6
+
+
+def test_adamw_restatement_matches_torch():
+    g = torch.Generator().manual_seed(3)
+    p0 = torch.randn(1000, generator=g) * 0.02
+    tp = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([tp], lr=5e-5, weight_decay=0.01)
+    p, m, v = p0.clone(), torch.zeros(1000), torch.zeros(1000)
+    for step in range(1, 5):
+        gr = torch.randn(1000, generator=g) * 1e-2
+        tp.grad = gr.clone()
+        opt.step()
+        p, m, v = O.adamw_update(p, gr, m, v, step, 5e-5, wd=0.01)
+    assert rel(p - p0, tp.detach() - p0) < 1e-5
+
+
+def test_linear_schedule_matches_transformers():
+    from transformers import get_linear_schedule_with_warmup
+    tp = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([tp], lr=5e-5)
+    sch = get_linear_schedule_with_warmup(opt, 0, 10)
+    for i in range(10):
+        assert abs(opt.param_groups[0]["lr"] - O.linear_lr(i, 10)) < 1e-12
+        opt.step()
+        sch.step()
+
+
+def test_bf16_round_matches_torch():
+    x = np.random.default_rng(0).standard_normal(10000).astype(np.float32) * 3
+    assert np.array_equal(O.bf16_round(x), torch.tensor(x).bfloat16().float().numpy())
+
+
+def test_hf_bf16_distance():
+    """How far an HF model run in bf16 sits from its own fp32 run on the golden inputs — the
+    yardstick for the logits tolerance in tests/test_engine.py (documented, loose bound)."""
+    fx, a, seed = _load("llama_tiny_mha")
+    params = {k: torch.tensor(v) for k, v in O.seeded_params(a, seed).items()}
+    ids = torch.tensor(fx["ids"])
+    with torch.no_grad():
+        l32 = O.forward(params, ids, a)
+        l16 = O.forward({k: v.bfloat16() for k, v in params.items()}, ids, a).float()
+    d = rel(l16, l32)
+    print(f"bf16-vs-fp32 logits distance of the torch path itself: {d:.3e}")
+    assert 1e-4 < d < 3e-2

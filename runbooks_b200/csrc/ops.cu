@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(CE_THREADS)
 ce_loss_kernel(bf16* logits, const int32_t* __restrict__ targets, float* __restrict__ nll, int V,
                float inv_n) {
   __shared__ float red_m[32], red_s[32];
+  __shared__ float tgt_logit;  // stashed in pass 1: pass 2 overwrites the row in place
   const size_t row = blockIdx.x;
   bf16* lr = logits + row * V;
   const int tgt = targets[row];
@@ -278,6 +279,9 @@ ce_loss_kernel(bf16* logits, const int32_t* __restrict__ targets, float* __restr
   for (int i = threadIdx.x; i < nvec; i += CE_THREADS) {
     float f[8];
     load8(lr + i * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (i * 8 + j == tgt) tgt_logit = f[j];
     float mx = f[0];
 #pragma unroll
     for (int j = 1; j < 8; ++j) mx = fmaxf(mx, f[j]);
@@ -290,6 +294,7 @@ ce_loss_kernel(bf16* logits, const int32_t* __restrict__ targets, float* __restr
   }
   for (int i = nvec * 8 + threadIdx.x; i < V; i += CE_THREADS) {  // tail (V % 8)
     const float x = __bfloat162float(lr[i]);
+    if (i == tgt) tgt_logit = x;
     const float nm = fmaxf(m, x);
     s = s * __expf(m - nm) + __expf(x - nm);
     m = nm;
@@ -306,7 +311,7 @@ ce_loss_kernel(bf16* logits, const int32_t* __restrict__ targets, float* __restr
   const float gs = warp_sum(bm == -INFINITY ? 0.f : bs * __expf(bm - gm));
   const float lse = gm + logf(gs);
   const bool valid = tgt >= 0;
-  if (threadIdx.x == 0) nll[row] = valid ? (lse - __bfloat162float(lr[tgt])) : 0.f;
+  if (threadIdx.x == 0) nll[row] = valid ? (lse - tgt_logit) : 0.f;
   // pass 2: dlogits in place
   const float k = valid ? inv_n : 0.f;
   for (int i = threadIdx.x; i < nvec; i += CE_THREADS) {

@@ -113,6 +113,19 @@ B200W_API int b200w_comm_init(b200w_ctx* ctx, int rank, int nranks, const void* 
  * HOST floats (this rank's mean loss; global pre-clip gradient norm). */
 B200W_API int b200w_train_step(b200w_ctx* ctx, const int32_t* ids, const int32_t* labels, int n_seqs, float lr,
                      float* loss_out, float* gnorm_out);
+/* The same step with the batch already resident in HBM (DEVICE int32 pointers) and no host
+ * synchronisation: nothing crosses PCIe. n_valid = number of non-ignored shifted labels (what
+ * b200w_train_step counts on the host). Read loss / grad-norm later with b200w_read_scalars. */
+B200W_API int b200w_train_step_resident(b200w_ctx* ctx, const int32_t* ids_dev, const int32_t* labels_dev,
+                              int n_seqs, int64_t n_valid, float lr);
+B200W_API int b200w_read_scalars(b200w_ctx* ctx, float* loss_out, float* gnorm_out);
+/* CUDA-event timer on the stream the library launches on (torch.cuda.Event cannot see it). */
+B200W_API int b200w_timer_start(b200w_ctx* ctx);
+B200W_API int b200w_timer_stop(b200w_ctx* ctx, float* ms_out);
+/* Bracket every GEMM launch with CUDA events; read back summed device time, algorithmic FLOPs
+ * (2*M*N*K per launch) and launch count since profiling was enabled. */
+B200W_API int b200w_profile_gemm(b200w_ctx* ctx, int enable);
+B200W_API int b200w_profile_read(b200w_ctx* ctx, double* ms_out, double* flops_out, int64_t* launches_out);
 /* Forward + loss + backward only (no optimiser step): fills gradients for inspection. */
 B200W_API int b200w_forward_backward(b200w_ctx* ctx, const int32_t* ids, const int32_t* labels, int n_seqs,
                            float* loss_out);

@@ -53,6 +53,12 @@ PROTOTYPES = {
     "b200w_comm_unique_id": (C.c_int, [vp]),
     "b200w_comm_init": (C.c_int, [c_ctx, C.c_int, C.c_int, vp]),
     "b200w_train_step": (C.c_int, [c_ctx, vp, vp, C.c_int, C.c_float, f32p, f32p]),
+    "b200w_train_step_resident": (C.c_int, [c_ctx, vp, vp, C.c_int, C.c_int64, C.c_float]),
+    "b200w_read_scalars": (C.c_int, [c_ctx, f32p, f32p]),
+    "b200w_timer_start": (C.c_int, [c_ctx]),
+    "b200w_timer_stop": (C.c_int, [c_ctx, f32p]),
+    "b200w_profile_gemm": (C.c_int, [c_ctx, C.c_int]),
+    "b200w_profile_read": (C.c_int, [c_ctx, C.POINTER(C.c_double), C.POINTER(C.c_double), i64p]),
     "b200w_forward_backward": (C.c_int, [c_ctx, vp, vp, C.c_int, f32p]),
     "b200w_forward": (C.c_int, [c_ctx, vp, vp, C.c_int, vp, vp, f32p]),
     "b200w_launch_count": (C.c_int64, [c_ctx]),

@@ -145,6 +145,13 @@ struct b200w_ctx {
   float* host_scal = nullptr;  // pinned [4]
   float* hook_scal = nullptr;
 
+  // ---- timing / profiling (bench.py) ----
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  bool prof_gemm = false;
+  std::vector<cudaEvent_t> prof_events;  // pairs
+  size_t prof_used = 0;
+  double prof_flops = 0;
+
   // ---- DP ----
   void* comm = nullptr;
   int rank = 0, nranks = 1;
@@ -294,6 +301,29 @@ void alloc_activations(b200w_ctx* c) {
   rope_table(c->rope_tab, a.max_seq_len, a.head_dim, a.rope_theta, c->stream);
 }
 
+// GEMM launch with optional CUDA-event bracketing (bench.py's roofline leg)
+void egemm(b200w_ctx* c, const void* A, bool a_mn, int lda, const void* B, bool b_mn, int ldb, void* D,
+           const void* C, bool out_fp32, int ldd, int M, int N, int K) {
+  cudaStream_t s = c->stream;
+  if (c->prof_gemm) {
+    if (c->prof_used + 2 > c->prof_events.size()) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEvent_t e;
+        B200W_CUDA(cudaEventCreate(&e));
+        c->prof_events.push_back(e);
+      }
+    }
+    B200W_CUDA(cudaEventRecord(c->prof_events[c->prof_used], s));
+  }
+  gemm_bf16(A, a_mn, lda, B, b_mn, ldb, D, C, out_fp32, ldd, M, N, K, 0, s);
+  ++c->launches;
+  if (c->prof_gemm) {
+    B200W_CUDA(cudaEventRecord(c->prof_events[c->prof_used + 1], s));
+    c->prof_used += 2;
+    c->prof_flops += 2.0 * M * N * static_cast<double>(K);
+  }
+}
+
 // ---- forward of one micro-batch (ids already on device) -------------------------------------
 void forward_micro(b200w_ctx* c, const int32_t* ids, int nseq) {
   const b200w_arch& a = c->arch;
@@ -314,20 +344,20 @@ void forward_micro(b200w_ctx* c, const int32_t* ids, int nseq) {
     bf16* h_next = c->training ? (l + 1 < L ? c->la[l + 1].h_in : c->h_final)
                                : (h == c->la[0].h_in ? c->h_final : c->la[0].h_in);
     rmsnorm_fwd(h_in, c->w + p.ln1, x.n1, x.rstd1, T, d, a.rms_norm_eps, s); ++n;
-    gemm_bf16(x.n1, false, d, c->w + p.wqkv, false, d, x.qkv, nullptr, false, qkvd, T, qkvd, d, 0, s); ++n;
+    egemm(c, x.n1, false, d, c->w + p.wqkv, false, d, x.qkv, nullptr, false, qkvd, T, qkvd, d);
     rope_apply(x.qkv, qkvd, c->rope_tab, T, S, H + Hkv, dh, false, s); ++n;
     attention_fwd(x.qkv, qkvd, qd, qd + kd, x.attn, qd, x.lse, nseq, S, H, Hkv, scale, s); ++n;
-    gemm_bf16(x.attn, false, qd, c->w + p.wo, false, qd, x.h_mid, h_in, false, d, T, d, qd, 0, s); ++n;
+    egemm(c, x.attn, false, qd, c->w + p.wo, false, qd, x.h_mid, h_in, false, d, T, d, qd);
     rmsnorm_fwd(x.h_mid, c->w + p.ln2, x.n2, x.rstd2, T, d, a.rms_norm_eps, s); ++n;
-    gemm_bf16(x.n2, false, d, c->w + p.wgu, false, d, x.gu, nullptr, false, 2 * f, T, 2 * f, d, 0, s); ++n;
+    egemm(c, x.n2, false, d, c->w + p.wgu, false, d, x.gu, nullptr, false, 2 * f, T, 2 * f, d);
     swiglu_fwd(x.gu, x.act, T, f, s); ++n;
-    gemm_bf16(x.act, false, f, c->w + p.wd, false, f, h_next, x.h_mid, false, d, T, d, f, 0, s); ++n;
+    egemm(c, x.act, false, f, c->w + p.wd, false, f, h_next, x.h_mid, false, d, T, d, f);
     h = h_next;
   }
   // in training mode h == h_final; in forward-only mode h is whichever buffer came last
   rmsnorm_fwd(h, c->w + c->p_norm, c->nf, c->rstdf, T, d, a.rms_norm_eps, s); ++n;
-  gemm_bf16(c->nf, false, d, c->w + c->p_lm, false, d, c->logits, nullptr, false, a.vocab_size, T,
-            a.vocab_size, d, 0, s); ++n;
+  egemm(c, c->nf, false, d, c->w + c->p_lm, false, d, c->logits, nullptr, false, a.vocab_size, T,
+            a.vocab_size, d);
   if (c->training && h != c->h_final) throw Error("internal: residual stream bookkeeping");
 }
 
@@ -364,8 +394,8 @@ void backward_micro(b200w_ctx* c, const int32_t* ids, int nseq, bool first, bool
   auto acc = [&](size_t off) -> const void* { return first ? nullptr : g + off; };
 
   // lm_head: dnf = dlogits W ; dW += dlogits^T nf
-  gemm_bf16(c->logits, false, V, c->w + c->p_lm, true, d, c->dn, nullptr, false, d, T, d, V, 0, s); ++n;
-  gemm_bf16(c->logits, true, V, c->nf, true, d, g + c->p_lm, acc(c->p_lm), true, d, V, d, T, 0, s); ++n;
+  egemm(c, c->logits, false, V, c->w + c->p_lm, true, d, c->dn, nullptr, false, d, T, d, V);
+  egemm(c, c->logits, true, V, c->nf, true, d, g + c->p_lm, acc(c->p_lm), true, d, V, d, T);
   if (overlap_ar) allreduce_range(c, c->p_lm, static_cast<size_t>(V) * d);
   bf16* dh_cur = c->dh_a;
   bf16* dh_alt = c->dh_b;
@@ -376,24 +406,24 @@ void backward_micro(b200w_ctx* c, const int32_t* ids, int nseq, bool first, bool
     const auto& p = c->lp[l];
     const size_t o_q = p.wqkv, o_o = p.wo, o_gu = p.wgu, o_d = p.wd;
     // h_next = h_mid + act Wd^T
-    gemm_bf16(dh_cur, false, d, c->w + o_d, true, f, c->dact, nullptr, false, f, T, f, d, 0, s); ++n;
-    gemm_bf16(dh_cur, true, d, x.act, true, f, g + o_d, acc(o_d), true, f, d, f, T, 0, s); ++n;
+    egemm(c, dh_cur, false, d, c->w + o_d, true, f, c->dact, nullptr, false, f, T, f, d);
+    egemm(c, dh_cur, true, d, x.act, true, f, g + o_d, acc(o_d), true, f, d, f, T);
     swiglu_bwd(c->dact, x.gu, c->dgu, T, f, s); ++n;
-    gemm_bf16(c->dgu, false, 2 * f, c->w + o_gu, true, d, c->dn, nullptr, false, d, T, d, 2 * f, 0, s); ++n;
-    gemm_bf16(c->dgu, true, 2 * f, x.n2, true, d, g + o_gu, acc(o_gu), true, d, 2 * f, d, T, 0, s); ++n;
+    egemm(c, c->dgu, false, 2 * f, c->w + o_gu, true, d, c->dn, nullptr, false, d, T, d, 2 * f);
+    egemm(c, c->dgu, true, 2 * f, x.n2, true, d, g + o_gu, acc(o_gu), true, d, 2 * f, d, T);
     // dh_mid = dh + rmsnorm_bwd(dn2)
     rmsnorm_bwd(c->dn, x.h_mid, c->w + p.ln2, x.rstd2, dh_cur, dh_alt, g + p.ln2, T, d, s); ++n;
     std::swap(dh_cur, dh_alt);
     // h_mid = h_in + attn Wo^T
-    gemm_bf16(dh_cur, false, d, c->w + o_o, true, qd, c->dattn, nullptr, false, qd, T, qd, d, 0, s); ++n;
-    gemm_bf16(dh_cur, true, d, x.attn, true, qd, g + o_o, acc(o_o), true, qd, d, qd, T, 0, s); ++n;
+    egemm(c, dh_cur, false, d, c->w + o_o, true, qd, c->dattn, nullptr, false, qd, T, qd, d);
+    egemm(c, dh_cur, true, d, x.attn, true, qd, g + o_o, acc(o_o), true, qd, d, qd, T);
     B200W_CUDA(cudaMemsetAsync(c->dq32, 0, static_cast<size_t>(T) * qd * sizeof(float), s));
     attention_bwd(x.qkv, qkvd, qd, qd + kd, x.attn, c->dattn, qd, x.lse, c->delta, c->dq32, c->dqkv,
                   nseq, S, H, Hkv, scale, s); n += 2;
     cast_f32_to_bf16_2d(c->dq32, c->dqkv, qkvd, T, qd, s); ++n;
     rope_apply(c->dqkv, qkvd, c->rope_tab, T, S, H + Hkv, dh, true, s); ++n;
-    gemm_bf16(c->dqkv, false, qkvd, c->w + o_q, true, d, c->dn, nullptr, false, d, T, d, qkvd, 0, s); ++n;
-    gemm_bf16(c->dqkv, true, qkvd, x.n1, true, d, g + o_q, acc(o_q), true, d, qkvd, d, T, 0, s); ++n;
+    egemm(c, c->dqkv, false, qkvd, c->w + o_q, true, d, c->dn, nullptr, false, d, T, d, qkvd);
+    egemm(c, c->dqkv, true, qkvd, x.n1, true, d, g + o_q, acc(o_q), true, d, qkvd, d, T);
     rmsnorm_bwd(c->dn, x.h_in, c->w + p.ln1, x.rstd1, dh_cur, dh_alt, g + p.ln1, T, d, s); ++n;
     std::swap(dh_cur, dh_alt);
     if (overlap_ar) {
@@ -436,22 +466,20 @@ void upload_batch(b200w_ctx* c, const int32_t* ids, const int32_t* labels, size_
                              cudaMemcpyHostToDevice, c->stream));
 }
 
-void fwd_bwd_all(b200w_ctx* c, const int32_t* ids, const int32_t* labels, int n_seqs,
-                 bool allow_overlap) {
+// forward + loss + backward over a batch that is already on the device
+void fwd_bwd_device(b200w_ctx* c, const int32_t* ids_dev, const int32_t* labels_dev, int n_seqs,
+                    long nvalid, bool allow_overlap) {
   const int S = c->arch.max_seq_len, mb = c->micro_batch;
   B200W_CHECK(c->has_model && c->training, "model not initialised for training");
   B200W_CHECK(n_seqs > 0 && n_seqs % mb == 0, "n_seqs must be a positive multiple of micro_batch");
-  const size_t n_tok = static_cast<size_t>(n_seqs) * S;
-  const long nvalid = count_valid(labels, n_seqs, S);
   B200W_CHECK(nvalid > 0, "batch has no valid target token");
   const float inv_n = 1.f / static_cast<float>(nvalid);
-  upload_batch(c, ids, labels, n_tok);
   B200W_CUDA(cudaMemsetAsync(c->scal, 0, 8 * sizeof(float), c->stream));
   B200W_CUDA(cudaMemsetAsync(c->g, 0, c->n_zero_prefix * sizeof(float), c->stream));
   const int n_micro = n_seqs / mb;
   for (int mi = 0; mi < n_micro; ++mi) {
-    const int32_t* mids = c->ids_dev + static_cast<size_t>(mi) * mb * S;
-    const int32_t* mlab = c->labels_dev + static_cast<size_t>(mi) * mb * S;
+    const int32_t* mids = ids_dev + static_cast<size_t>(mi) * mb * S;
+    const int32_t* mlab = labels_dev + static_cast<size_t>(mi) * mb * S;
     forward_micro(c, mids, mb);
     loss_micro(c, mlab, mb, inv_n);
     const bool ar = allow_overlap && c->comm && mi == n_micro - 1;
@@ -461,6 +489,30 @@ void fwd_bwd_all(b200w_ctx* c, const int32_t* ids, const int32_t* labels, int n_
     B200W_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
     B200W_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
   }
+}
+
+void fwd_bwd_all(b200w_ctx* c, const int32_t* ids, const int32_t* labels, int n_seqs,
+                 bool allow_overlap) {
+  const int S = c->arch.max_seq_len;
+  B200W_CHECK(c->has_model && c->training, "model not initialised for training");
+  B200W_CHECK(n_seqs > 0, "empty batch");
+  const long nvalid = count_valid(labels, n_seqs, S);
+  upload_batch(c, ids, labels, static_cast<size_t>(n_seqs) * S);
+  fwd_bwd_device(c, c->ids_dev, c->labels_dev, n_seqs, nvalid, allow_overlap);
+}
+
+// all-reduce is complete on c->stream; global-norm clip + AdamW over the flat parameter space
+void optimizer_step(b200w_ctx* c, float lr) {
+  cudaStream_t s = c->stream;
+  B200W_CUDA(cudaMemsetAsync(c->sumsq, 0, sizeof(double), s));
+  grad_sumsq(c->g, c->n_elems, c->sumsq, s); ++c->launches;
+  // the all-reduce summed the ranks: DDP averages, so fold 1/nranks into the gradient scale
+  clip_coef(c->sumsq, c->hp.max_grad_norm, 1.f / static_cast<float>(c->nranks), c->scal + 1,
+            c->scal + 2, s); ++c->launches;
+  c->step += 1;
+  adamw_step(c->master, c->m, c->v, c->g, c->w, c->n_elems, lr, c->hp.beta1, c->hp.beta2, c->hp.eps,
+             c->hp.weight_decay, c->step, c->scal + 1, s);
+  ++c->launches;
 }
 
 }  // namespace
@@ -516,6 +568,9 @@ void b200w_destroy(b200w_ctx* ctx) {
   if (ctx->host_scal) cudaFreeHost(ctx->host_scal);
   if (ctx->ev_grad) cudaEventDestroy(ctx->ev_grad);
   if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
+  if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+  if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   delete ctx;
@@ -720,20 +775,74 @@ int b200w_train_step(b200w_ctx* ctx, const int32_t* ids, const int32_t* labels, 
   return guarded(ctx, [&] {
     B200W_CHECK(ids && labels, "NULL batch");
     fwd_bwd_all(ctx, ids, labels, n_seqs, /*allow_overlap=*/true);
+    optimizer_step(ctx, lr);
     cudaStream_t s = ctx->stream;
-    B200W_CUDA(cudaMemsetAsync(ctx->sumsq, 0, sizeof(double), s));
-    grad_sumsq(ctx->g, ctx->n_elems, ctx->sumsq, s); ++ctx->launches;
-    // all-reduce summed the ranks: DDP averages, so fold 1/nranks into the gradient scale
-    clip_coef(ctx->sumsq, ctx->hp.max_grad_norm, 1.f / static_cast<float>(ctx->nranks),
-              ctx->scal + 1, ctx->scal + 2, s); ++ctx->launches;
-    ctx->step += 1;
-    adamw_step(ctx->master, ctx->m, ctx->v, ctx->g, ctx->w, ctx->n_elems, lr, ctx->hp.beta1,
-               ctx->hp.beta2, ctx->hp.eps, ctx->hp.weight_decay, ctx->step, ctx->scal + 1, s);
-    ++ctx->launches;
     B200W_CUDA(cudaMemcpyAsync(ctx->host_scal, ctx->scal, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
     B200W_CUDA(cudaStreamSynchronize(s));
     if (loss_out) *loss_out = ctx->host_scal[0];
     if (gnorm_out) *gnorm_out = ctx->host_scal[2];
+  });
+}
+
+int b200w_train_step_resident(b200w_ctx* ctx, const int32_t* ids_dev, const int32_t* labels_dev,
+                              int n_seqs, int64_t n_valid, float lr) {
+  return guarded(ctx, [&] {
+    B200W_CHECK(ids_dev && labels_dev, "NULL batch");
+    fwd_bwd_device(ctx, ids_dev, labels_dev, n_seqs, static_cast<long>(n_valid), /*allow_overlap=*/true);
+    optimizer_step(ctx, lr);
+  });
+}
+
+int b200w_read_scalars(b200w_ctx* ctx, float* loss_out, float* gnorm_out) {
+  return guarded(ctx, [&] {
+    B200W_CHECK(ctx->has_model, "no model");
+    B200W_CUDA(cudaMemcpyAsync(ctx->host_scal, ctx->scal, 4 * sizeof(float), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+    B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (loss_out) *loss_out = ctx->host_scal[0];
+    if (gnorm_out) *gnorm_out = ctx->host_scal[2];
+  });
+}
+
+int b200w_timer_start(b200w_ctx* ctx) {
+  return guarded(ctx, [&] {
+    if (!ctx->ev_t0) {
+      B200W_CUDA(cudaEventCreate(&ctx->ev_t0));
+      B200W_CUDA(cudaEventCreate(&ctx->ev_t1));
+    }
+    B200W_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+  });
+}
+
+int b200w_timer_stop(b200w_ctx* ctx, float* ms_out) {
+  return guarded(ctx, [&] {
+    B200W_CHECK(ctx->ev_t0 != nullptr && ms_out, "timer not started");
+    // everything the step put on the comm stream has already been joined into ctx->stream
+    B200W_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
+    B200W_CUDA(cudaEventSynchronize(ctx->ev_t1));
+    B200W_CUDA(cudaEventElapsedTime(ms_out, ctx->ev_t0, ctx->ev_t1));
+  });
+}
+
+int b200w_profile_gemm(b200w_ctx* ctx, int enable) {
+  return guarded(ctx, [&] {
+    ctx->prof_gemm = enable != 0;
+    if (enable) { ctx->prof_used = 0; ctx->prof_flops = 0; }
+  });
+}
+
+int b200w_profile_read(b200w_ctx* ctx, double* ms_out, double* flops_out, int64_t* launches_out) {
+  return guarded(ctx, [&] {
+    B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    double ms = 0;
+    for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+      float t = 0;
+      B200W_CUDA(cudaEventElapsedTime(&t, ctx->prof_events[i], ctx->prof_events[i + 1]));
+      ms += t;
+    }
+    if (ms_out) *ms_out = ms;
+    if (flops_out) *flops_out = ctx->prof_flops;
+    if (launches_out) *launches_out = static_cast<int64_t>(ctx->prof_used / 2);
   });
 }
 

@@ -186,6 +186,33 @@ class Engine:
                                                ids.shape[0], lr, C.byref(loss), C.byref(gn)))
         return loss.value, gn.value
 
+    def train_step_resident(self, ids_dev_ptr: int, labels_dev_ptr: int, n_seqs: int, n_valid: int,
+                            lr: float = 5e-5):
+        """The same step on a batch already in HBM (raw device addresses); no host sync."""
+        self._check(self._lib.b200w_train_step_resident(self._h, ids_dev_ptr, labels_dev_ptr, n_seqs,
+                                                        n_valid, lr))
+
+    def read_scalars(self) -> Tuple[float, float]:
+        loss, gn = C.c_float(), C.c_float()
+        self._check(self._lib.b200w_read_scalars(self._h, C.byref(loss), C.byref(gn)))
+        return loss.value, gn.value
+
+    def timer_start(self):
+        self._check(self._lib.b200w_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.b200w_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def profile_gemm(self, enable: bool):
+        self._check(self._lib.b200w_profile_gemm(self._h, 1 if enable else 0))
+
+    def profile_read(self) -> Tuple[float, float, int]:
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        self._check(self._lib.b200w_profile_read(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
+        return ms.value, fl.value, n.value
+
     def forward_backward(self, ids, labels) -> float:
         ids, labels = _as_i32(ids), _as_i32(labels)
         loss = C.c_float()

@@ -1,0 +1,149 @@
+"""Host side of the container contract (docs/container-contract.md; params_reconciler.go:28-68):
+params.json parsing incl. string-typed numbers and PARAM_* env, prompt templating, packing,
+LR schedule, HF-format checkpoint round trip. CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from runbooks_b200 import contract
+
+
+def test_params_defaults_when_file_is_empty_object(tmp_path):
+    p = tmp_path / "params.json"
+    p.write_text("{}")          # what the controller writes when spec.params is empty
+    tp = contract.load_params(str(p), environ={})
+    assert tp.num_train_epochs == 3.0 and tp.learning_rate == 5e-5 and tp.save_steps == 500
+    assert tp.per_device_train_batch_size == 8 and tp.max_grad_norm == 1.0 and tp.weight_decay == 0.0
+
+
+def test_params_int_or_string_and_aliases(tmp_path):
+    p = tmp_path / "params.json"
+    # json.MarshalIndent of map[string]intstr.IntOrString: numbers may arrive as strings
+    p.write_text(json.dumps({"num_train_epochs": 1, "save_steps": "5", "epochs": "2",
+                             "learning_rate": "1e-4", "prompt_template": "Q: {prompt}\nA: {completion}",
+                             "something_else": "kept"}, indent=2))
+    tp = contract.load_params(str(p), environ={"PARAM_SAVE_STEPS": "7", "UNRELATED": "x"})
+    assert tp.num_train_epochs == 2.0          # alias from examples/facebook-opt-125m
+    assert tp.save_steps == 7                  # PARAM_* env overrides the file
+    assert tp.learning_rate == 1e-4
+    assert tp.extra == {"something_else": "kept"}
+
+
+def test_params_errors(tmp_path):
+    p = tmp_path / "params.json"
+    p.write_text("[1,2]")
+    with pytest.raises(ValueError):
+        contract.load_params(str(p), environ={})
+    p.write_text(json.dumps({"save_steps": "often"}))
+    with pytest.raises(ValueError):
+        contract.load_params(str(p), environ={})
+    # a missing file behaves like {}
+    assert contract.load_params(str(tmp_path / "nope.json"), environ={}).save_steps == 500
+
+
+def test_linear_schedule_matches_transformers():
+    from transformers import get_linear_schedule_with_warmup
+    for warm in (0, 3):
+        tp = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.AdamW([tp], lr=5e-5)
+        sch = get_linear_schedule_with_warmup(opt, warm, 12)
+        for i in range(12):
+            assert abs(opt.param_groups[0]["lr"] - contract.linear_lr(i, 12, 5e-5, warm)) < 1e-12
+            opt.step()
+            sch.step()
+
+
+def test_render_and_records(tmp_path):
+    d = tmp_path / "data"
+    d.mkdir()
+    (d / "a.jsonl").write_text('{"prompt": "p1", "completion": "c1"}\n\n{"prompt": "p2", "completion": "c2"}\n')
+    (d / "b.json").write_text(json.dumps([{"text": "plain"}]))
+    recs = list(contract.iter_records(str(d)))
+    assert len(recs) == 3
+    tpl = "## Instruction\n{prompt}\n## Response:\n{completion}"
+    assert contract.render(recs[0], tpl) == "## Instruction\np1\n## Response:\nc1"
+    assert contract.render({"text": "plain"}, tpl) == "plain"
+    with pytest.raises(FileNotFoundError):
+        list(contract.iter_records(str(tmp_path / "empty")))
+
+
+def test_packing():
+    docs = [[5, 6, 7], [8], list(range(10, 20))]
+    ids, labels = contract.pack_sequences(docs, 8, bos_id=1, eos_id=2)
+    stream = [1, 5, 6, 7, 2, 1, 8, 2, 1] + list(range(10, 20)) + [2]
+    assert ids.shape == (3, 8) and ids.dtype == np.int32
+    flat = ids.reshape(-1)
+    assert list(flat[: len(stream)]) == stream
+    assert (flat[len(stream):] == 2).all()                       # tail padded with eos
+    assert (labels.reshape(-1)[: len(stream)] == flat[: len(stream)]).all()
+    assert (labels.reshape(-1)[len(stream):] == -100).all()      # and ignored by the loss
+    with pytest.raises(ValueError):
+        contract.pack_sequences([], 8, None, None)
+
+
+def _tiny_model_dir(tmp_path):
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    from oracle import llama_oracle as O
+    from runbooks_b200.engine import LlamaArch
+
+    a = O.Arch(256, 256, 384, 2, 2, 2, 128, 128, 1e-5, 10000.0)
+    params = O.seeded_params(a, 3)
+    md = tmp_path / "model"
+    md.mkdir()
+    vocab = {"<s>": 0, "</s>": 1, "<unk>": 2, **{f"w{i}": i + 3 for i in range(253)}}
+    tok = Tokenizer(models.WordLevel(vocab, unk_token="<unk>"))
+    tok.pre_tokenizer = pre_tokenizers.Whitespace()
+    tok.save(str(md / "tokenizer.json"))
+    (md / "tokenizer_config.json").write_text(json.dumps({"bos_token": "<s>", "eos_token": "</s>"}))
+    arch = LlamaArch(256, 256, 384, 2, 2, 2, 128, 128, 1e-5, 10000.0)
+    from tests.util import bf16_bits
+    contract.save_hf_checkpoint(str(md), arch.to_hf_config(), ((k, bf16_bits(v)) for k, v in params.items()))
+    return md, a, params
+
+
+def test_checkpoint_round_trip_loads_in_hf(tmp_path):
+    """Our artifact layout must be loadable as a model input again (the Server later mounts it:
+    server_controller.go:184-193) — checked with the real AutoModelForCausalLM."""
+    from transformers import AutoModelForCausalLM
+    from oracle import llama_oracle as O
+
+    md, a, params = _tiny_model_dir(tmp_path)
+    assert sorted(os.listdir(md)) == ["config.json", "model.safetensors", "tokenizer.json", "tokenizer_config.json"]
+    back = dict(contract.iter_safetensors(str(md)))
+    assert set(back) == set(params)
+    for k, v in params.items():
+        assert back[k].dtype == np.uint16 and back[k].shape == v.shape
+        assert np.array_equal(torch.from_numpy(back[k]).view(torch.bfloat16).float().numpy(), v)
+    model = AutoModelForCausalLM.from_pretrained(str(md), torch_dtype=torch.float32)
+    ids = torch.randint(0, 256, (1, 128), generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        hf = model(ids).logits
+        mine = O.forward({k: torch.tensor(v) for k, v in params.items()}, ids, a)
+    assert float((hf - mine).norm() / mine.norm()) < 2e-5
+
+
+def test_checkpoint_sharding(tmp_path, monkeypatch):
+    monkeypatch.setattr(contract, "MAX_SHARD_BYTES", 300_000)
+    md, a, params = _tiny_model_dir(tmp_path)
+    files = sorted(f for f in os.listdir(md) if f.endswith(".safetensors"))
+    assert len(files) > 1 and files[0].startswith("model-00001-of-")
+    idx = json.load(open(md / "model.safetensors.index.json"))
+    assert set(idx["weight_map"]) == set(params)
+    assert set(dict(contract.iter_safetensors(str(md)))) == set(params)
+
+
+def test_tokenizer_and_dataset_build(tmp_path):
+    from runbooks_b200 import worker
+    md, a, params = _tiny_model_dir(tmp_path)
+    d = tmp_path / "data"
+    d.mkdir()
+    (d / "x.jsonl").write_text("\n".join(json.dumps({"prompt": "w1 w2 w3", "completion": "w4 w5"}) for _ in range(40)))
+    tp = contract.TrainParams(prompt_template="{prompt} w9 {completion}")
+    ids, labels = worker.build_dataset(tp, str(md), str(d), 128)
+    assert ids.shape[1] == 128 and ids.shape == labels.shape
+    assert list(ids[0, :8]) == [0, 4, 5, 6, 12, 7, 8, 1]   # <s> w1 w2 w3 w9 w4 w5 </s>
+    per_step, spe, total = worker.plan_steps(len(ids), contract.TrainParams(num_train_epochs=1, per_device_train_batch_size=1), 2)
+    assert per_step == 2 and spe == len(ids) // 2 and total == spe

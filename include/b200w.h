@@ -165,8 +165,7 @@ B200W_API int b200w_op_attention_fwd(b200w_ctx* ctx, const void* qkv, int ld_qkv
                            float scale);
 B200W_API int b200w_op_attention_bwd(b200w_ctx* ctx, const void* qkv, int ld_qkv, int k_off, int v_off,
                            const void* out, const void* dout, int ld_out, const float* lse2,
-                           float* delta, float* dq32, void* dqkv, int B, int S, int H, int Hkv,
-                           float scale);
+                           float* delta, void* dqkv, int B, int S, int H, int Hkv, float scale);
 B200W_API int b200w_op_adamw(b200w_ctx* ctx, float* master, float* m, float* v, const float* g, void* w_bf16,
                    int64_t n, float lr, float beta1, float beta2, float eps, float wd, int step,
                    float gscale);

@@ -77,7 +77,7 @@ PROTOTYPES = {
     "b200w_op_attention_fwd": (C.c_int, [c_ctx, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp,
                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
     "b200w_op_attention_bwd": (C.c_int, [c_ctx, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp,
-                                         vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
+                                         vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
     "b200w_op_adamw": (C.c_int, [c_ctx, vp, vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float,
                                  C.c_float, C.c_float, C.c_float, C.c_int, C.c_float]),
     "b200w_op_grad_norm": (C.c_int, [c_ctx, vp, C.c_int64, f32p]),

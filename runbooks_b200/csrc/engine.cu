@@ -139,7 +139,7 @@ struct b200w_ctx {
   size_t pinned_cap = 0;
   bf16 *dh_a = nullptr, *dh_b = nullptr, *dn = nullptr, *dact = nullptr, *dgu = nullptr,
        *dattn = nullptr, *dqkv = nullptr;
-  float *dq32 = nullptr, *delta = nullptr;
+  float *delta = nullptr, *dw_partial = nullptr;
   float* scal = nullptr;    // [0] loss, [1] gscale, [2] gnorm
   double* sumsq = nullptr;
   float* host_scal = nullptr;  // pinned [4]
@@ -294,8 +294,8 @@ void alloc_activations(b200w_ctx* c) {
     c->dgu = c->alloc<bf16>(T * 2 * f);
     c->dattn = c->alloc<bf16>(T * qd);
     c->dqkv = c->alloc<bf16>(T * qkvd);
-    c->dq32 = c->alloc<float>(T * qd);
     c->delta = c->alloc<float>(H * T);
+    c->dw_partial = c->alloc<float>(static_cast<size_t>(rmsnorm_bwd_blocks(static_cast<int>(T))) * d);
   }
   c->rope_tab = c->alloc<float2>(static_cast<size_t>(a.max_seq_len) * (a.head_dim / 2));
   rope_table(c->rope_tab, a.max_seq_len, a.head_dim, a.rope_theta, c->stream);
@@ -399,7 +399,7 @@ void backward_micro(b200w_ctx* c, const int32_t* ids, int nseq, bool first, bool
   if (overlap_ar) allreduce_range(c, c->p_lm, static_cast<size_t>(V) * d);
   bf16* dh_cur = c->dh_a;
   bf16* dh_alt = c->dh_b;
-  rmsnorm_bwd(c->dn, c->h_final, c->w + c->p_norm, c->rstdf, nullptr, dh_cur, g + c->p_norm, T, d, s); ++n;
+  rmsnorm_bwd(c->dn, c->h_final, c->w + c->p_norm, c->rstdf, nullptr, dh_cur, g + c->p_norm, c->dw_partial, T, d, s); n += 2;
 
   for (int l = L - 1; l >= 0; --l) {
     auto& x = c->la[l];
@@ -412,19 +412,17 @@ void backward_micro(b200w_ctx* c, const int32_t* ids, int nseq, bool first, bool
     egemm(c, c->dgu, false, 2 * f, c->w + o_gu, true, d, c->dn, nullptr, false, d, T, d, 2 * f);
     egemm(c, c->dgu, true, 2 * f, x.n2, true, d, g + o_gu, acc(o_gu), true, d, 2 * f, d, T);
     // dh_mid = dh + rmsnorm_bwd(dn2)
-    rmsnorm_bwd(c->dn, x.h_mid, c->w + p.ln2, x.rstd2, dh_cur, dh_alt, g + p.ln2, T, d, s); ++n;
+    rmsnorm_bwd(c->dn, x.h_mid, c->w + p.ln2, x.rstd2, dh_cur, dh_alt, g + p.ln2, c->dw_partial, T, d, s); n += 2;
     std::swap(dh_cur, dh_alt);
     // h_mid = h_in + attn Wo^T
     egemm(c, dh_cur, false, d, c->w + o_o, true, qd, c->dattn, nullptr, false, qd, T, qd, d);
     egemm(c, dh_cur, true, d, x.attn, true, qd, g + o_o, acc(o_o), true, qd, d, qd, T);
-    B200W_CUDA(cudaMemsetAsync(c->dq32, 0, static_cast<size_t>(T) * qd * sizeof(float), s));
-    attention_bwd(x.qkv, qkvd, qd, qd + kd, x.attn, c->dattn, qd, x.lse, c->delta, c->dq32, c->dqkv,
-                  nseq, S, H, Hkv, scale, s); n += 2;
-    cast_f32_to_bf16_2d(c->dq32, c->dqkv, qkvd, T, qd, s); ++n;
+    attention_bwd(x.qkv, qkvd, qd, qd + kd, x.attn, c->dattn, qd, x.lse, c->delta, c->dqkv, nseq, S, H,
+                  Hkv, scale, s); n += 3;
     rope_apply(c->dqkv, qkvd, c->rope_tab, T, S, H + Hkv, dh, true, s); ++n;
     egemm(c, c->dqkv, false, qkvd, c->w + o_q, true, d, c->dn, nullptr, false, d, T, d, qkvd);
     egemm(c, c->dqkv, true, qkvd, x.n1, true, d, g + o_q, acc(o_q), true, d, qkvd, d, T);
-    rmsnorm_bwd(c->dn, x.h_in, c->w + p.ln1, x.rstd1, dh_cur, dh_alt, g + p.ln1, T, d, s); ++n;
+    rmsnorm_bwd(c->dn, x.h_in, c->w + p.ln1, x.rstd1, dh_cur, dh_alt, g + p.ln1, c->dw_partial, T, d, s); n += 2;
     std::swap(dh_cur, dh_alt);
     if (overlap_ar) {
       // the layer's matrices are contiguous: [wqkv .. wd + d*f)
@@ -910,7 +908,17 @@ int b200w_op_rmsnorm_fwd(b200w_ctx* ctx, const void* x, const void* w, void* y, 
 }
 int b200w_op_rmsnorm_bwd(b200w_ctx* ctx, const void* dy, const void* x, const void* w,
                          const float* rstd, const void* dresid, void* dx, float* dw, int T, int d) {
-  HOOK(rmsnorm_bwd(dy, x, w, rstd, dresid, dx, dw, T, d, ctx->stream));
+  return guarded(ctx, [&] {
+    float* part = nullptr;
+    B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&part),
+                          static_cast<size_t>(rmsnorm_bwd_blocks(T)) * d * sizeof(float)));
+    try {
+      rmsnorm_bwd(dy, x, w, rstd, dresid, dx, dw, part, T, d, ctx->stream);
+      ctx->launches += 2;
+      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    } catch (...) { cudaFree(part); throw; }
+    cudaFree(part);
+  });
 }
 int b200w_op_rope(b200w_ctx* ctx, void* buf, int ld, int T, int S, int nheads, int dh, float theta,
                   int inverse) {
@@ -953,10 +961,9 @@ int b200w_op_attention_fwd(b200w_ctx* ctx, const void* qkv, int ld_qkv, int k_of
 }
 int b200w_op_attention_bwd(b200w_ctx* ctx, const void* qkv, int ld_qkv, int k_off, int v_off,
                            const void* out, const void* dout, int ld_out, const float* lse2,
-                           float* delta, float* dq32, void* dqkv, int B, int S, int H, int Hkv,
-                           float scale) {
-  HOOK(attention_bwd(qkv, ld_qkv, k_off, v_off, out, dout, ld_out, lse2, delta, dq32, dqkv, B, S, H,
-                     Hkv, scale, ctx->stream));
+                           float* delta, void* dqkv, int B, int S, int H, int Hkv, float scale) {
+  HOOK(attention_bwd(qkv, ld_qkv, k_off, v_off, out, dout, ld_out, lse2, delta, dqkv, B, S, H, Hkv,
+                     scale, ctx->stream));
 }
 int b200w_op_adamw(b200w_ctx* ctx, float* master, float* m, float* v, const float* g, void* w_bf16,
                    int64_t n, float lr, float beta1, float beta2, float eps, float wd, int step,

@@ -121,15 +121,18 @@ rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16*
 }
 
 // One block walks rows blockIdx.x, +gridDim.x, ...; per-thread dw partials live in registers
-// for the whole walk and are flushed with one atomicAdd per column at the end.
-__global__ void __launch_bounds__(NORM_THREADS)
+// for the whole walk and leave as one row of dw_partial[gridDim.x][d] (summed by
+// rmsnorm_dw_reduce_kernel) — no atomics, so the result is deterministic and the kernel stays
+// on its HBM bound (4 x T x d x 2 bytes).
+template <int P>
+__global__ void __launch_bounds__(NORM_THREADS, (P <= 2) ? 2 : 1)
 rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                    const bf16* __restrict__ w, const float* __restrict__ rstd,
-                   const bf16* dresid, bf16* dx, float* __restrict__ dw, int T, int d) {
+                   const bf16* dresid, bf16* dx, float* __restrict__ dw_partial, int T, int d) {
   __shared__ float red[32];
-  float wv[NORM_MAXP][8], dwp[NORM_MAXP][8];
+  float wv[P][8], dwp[P][8];
 #pragma unroll
-  for (int p = 0; p < NORM_MAXP; ++p) {
+  for (int p = 0; p < P; ++p) {
     const int c = (p * NORM_THREADS + threadIdx.x) * 8;
     if (c < d) load8(w + c, wv[p]);
 #pragma unroll
@@ -139,10 +142,10 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
   for (int row = blockIdx.x; row < T; row += gridDim.x) {
     const size_t off = static_cast<size_t>(row) * d;
     const float rs = rstd[row];
-    float xh[NORM_MAXP][8], g[NORM_MAXP][8];
+    float xh[P][8], g[P][8];
     float dot = 0.f;
 #pragma unroll
-    for (int p = 0; p < NORM_MAXP; ++p) {
+    for (int p = 0; p < P; ++p) {
       const int c = (p * NORM_THREADS + threadIdx.x) * 8;
       if (c < d) {
         float dyv[8];
@@ -159,7 +162,7 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
     }
     dot = block_sum(dot, red) * inv_d;
 #pragma unroll
-    for (int p = 0; p < NORM_MAXP; ++p) {
+    for (int p = 0; p < P; ++p) {
       const int c = (p * NORM_THREADS + threadIdx.x) * 8;
       if (c < d) {
         float o[8];
@@ -174,14 +177,25 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
       }
     }
   }
+  float* part = dw_partial + static_cast<size_t>(blockIdx.x) * d;
 #pragma unroll
-  for (int p = 0; p < NORM_MAXP; ++p) {
+  for (int p = 0; p < P; ++p) {
     const int c = (p * NORM_THREADS + threadIdx.x) * 8;
     if (c < d) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(dw + c + j, dwp[p][j]);
+      *reinterpret_cast<float4*>(part + c) = make_float4(dwp[p][0], dwp[p][1], dwp[p][2], dwp[p][3]);
+      *reinterpret_cast<float4*>(part + c + 4) = make_float4(dwp[p][4], dwp[p][5], dwp[p][6], dwp[p][7]);
     }
   }
+}
+
+// dw[c] += sum_b dw_partial[b][c]
+__global__ void rmsnorm_dw_reduce_kernel(const float* __restrict__ dw_partial, float* __restrict__ dw,
+                                         int nblocks, int d) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  float acc = 0.f;
+  for (int b = 0; b < nblocks; ++b) acc += dw_partial[static_cast<size_t>(b) * d + c];
+  dw[c] += acc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -489,13 +503,26 @@ void rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int T, int 
                                                 rstd, d, eps);
   B200W_CUDA(cudaGetLastError());
 }
+int rmsnorm_bwd_blocks(int T) { return T < sm_count() * 2 ? T : sm_count() * 2; }
+
 void rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd,
-                 const void* dresid, void* dx, float* dw, int T, int d, cudaStream_t s) {
+                 const void* dresid, void* dx, float* dw, float* dw_partial, int T, int d,
+                 cudaStream_t s) {
   B200W_CHECK(d % 8 == 0 && d <= NORM_THREADS * 8 * NORM_MAXP, "unsupported hidden size");
-  const int grid = T < sm_count() * 4 ? T : sm_count() * 4;
-  rmsnorm_bwd_kernel<<<grid, NORM_THREADS, 0, s>>>(
-      static_cast<const bf16*>(dy), static_cast<const bf16*>(x), static_cast<const bf16*>(w), rstd,
-      static_cast<const bf16*>(dresid), static_cast<bf16*>(dx), dw, T, d);
+  B200W_CHECK(dw_partial != nullptr, "rmsnorm_bwd needs a [rmsnorm_bwd_blocks(T), d] fp32 scratch");
+  const int grid = rmsnorm_bwd_blocks(T);
+  const bf16 *dyp = static_cast<const bf16*>(dy), *xp = static_cast<const bf16*>(x),
+             *wp = static_cast<const bf16*>(w), *rp = static_cast<const bf16*>(dresid);
+  bf16* dxp = static_cast<bf16*>(dx);
+  const int passes = (d + NORM_THREADS * 8 - 1) / (NORM_THREADS * 8);
+  if (passes <= 1)
+    rmsnorm_bwd_kernel<1><<<grid, NORM_THREADS, 0, s>>>(dyp, xp, wp, rstd, rp, dxp, dw_partial, T, d);
+  else if (passes == 2)
+    rmsnorm_bwd_kernel<2><<<grid, NORM_THREADS, 0, s>>>(dyp, xp, wp, rstd, rp, dxp, dw_partial, T, d);
+  else
+    rmsnorm_bwd_kernel<4><<<grid, NORM_THREADS, 0, s>>>(dyp, xp, wp, rstd, rp, dxp, dw_partial, T, d);
+  B200W_CUDA(cudaGetLastError());
+  rmsnorm_dw_reduce_kernel<<<(d + 255) / 256, 256, 0, s>>>(dw_partial, dw, grid, d);
   B200W_CUDA(cudaGetLastError());
 }
 

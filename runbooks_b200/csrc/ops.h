@@ -19,11 +19,11 @@ void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int 
 // out: [T, ld_out] (head h at column h*128); lse2: [H, T] fp32 (log2-domain logsumexp).
 void attention_fwd(const void* qkv, int ld_qkv, int k_off, int v_off, void* out, int ld_out,
                    float* lse2, int B, int S, int H, int Hkv, float scale, cudaStream_t s);
-// dqkv gets dk, dv (bf16) at k_off / v_off; dq is accumulated in fp32 into dq32 [T, H*128]
-// (must be zero on entry). delta: [H, T] fp32 scratch.
+// dqkv [T, ld_qkv] receives dq (column 0), dk (k_off), dv (v_off) in bf16; three launches
+// (delta, dK/dV, dQ), no global atomics. delta: [H, T] fp32 scratch.
 void attention_bwd(const void* qkv, int ld_qkv, int k_off, int v_off, const void* out,
-                   const void* dout, int ld_out, const float* lse2, float* delta, float* dq32,
-                   void* dqkv, int B, int S, int H, int Hkv, float scale, cudaStream_t s);
+                   const void* dout, int ld_out, const float* lse2, float* delta, void* dqkv, int B,
+                   int S, int H, int Hkv, float scale, cudaStream_t s);
 
 // ---- ops.cu --------------------------------------------------------------------------------
 void embed_fwd(const int32_t* ids, const void* table, void* out, int T, int d, int vocab,
@@ -33,9 +33,12 @@ void embed_bwd(const int32_t* ids, const void* dout, float* dtable, int T, int d
 
 void rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int T, int d, float eps,
                  cudaStream_t s);
-// dx = (dresid ? dresid : 0) + d(rmsnorm)/dx ; dw (fp32) += sum_t dy * xhat
+// dx = (dresid ? dresid : 0) + d(rmsnorm)/dx ; dw (fp32) += sum_t dy * xhat.
+// dw_partial: fp32 scratch [rmsnorm_bwd_blocks(T), d]; two launches (walk + column reduce).
+int rmsnorm_bwd_blocks(int T);
 void rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd,
-                 const void* dresid, void* dx, float* dw, int T, int d, cudaStream_t s);
+                 const void* dresid, void* dx, float* dw, float* dw_partial, int T, int d,
+                 cudaStream_t s);
 
 // cos/sin table for rotate_half RoPE: tab[pos*(dh/2) + i] = {cos, sin}(pos * theta^(-2i/dh))
 void rope_table(float2* tab, int S, int dh, float theta, cudaStream_t s);

@@ -64,10 +64,9 @@ def main():
     print(f"attention fwd S{S} H{H}: {t * 1e3:.3f} ms  {fl / t / 1e12:.1f} TF/s (causal flops)", flush=True)
     do = torch.randn_like(o)
     delta = torch.empty_like(lse)
-    dq32 = torch.zeros(B_ * S, H * 128, device="cuda", dtype=torch.float32)
     dqkv = torch.empty_like(qkv)
     t = timeit(lambda: call(e, "b200w_op_attention_bwd", qkv, 3 * H * 128, H * 128, 2 * H * 128, o, do,
-                            H * 128, lse, delta, dq32, dqkv, B_, S, H, H, 128 ** -0.5))
+                            H * 128, lse, delta, dqkv, B_, S, H, H, 128 ** -0.5))
     out["attn_bwd"] = dict(ms=t * 1e3, tflops=2.5 * fl / t / 1e12)
     print(f"attention bwd S{S} H{H}: {t * 1e3:.3f} ms  {2.5 * fl / t / 1e12:.1f} TF/s (causal flops)", flush=True)
     os.makedirs("gpurun_out", exist_ok=True)

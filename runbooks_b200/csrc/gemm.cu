@@ -254,6 +254,202 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// ==========================================================================================
+// CTA-pair variant: cluster of 2 CTAs computes a 256 x 256 tile with tcgen05.mma.cta_group::2.
+// Each CTA stages its own 128 rows of A and HALF of B (128 of the 256 N columns), so per-SM
+// shared-memory traffic per MMA drops by a third and 6 pipeline stages fit instead of 4.
+// Barriers: full[] live in the leader (rank 0) and collect both CTAs' TMA bytes; empty[] and
+// tfull[] exist in both CTAs and are signalled by the leader's multicast tcgen05.commit;
+// tempty[] live in the leader and collect one arrival per epilogue warp of both CTAs.
+// ==========================================================================================
+constexpr int PAIR_N = 256;
+constexpr int PAIR_STAGE_BYTES = A_STAGE_BYTES + (PAIR_N / 2) * BLOCK_K * 2;  // 32 KB
+constexpr int PAIR_STAGES = 6;
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256;
+
+template <bool A_MN, bool B_MN, typename OutT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      OutT* D, const OutT* C, int M, int N, int K, int ldd) {
+  constexpr int STAGES = PAIR_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * PAIR_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2] (used in the leader only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);  // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (M + 255) / 256;
+  const int num_n = (N + PAIR_N - 1) / PAIR_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile % num_m) * 256 + rank * 128;          // my 128 rows of A
+        const int n0 = (tile / num_m) * PAIR_N + rank * (PAIR_N / 2);  // my half of B
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * PAIR_STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          // only the leader's barrier counts bytes: both CTAs' TMA traffic lands on it
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_2d_pair(sa, &tmA, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+              tma_load_2d_pair(sa + a * (BLOCK_K * 128), &tmA, &full_bar[stage], m0 + a * 64, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_pair(sb, &tmB, &full_bar[stage], k0, n0);  // box [128 rows(n), 64 k]
+          } else {
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+              tma_load_2d_pair(sb + a * (BLOCK_K * 128), &tmB, &full_bar[stage], n0 + a * 64, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, PAIR_N, A_MN, B_MN);
+      constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+      constexpr uint32_t b_kstep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+      constexpr uint32_t a_lbo = A_MN ? (BLOCK_K * 128) : 16;
+      constexpr uint32_t b_lbo = B_MN ? (BLOCK_K * 128) : 16;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * PAIR_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * PAIR_STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t da = make_smem_desc(sa, a_lbo, 1024);
+          const uint64_t db = make_smem_desc(sb, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            tc_mma_bf16_pair(tmem_d, desc_advance(da, k * a_kstep), desc_advance(db, k * b_kstep),
+                             idesc, (kb | k) != 0);
+          tc_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile % num_m) * 256 + rank * 128;
+      const int n0 = (tile / num_m) * PAIR_N;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      __syncwarp();
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      OutT* drow = D + static_cast<size_t>(row) * ldd + n0;
+      const OutT* crow = C ? C + static_cast<size_t>(row) * ldd + n0 : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < PAIR_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_addr(tmem_base, q * 32, acc * PAIR_N + c * 32), r);
+        tmem_ld_wait();
+        const int ncols = N - (n0 + c * 32);
+        if (row_ok && ncols > 0) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          store_chunk32<OutT>(drow + c * 32, crow ? crow + c * 32 : nullptr, v, ncols,
+                              crow != nullptr);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA thread waits on it
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncwarp();        // the .aligned cluster barrier wants whole warps
+  cluster_sync_all();  // nobody leaves while the peer may still touch its smem / barriers / TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+template <bool A_MN, bool B_MN, typename OutT>
+void launch_pair(const void* A, const void* B, OutT* D, const OutT* C, int M, int N, int K, int lda,
+                 int ldb, int ldd, cudaStream_t stream) {
+  CUtensorMap tmA = A_MN ? make_tmap_bf16_2d(A, K, M, lda, BLOCK_K, 64)
+                         : make_tmap_bf16_2d(A, M, K, lda, BLOCK_M, BLOCK_K);
+  CUtensorMap tmB = B_MN ? make_tmap_bf16_2d(B, K, N, ldb, BLOCK_K, 64)
+                         : make_tmap_bf16_2d(B, N, K, ldb, PAIR_N / 2, BLOCK_K);
+  auto kern = gemm_bf16_pair_kernel<A_MN, B_MN, OutT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200W_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_tiles = ((M + 255) / 256) * ((N + PAIR_N - 1) / PAIR_N);
+  const int max_clusters = sm_count() / 2;
+  const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+  kern<<<clusters * 2, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(tmA, tmB, D, C, M, N, K, ldd);
+  B200W_CUDA(cudaGetLastError());
+}
+
+template <typename OutT>
+void dispatch_pair(bool a_mn, bool b_mn, const void* A, const void* B, OutT* D, const OutT* C, int M,
+                   int N, int K, int lda, int ldb, int ldd, cudaStream_t s) {
+  if (!a_mn && !b_mn) launch_pair<false, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
+  else if (!a_mn && b_mn) launch_pair<false, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
+  else if (a_mn && b_mn) launch_pair<true, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
+  else launch_pair<true, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT>
 void launch(const void* A, const void* B, OutT* D, const OutT* C, int M, int N, int K, int lda,
             int ldb, int ldd, cudaStream_t stream) {
@@ -303,7 +499,16 @@ void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int 
     const long tiles256 = static_cast<long>((M + 127) / 128) * ((N + 255) / 256);
     block_n = (N >= 256 && tiles256 >= sm_count()) ? 256 : 128;
   }
-  B200W_CHECK(block_n == 128 || block_n == 256, "block_n must be 128 or 256");
+  if (block_n == 512) {  // CTA-pair kernel: 256 x 256 tiles on tcgen05.mma.cta_group::2
+    if (out_fp32)
+      dispatch_pair<float>(a_mn, b_mn, A, B, static_cast<float*>(D), static_cast<const float*>(C), M, N,
+                           K, lda, ldb, ldd, stream);
+    else
+      dispatch_pair<__nv_bfloat16>(a_mn, b_mn, A, B, static_cast<__nv_bfloat16*>(D),
+                                   static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb, ldd, stream);
+    return;
+  }
+  B200W_CHECK(block_n == 128 || block_n == 256, "block_n must be 0, 128, 256 or 512 (CTA pair)");
   if (out_fp32) {
     if (block_n == 256)
       dispatch_major<256, float>(a_mn, b_mn, A, B, static_cast<float*>(D),

@@ -21,7 +21,7 @@ def _operands(M, N, K, a_mn, b_mn, seed=0):
     return Ad, Bd, ref
 
 
-@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("block_n", [128, 256, 512])  # 512 = CTA-pair kernel (cta_group::2)
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_gemm_f32_out(engine, M, N, K, a_mn, b_mn, block_n):
@@ -34,14 +34,15 @@ def test_gemm_f32_out(engine, M, N, K, a_mn, b_mn, block_n):
     assert err < 2e-5
 
 
+@pytest.mark.parametrize("block_n", [0, 512])
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
-def test_gemm_bf16_out_with_residual(engine, a_mn, b_mn):
+def test_gemm_bf16_out_with_residual(engine, a_mn, b_mn, block_n):
     M, N, K = 384, 512, 320
     Ad, Bd, ref = _operands(M, N, K, a_mn, b_mn, seed=1)
     Cres = torch.randn(M, N, generator=torch.Generator().manual_seed(2)).bfloat16()
     D = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
     call(engine, "b200w_op_gemm", Ad, a_mn, Ad.shape[1], Bd, b_mn, Bd.shape[1], D, dev(Cres), 0, N, M, N,
-         K, 0)
+         K, block_n)
     err = rel_err(D.float(), ref + Cres.float())
     print(f"gemm bf16+residual a_mn{a_mn} b_mn{b_mn}: rel_err {err:.3e}")
     assert err < 3e-3
@@ -69,7 +70,8 @@ def test_gemm_strided_output(engine):
     assert bool((D[:, :N] == 7).all()) and bool((D[:, 2 * N:] == 7).all())
 
 
-def test_gemm_llama_shapes(engine):
+@pytest.mark.parametrize("block_n", [0, 512])
+def test_gemm_llama_shapes(engine, block_n):
     """One forward, one dgrad and one wgrad GEMM at Llama-2-7B layer width, T = 1024."""
     T, d = 1024, 4096
     for (M, N, K, a_mn, b_mn) in [(T, 3 * d, d, 0, 0), (T, d, 3 * d, 0, 1), (d, d, T, 1, 1)]:
@@ -79,9 +81,9 @@ def test_gemm_llama_shapes(engine):
         ref = A32 @ B32.T
         D = torch.empty(M, N, device="cuda", dtype=torch.float32)
         call(engine, "b200w_op_gemm", Ad, a_mn, Ad.shape[1], Bd, b_mn, Bd.shape[1], D, None, 1, N, M, N,
-             K, 0)
+             K, block_n)
         err = rel_err(D, ref)
-        print(f"gemm llama M{M} N{N} K{K}: rel_err {err:.3e}")
+        print(f"gemm llama M{M} N{N} K{K} bn{block_n}: rel_err {err:.3e}")
         assert err < 2e-5
 
 

@@ -45,7 +45,7 @@ def main():
         B = torch.randn((K, N) if b_mn else (N, K), device="cuda").bfloat16()
         wg = name.startswith("wgrad")
         D = torch.empty(M, N, device="cuda", dtype=torch.float32 if wg else torch.bfloat16)
-        for bn in (128, 256):
+        for bn in (256, 512):
             t = timeit(lambda: call(e, "b200w_op_gemm", A, a_mn, A.shape[1], B, b_mn, B.shape[1], D, None,
                                     1 if wg else 0, N, M, N, K, bn))
             tf = 2.0 * M * N * K / t / 1e12

@@ -2,18 +2,21 @@
 // Oracle: F.scaled_dot_product_attention(q, k, v, is_causal=True) as called by HF
 // LlamaAttention with _attn_implementation == "sdpa" (SURVEY.md §8 a7).
 //
-// All three kernels keep every accumulator in TMEM and give each of the 128 threads one TMEM lane
-// (= one matrix row), so softmax row statistics never need a cross-thread reduction. Each is
-// software-pipelined around one idea: the score MMAs of block i+1 are issued BEFORE the threads
-// start the softmax of block i (double-buffered TMEM), so the tensor pipe works under the MUFU /
-// FMA work instead of waiting for it.
+// Common structure of the three kernels (CTA = 9 warps):
+//   warp 8        control: every TMA load and every tcgen05.mma is issued by its lane 0, which
+//                 also owns all the "is this buffer free" waits;
+//   warps 0..7    compute: a TMEM lane is a matrix row; warp w touches lane quarter (w & 3) and
+//                 column half (w >> 2) of each 64-column score block, i.e. TWO threads per row, so
+//                 every SM sub-partition has >= 2 warps of MUFU/FMA work to overlap;
+//   handoffs      mbarriers only (tcgen05.commit -> compute, 256-thread arrive -> control).
+// The score MMAs of block i+1 are issued before the compute warps start block i (double-buffered
+// TMEM), so the tensor pipe runs under the softmax instead of after it.
 //
 // forward       CTA = (128-query tile, head, sequence), 64-key blocks, 2 CTAs / SM:
-//                 S = Q K^T -> TMEM;  P = exp2(S - m) -> smem bf16 (SW128 K-major)
-//                 O += P V    accumulated IN TMEM; rescaled (tcgen05.ld/st) only when the running
-//                 max grows by more than 2^8 ("lazy rescale"), the final O / l is exact either way.
-// backward dKdV CTA = (128-key block, kv head, sequence), 64-query blocks, transposed form so
-//                 P^T / dS^T leave TMEM in the layout the next MMAs read:
+//                 S = Q K^T -> TMEM;  P = 2^(S - m) -> smem bf16 (SW128 K-major)
+//                 O += P V accumulated IN TMEM; rescaled (tcgen05.ld/st) only when the running max
+//                 grows by more than 2^8 ("lazy rescale"); the final O / l is exact either way.
+// backward dKdV CTA = (128-key block, kv head, sequence), 64-query blocks, transposed form:
 //                 S^T = K Q^T, dP^T = V dO^T -> TMEM;  P^T, dS^T -> smem;
 //                 dV += P^T dO,  dK += dS^T Q   (TMEM accumulators across the whole loop)
 // backward dQ   CTA = (128-query tile, head, sequence), 64-key blocks: S, dP recomputed,
@@ -30,6 +33,8 @@ using bf16 = __nv_bfloat16;
 constexpr int DH = 128;
 constexpr int ATOM64 = 64 * 128;    // bytes of a [64 rows x 128 B] swizzle-atom column
 constexpr int ATOM128 = 128 * 128;  // bytes of a [128 rows x 128 B] one
+constexpr int NCOMPUTE = 256;
+constexpr int NTHREADS = 288;
 constexpr float LAZY_RESCALE_LOG2 = 8.f;
 
 __device__ __forceinline__ void require_1024_aligned(const void* p) {
@@ -38,9 +43,17 @@ __device__ __forceinline__ void require_1024_aligned(const void* p) {
     __trap();
   }
 }
+__device__ __forceinline__ float ex2(float x) {  // one MUFU.EX2
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void compute_bar_sync() {  // the 256 compute threads only
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
 
-// K-major operand tile whose rows are 128 B (64 elements) wide, `atoms` of them side by side
-// along the contraction (dh = 128 -> 2 atoms, `atom_bytes` apart). Issues dh/16 MMAs.
+// K-major operands whose rows are 128 B (64 elements) wide, 2 atoms side by side along the
+// contraction (dh = 128), `*_atom_bytes` apart. Issues dh/16 = 8 MMAs into tmem_d.
 __device__ __forceinline__ void mma_kmajor_dh(uint32_t tmem_d, uint32_t a_base, uint32_t a_atom_bytes,
                                               uint32_t b_base, uint32_t b_atom_bytes, uint32_t idesc) {
 #pragma unroll
@@ -51,12 +64,39 @@ __device__ __forceinline__ void mma_kmajor_dh(uint32_t tmem_d, uint32_t a_base, 
     tc_mma_bf16(tmem_d, da, db, idesc, k != 0);
   }
 }
+// D (+)= A[128 x 64, K-major, one atom] * B[MN-major: N = dh (2 atoms, ATOM64 apart), K = 64 rows]
+__device__ __forceinline__ void mma_a64_bmn(uint32_t tmem_d, uint32_t a_base, uint32_t b_base,
+                                            uint32_t idesc, bool accumulate_first) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t da = make_smem_desc(a_base + k * 32, 16, 1024);
+    const uint64_t db = make_smem_desc(b_base + k * 2048, ATOM64, 1024);
+    tc_mma_bf16(tmem_d, da, db, idesc, accumulate_first || k != 0);
+  }
+}
 
 __device__ __forceinline__ uint4 pack8(const float (&p)[8]) {
   uint4 u;
   u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
   u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
   return u;
+}
+// 64 fp32 TMEM columns [col0, col0+64) of this thread's lane -> bf16 row in global memory
+__device__ __forceinline__ void tmem_row64_to_global(uint32_t taddr, bf16* dst, float mul) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float o8[8] = {__uint_as_float(r[i * 8 + 0]) * mul, __uint_as_float(r[i * 8 + 1]) * mul,
+                           __uint_as_float(r[i * 8 + 2]) * mul, __uint_as_float(r[i * 8 + 3]) * mul,
+                           __uint_as_float(r[i * 8 + 4]) * mul, __uint_as_float(r[i * 8 + 5]) * mul,
+                           __uint_as_float(r[i * 8 + 6]) * mul, __uint_as_float(r[i * 8 + 7]) * mul};
+      reinterpret_cast<uint4*>(dst + c * 32)[i] = pack8(o8);
+    }
+  }
 }
 
 // ==========================================================================================
@@ -67,7 +107,7 @@ constexpr int FWD_SMEM = 2 * ATOM128 /*Q*/ + 2 * 2 * ATOM64 /*K x2*/ + 2 * 2 * A
                          ATOM128 /*P*/ + 256 /*barriers*/;
 constexpr int FWD_TMEM_COLS = 256;  // S[2]: [0,64) [64,128)   O: [128,256)
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(NTHREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, int ld_out,
                 float* __restrict__ lse2, int k_off, int v_off, int B, int S, int H, int Hkv,
                 float scale_log2) {
@@ -80,9 +120,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(sP + ATOM128);
   uint64_t* bar_k = bar_q + 1;  // [2]
   uint64_t* bar_v = bar_k + 2;  // [2]
-  uint64_t* bar_s = bar_v + 2;  // [2]
-  uint64_t* bar_o = bar_s + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
+  uint64_t* bar_s = bar_v + 2;  // [2] S(j) in TMEM
+  uint64_t* bar_o = bar_s + 2;  //     PV(j) retired
+  uint64_t* bar_p = bar_o + 1;  //     P(j) in smem (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_p + 1);
 
   const int nq = S / FWD_BQ;
   const int bh = blockIdx.x % (B * H);
@@ -92,7 +133,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
   const int tok0 = b * S;                // first token of this sequence
   const int q0 = qi * FWD_BQ;            // first query row inside the sequence
   const int njb = 2 * qi + 2;            // causal: key blocks [0, njb)
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -103,168 +144,176 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
       mbar_init(&bar_s[i], 1);
     }
     mbar_init(bar_o, 1);
+    mbar_init(bar_p, NCOMPUTE);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, FWD_TMEM_COLS);
+  if (warp == 8) tmem_alloc(tmem_slot, FWD_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + 128;
 
-  auto load_k = [&](int j, int buf) {
-    mbar_arrive_expect_tx(&bar_k[buf], 2 * ATOM64);
+  if (warp == 8) {
+    // =============================== control ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, FWD_BKV, false, false);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, DH, false, true);
+      auto load_k = [&](int j) {
+        const int buf = j & 1;
+        mbar_arrive_expect_tx(&bar_k[buf], 2 * ATOM64);
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
-      tma_load_2d(sK + (buf * 2 + a) * ATOM64, &tm_qkv, &bar_k[buf], k_off + hk * DH + a * 64,
-                  tok0 + j * FWD_BKV);
-  };
-  auto load_v = [&](int j, int buf) {
-    mbar_arrive_expect_tx(&bar_v[buf], 2 * ATOM64);
+        for (int a = 0; a < 2; ++a)
+          tma_load_2d(sK + (buf * 2 + a) * ATOM64, &tm_qkv, &bar_k[buf], k_off + hk * DH + a * 64,
+                      tok0 + j * FWD_BKV);
+      };
+      auto load_v = [&](int j) {
+        const int buf = j & 1;
+        mbar_arrive_expect_tx(&bar_v[buf], 2 * ATOM64);
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
-      tma_load_2d(sV + (buf * 2 + a) * ATOM64, &tm_qkv, &bar_v[buf], v_off + hk * DH + a * 64,
-                  tok0 + j * FWD_BKV);
-  };
-  constexpr uint32_t idesc_s = make_idesc_bf16(128, FWD_BKV, false, false);
-  constexpr uint32_t idesc_o = make_idesc_bf16(128, DH, false, true);
-  auto issue_s = [&](int j) {  // S(j) = Q K(j)^T -> TMEM S[j & 1]
-    mma_kmajor_dh(tmem_base + (j & 1) * 64, smem_u32(sQ), ATOM128, smem_u32(sK + (j & 1) * 2 * ATOM64),
-                  ATOM64, idesc_s);
-    tc_commit(&bar_s[j & 1]);
-  };
-
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, 2 * ATOM128);
+        for (int a = 0; a < 2; ++a)
+          tma_load_2d(sV + (buf * 2 + a) * ATOM64, &tm_qkv, &bar_v[buf], v_off + hk * DH + a * 64,
+                      tok0 + j * FWD_BKV);
+      };
+      auto issue_s = [&](int j) {  // S(j) = Q K(j)^T -> TMEM S[j & 1]
+        mma_kmajor_dh(tmem_base + (j & 1) * 64, smem_u32(sQ), ATOM128,
+                      smem_u32(sK + (j & 1) * 2 * ATOM64), ATOM64, idesc_s);
+        tc_commit(&bar_s[j & 1]);
+      };
+      mbar_arrive_expect_tx(bar_q, 2 * ATOM128);
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
-        tma_load_2d(sQ + a * ATOM128 + r * ATOM64, &tm_qkv, bar_q, h * DH + a * 64,
-                    tok0 + q0 + r * 64);
-    load_k(0, 0);
-    load_v(0, 0);
-    load_k(1, 1);  // njb >= 2 always
-    load_v(1, 1);
-    mbar_wait(bar_q, 0);
-    mbar_wait(&bar_k[0], 0);
-    tc_fence_after();
-    issue_s(0);
-  }
-
-  float m_used = -INFINITY, l_run = 0.f;  // m_used: the (possibly stale) max the exponentials use
-  const int row_local = tid;              // TMEM lane == query row inside the tile
-  const int row_seq = q0 + row_local;     // query position inside the sequence
-  const uint32_t lane_base = (warp * 32u) << 16;
-
-  for (int j = 0; j < njb; ++j) {
-    const int buf = j & 1;
-    if (tid == 0 && j + 1 < njb) {  // score MMAs of the next block run under this block's softmax
-      mbar_wait(&bar_k[buf ^ 1], ((j + 1) >> 1) & 1);
+        for (int r = 0; r < 2; ++r)
+          tma_load_2d(sQ + a * ATOM128 + r * ATOM64, &tm_qkv, bar_q, h * DH + a * 64,
+                      tok0 + q0 + r * 64);
+      load_k(0);
+      load_v(0);
+      load_k(1);  // njb >= 2 always
+      load_v(1);
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_k[0], 0);
       tc_fence_after();
-      issue_s(j + 1);
+      issue_s(0);
+      for (int j = 0; j < njb; ++j) {
+        const int buf = j & 1;
+        if (j + 1 < njb) {  // S buffer buf^1 was drained by the compute warps before bar_p(j-1)
+          mbar_wait(&bar_k[buf ^ 1], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        mbar_wait(bar_p, j & 1);  // P(j) written (and S(j) drained)
+        mbar_wait(&bar_v[buf], (j >> 1) & 1);
+        tc_fence_after();
+        mma_a64_bmn(tmem_O, smem_u32(sP), smem_u32(sV + buf * 2 * ATOM64), idesc_o, j != 0);
+        tc_commit(bar_o);
+        if (j + 2 < njb) {
+          mbar_wait(&bar_s[buf], (j >> 1) & 1);  // S(j) retired: K buffer free
+          load_k(j + 2);
+          mbar_wait(bar_o, j & 1);               // PV(j) retired: V buffer free
+          load_v(j + 2);
+        }
+      }
     }
-    mbar_wait(&bar_s[buf], (j >> 1) & 1);
-    __syncwarp();
-    tc_fence_after();
-    uint32_t sr[2][32];
-    tmem_ld32(tmem_base + buf * 64 + lane_base, sr[0]);
-    tmem_ld32(tmem_base + buf * 64 + lane_base + 32, sr[1]);
-    tmem_ld_wait();
-    if (tid == 0 && j + 2 < njb) load_k(j + 2, buf);  // S(j) retired: its K buffer is free
+  } else {
+    // =============================== compute ===============================
+    const int q = warp & 3, hc = warp >> 2;
+    const int row_local = q * 32 + lane;   // TMEM lane == query row inside the tile
+    const int row_seq = q0 + row_local;    // query position inside the sequence
+    const uint32_t lane_base = (q * 32u) << 16;
+    float m_used = -INFINITY, l_part = 0.f;  // l_part: this thread's half of the row sum
 
-    const int col0 = j * FWD_BKV;
-    const bool diag = (col0 + FWD_BKV - 1) > q0;  // block reaches past the first row's diagonal
-    float mx = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < 64; ++c) {
-      float s = __uint_as_float(sr[c >> 5][c & 31]) * scale_log2;
-      if (diag && (col0 + c > row_seq)) s = -INFINITY;
-      sr[c >> 5][c & 31] = __float_as_uint(s);
-      mx = fmaxf(mx, s);
-    }
-    // lazy rescale: keep the old reference max unless the new one is > 2^8 above it. Block 0 always
-    // sets it (column 0 is visible to every row), so m_used is finite from then on.
-    const bool grow = mx > m_used + LAZY_RESCALE_LOG2;
-    const float m_new = grow ? mx : m_used;
-    const float alpha = grow ? exp2f(m_used - m_new) : 1.f;
-    float pv[64];
-    float psum = 0.f;
-#pragma unroll
-    for (int c = 0; c < 64; ++c) {
-      pv[c] = exp2f(__uint_as_float(sr[c >> 5][c & 31]) - m_new);
-      psum += pv[c];
-    }
-    l_run = l_run * alpha + psum;
-    m_used = m_new;
-
-    if (j > 0) {
-      mbar_wait(bar_o, (j - 1) & 1);  // PV(j-1) retired: P smem, V buffer buf^1 and O are free
+    for (int j = 0; j < njb; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&bar_s[buf], (j >> 1) & 1);
       __syncwarp();
       tc_fence_after();
-      if (tid == 0 && j + 1 < njb) load_v(j + 1, buf ^ 1);
-      if (__any_sync(0xffffffffu, grow)) {  // rare after the first blocks
+      uint32_t sr[2][32];  // the whole 64-column row: both half-row threads derive the same max
+      tmem_ld32(tmem_base + buf * 64 + lane_base, sr[0]);
+      tmem_ld32(tmem_base + buf * 64 + lane_base + 32, sr[1]);
+      tmem_ld_wait();
+
+      const int col0 = j * FWD_BKV;
+      const bool diag = (col0 + FWD_BKV - 1) > q0;  // block reaches past the first row's diagonal
+      float mx = -INFINITY;
+      if (diag) {
 #pragma unroll
-        for (int c = 0; c < DH / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(tmem_O + lane_base + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st32(tmem_O + lane_base + c * 32, r);
+        for (int c = 0; c < 64; ++c) {
+          float s = __uint_as_float(sr[c >> 5][c & 31]);
+          if (col0 + c > row_seq) s = -INFINITY;
+          sr[c >> 5][c & 31] = __float_as_uint(s);
+          mx = fmaxf(mx, s);
         }
-        tmem_st_wait();
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(sr[c >> 5][c & 31]));
       }
-    }
+      mx *= scale_log2;  // scale > 0, so max commutes with it
+      // lazy rescale: keep the old reference max unless the new one is > 2^8 above it. Block 0 always
+      // sets it (column 0 is visible to every row), so m_used is finite from then on.
+      const bool grow = mx > m_used + LAZY_RESCALE_LOG2;
+      const float m_new = grow ? mx : m_used;
+      const float alpha = grow ? ex2(m_used - m_new) : 1.f;
+      uint4 pk[4];
+      float psum = 0.f;
 #pragma unroll
-    for (int c8 = 0; c8 < 8; ++c8) {
-      const float p8[8] = {pv[c8 * 8 + 0], pv[c8 * 8 + 1], pv[c8 * 8 + 2], pv[c8 * 8 + 3],
-                           pv[c8 * 8 + 4], pv[c8 * 8 + 5], pv[c8 * 8 + 6], pv[c8 * 8 + 7]};
-      *reinterpret_cast<uint4*>(sP + sw128_offset(row_local, c8)) = pack8(p8);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-
-    if (tid == 0) {
-      tc_fence_after();
-      mbar_wait(&bar_v[buf], (j >> 1) & 1);
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float p8[8];
 #pragma unroll
-      for (int k = 0; k < FWD_BKV / 16; ++k) {
-        const uint64_t da = make_smem_desc(smem_u32(sP) + k * 32, 16, 1024);
-        // V as MN-major B: N = dh (2 atoms of 64, ATOM64 apart), K = kv rows (16 rows = 2048 B)
-        const uint64_t db = make_smem_desc(smem_u32(sV + buf * 2 * ATOM64) + k * 2048, ATOM64, 1024);
-        tc_mma_bf16(tmem_O, da, db, idesc_o, (j | k) != 0);
+        for (int e = 0; e < 8; ++e) {
+          // sr[hc] is a compile-time-unknown index only through hc; keep both halves addressable
+          const float s = __uint_as_float(hc ? sr[1][c8 * 8 + e] : sr[0][c8 * 8 + e]);
+          p8[e] = ex2(fmaf(s, scale_log2, -m_new));
+          psum += p8[e];
+        }
+        pk[c8] = pack8(p8);
       }
-      tc_commit(bar_o);
-    }
-  }
+      l_part = l_part * alpha + psum;
+      m_used = m_new;
 
-  mbar_wait(bar_o, (njb - 1) & 1);
-  __syncwarp();
-  tc_fence_after();
-  const float inv_l = 1.f / l_run;
-  bf16* orow = out + static_cast<size_t>(tok0 + row_seq) * ld_out + h * DH;
+      if (j > 0) {
+        mbar_wait(bar_o, (j - 1) & 1);  // PV(j-1) retired: P smem and O are free
+        __syncwarp();
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {  // rare after the first blocks; my 64 of O's columns
 #pragma unroll
-  for (int c = 0; c < DH / 32; ++c) {
-    uint32_t r[32];
-    tmem_ld32(tmem_O + lane_base + c * 32, r);
-    tmem_ld_wait();
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_O + lane_base + hc * 64 + c * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float o8[8] = {__uint_as_float(r[i * 8 + 0]) * inv_l, __uint_as_float(r[i * 8 + 1]) * inv_l,
-                           __uint_as_float(r[i * 8 + 2]) * inv_l, __uint_as_float(r[i * 8 + 3]) * inv_l,
-                           __uint_as_float(r[i * 8 + 4]) * inv_l, __uint_as_float(r[i * 8 + 5]) * inv_l,
-                           __uint_as_float(r[i * 8 + 6]) * inv_l, __uint_as_float(r[i * 8 + 7]) * inv_l};
-      reinterpret_cast<uint4*>(orow + c * 32)[i] = pack8(o8);
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st32(tmem_O + lane_base + hc * 64 + c * 32, r);
+          }
+          tmem_st_wait();
+        }
+      }
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8)
+        *reinterpret_cast<uint4*>(sP + sw128_offset(row_local, hc * 4 + c8)) = pk[c8];
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
     }
+
+    mbar_wait(bar_o, (njb - 1) & 1);
+    __syncwarp();
+    tc_fence_after();
+    // combine the two half-row sums through smem (P is dead now)
+    float* sL = reinterpret_cast<float*>(sP);
+    sL[hc * 128 + row_local] = l_part;
+    compute_bar_sync();
+    const float l_row = l_part + sL[(hc ^ 1) * 128 + row_local];
+    bf16* orow = out + static_cast<size_t>(tok0 + row_seq) * ld_out + h * DH + hc * 64;
+    tmem_row64_to_global(tmem_O + lane_base + hc * 64, orow, 1.f / l_row);
+    if (hc == 0)
+      lse2[static_cast<size_t>(h) * (static_cast<size_t>(B) * S) + tok0 + row_seq] =
+          m_used + log2f(l_row);
   }
-  lse2[static_cast<size_t>(h) * (static_cast<size_t>(B) * S) + tok0 + row_seq] =
-      m_used + log2f(l_run);
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, FWD_TMEM_COLS);
   }
@@ -280,7 +329,7 @@ constexpr int KV_SMEM = 2 * ATOM128 /*K*/ + 2 * ATOM128 /*V*/ + 3 * 2 * ATOM64 /
 // S^T[2]: [0,64) [64,128)   dP^T[2]: [128,192) [192,256)   dV: [256,384)   dK: [384,512)
 constexpr int KV_TMEM_COLS = 512;
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                      const float* __restrict__ lse2, const float* __restrict__ delta,
                      bf16* __restrict__ dqkv, int ld_qkv, int k_off, int v_off, int B, int S, int H,
@@ -293,12 +342,13 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   uint8_t* sdO = sQ + 3 * 2 * ATOM64;
   uint8_t* sP = sdO + 3 * 2 * ATOM64;       // P^T  [128 kv x 64 q]
   uint8_t* sdS = sP + ATOM128;              // dS^T [128 kv x 64 q]
-  float* sStat = reinterpret_cast<float*>(sdS + ATOM128);  // [2 bufs][lse 64 | delta 64]
+  float* sStat = reinterpret_cast<float*>(sdS + ATOM128);  // [2 bufs][lse 64 | delta*scale 64]
   uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sStat + 2 * 128);
   uint64_t* bar_q = bar_kv + 1;  // [3]
-  uint64_t* bar_s = bar_q + 3;   // [2]
-  uint64_t* bar_d = bar_s + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 1);
+  uint64_t* bar_s = bar_q + 3;   // [2] S^T, dP^T (it) in TMEM
+  uint64_t* bar_d = bar_s + 2;   //     dV/dK MMAs (it) retired
+  uint64_t* bar_p = bar_d + 1;   //     P^T, dS^T (it) in smem (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_p + 1);
 
   const int G = H / Hkv;
   const int jb = blockIdx.x / (B * Hkv);  // earliest key blocks (longest query loops) first
@@ -308,7 +358,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   const int kv0 = jb * BWD_BKV;
   const int nqb = S / BWD_BQ - 2 * jb;  // query blocks [2 jb, S/64) see this key block
   const int n_iter = G * nqb;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t Ttot = static_cast<size_t>(B) * S;
 
   if (tid == 0) {
@@ -318,9 +368,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     for (int i = 0; i < 3; ++i) mbar_init(&bar_q[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&bar_s[i], 1);
     mbar_init(bar_d, 1);
+    mbar_init(bar_p, NCOMPUTE);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, KV_TMEM_COLS);
+  if (warp == 8) tmem_alloc(tmem_slot, KV_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -330,154 +381,135 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   auto iter_head = [&](int it) { return hk * G + it / nqb; };
   auto iter_qrow = [&](int it) { return (2 * jb + it % nqb) * BWD_BQ; };  // inside the sequence
 
-  auto load_q = [&](int it) {
-    const int buf = it % 3;
-    mbar_arrive_expect_tx(&bar_q[buf], 4 * ATOM64);
-    const int h = iter_head(it), row = tok0 + iter_qrow(it);
+  if (warp == 8) {
+    // =============================== control ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_st = make_idesc_bf16(128, BWD_BQ, false, false);  // S^T, dP^T
+      constexpr uint32_t idesc_dv = make_idesc_bf16(128, DH, false, true);       // dV, dK
+      auto load_q = [&](int it) {
+        const int buf = it % 3;
+        mbar_arrive_expect_tx(&bar_q[buf], 4 * ATOM64);
+        const int h = iter_head(it), row = tok0 + iter_qrow(it);
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      tma_load_2d(sQ + (buf * 2 + a) * ATOM64, &tm_qkv, &bar_q[buf], h * DH + a * 64, row);
-      tma_load_2d(sdO + (buf * 2 + a) * ATOM64, &tm_do, &bar_q[buf], h * DH + a * 64, row);
-    }
-  };
-  auto load_stats = [&](int it) {  // all 128 threads
-    const int h = iter_head(it);
-    const size_t base = static_cast<size_t>(h) * Ttot + tok0 + iter_qrow(it);
-    sStat[(it & 1) * 128 + tid] = (tid < 64) ? lse2[base + tid] : delta[base + tid - 64];
-  };
-  constexpr uint32_t idesc_st = make_idesc_bf16(128, BWD_BQ, false, false);  // S^T, dP^T
-  constexpr uint32_t idesc_dv = make_idesc_bf16(128, DH, false, true);       // dV, dK
-  auto issue_scores = [&](int it) {  // S^T(it) = K Q^T, dP^T(it) = V dO^T -> TMEM buffers it & 1
-    const int qb = it % 3;
-    mma_kmajor_dh(tmem_base + (it & 1) * 64, smem_u32(sK), ATOM128, smem_u32(sQ + qb * 2 * ATOM64),
-                  ATOM64, idesc_st);
-    mma_kmajor_dh(tmem_base + 128 + (it & 1) * 64, smem_u32(sV), ATOM128,
-                  smem_u32(sdO + qb * 2 * ATOM64), ATOM64, idesc_st);
-    tc_commit(&bar_s[it & 1]);
-  };
-
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_kv, 4 * ATOM128);
+        for (int a = 0; a < 2; ++a) {
+          tma_load_2d(sQ + (buf * 2 + a) * ATOM64, &tm_qkv, &bar_q[buf], h * DH + a * 64, row);
+          tma_load_2d(sdO + (buf * 2 + a) * ATOM64, &tm_do, &bar_q[buf], h * DH + a * 64, row);
+        }
+      };
+      auto issue_scores = [&](int it) {  // S^T(it) = K Q^T, dP^T(it) = V dO^T -> TMEM buffers it & 1
+        const int qb = it % 3;
+        mma_kmajor_dh(tmem_base + (it & 1) * 64, smem_u32(sK), ATOM128,
+                      smem_u32(sQ + qb * 2 * ATOM64), ATOM64, idesc_st);
+        mma_kmajor_dh(tmem_base + 128 + (it & 1) * 64, smem_u32(sV), ATOM128,
+                      smem_u32(sdO + qb * 2 * ATOM64), ATOM64, idesc_st);
+        tc_commit(&bar_s[it & 1]);
+      };
+      mbar_arrive_expect_tx(bar_kv, 4 * ATOM128);
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        tma_load_2d(sK + a * ATOM128 + r * ATOM64, &tm_qkv, bar_kv, k_off + hk * DH + a * 64,
-                    tok0 + kv0 + r * 64);
-        tma_load_2d(sV + a * ATOM128 + r * ATOM64, &tm_qkv, bar_kv, v_off + hk * DH + a * 64,
-                    tok0 + kv0 + r * 64);
-      }
-    load_q(0);
-    if (n_iter > 1) load_q(1);
-    mbar_wait(bar_kv, 0);
-    mbar_wait(&bar_q[0], 0);
-    tc_fence_after();
-    issue_scores(0);
-  }
-  load_stats(0);
-  __syncthreads();
-
-  const int row_local = tid;                 // TMEM lane == key row inside the block
-  const int kv_seq = kv0 + row_local;        // key position inside the sequence
-  const uint32_t lane_base = (warp * 32u) << 16;
-
-  for (int it = 0; it < n_iter; ++it) {
-    const int tb = it & 1;
-    const int q_seq0 = iter_qrow(it);
-    if (it + 1 < n_iter) load_stats(it + 1);  // other buffer; visible after this iteration's barrier
-    if (tid == 0 && it + 1 < n_iter) {
-      mbar_wait(&bar_q[(it + 1) % 3], ((it + 1) / 3) & 1);
+        for (int r = 0; r < 2; ++r) {
+          tma_load_2d(sK + a * ATOM128 + r * ATOM64, &tm_qkv, bar_kv, k_off + hk * DH + a * 64,
+                      tok0 + kv0 + r * 64);
+          tma_load_2d(sV + a * ATOM128 + r * ATOM64, &tm_qkv, bar_kv, v_off + hk * DH + a * 64,
+                      tok0 + kv0 + r * 64);
+        }
+      load_q(0);
+      if (n_iter > 1) load_q(1);
+      if (n_iter > 2) load_q(2);
+      mbar_wait(bar_kv, 0);
+      mbar_wait(&bar_q[0], 0);
       tc_fence_after();
-      issue_scores(it + 1);  // runs under this block's softmax
+      issue_scores(0);
+      for (int it = 0; it < n_iter; ++it) {
+        if (it + 1 < n_iter) {  // TMEM score buffers (it+1)&1 were drained before bar_p(it-1)
+          mbar_wait(&bar_q[(it + 1) % 3], ((it + 1) / 3) & 1);
+          tc_fence_after();
+          issue_scores(it + 1);
+        }
+        mbar_wait(bar_p, it & 1);
+        tc_fence_after();
+        const int qb = it % 3;
+        // dV += P^T dO, dK += dS^T Q : A K-major [128 kv x 64 q], B MN-major (N = dh, K = q rows)
+        mma_a64_bmn(tmem_dV, smem_u32(sP), smem_u32(sdO + qb * 2 * ATOM64), idesc_dv, it != 0);
+        mma_a64_bmn(tmem_dK, smem_u32(sdS), smem_u32(sQ + qb * 2 * ATOM64), idesc_dv, it != 0);
+        tc_commit(bar_d);
+        if (it + 3 < n_iter) {  // block it+3 reuses this iteration's Q/dO buffer
+          mbar_wait(bar_d, it & 1);
+          load_q(it + 3);
+        }
+      }
     }
-    mbar_wait(&bar_s[tb], (it >> 1) & 1);
-    if (it > 0) mbar_wait(bar_d, (it - 1) & 1);  // dV/dK(it-1) retired: sP, sdS, Q/dO buf (it-1)%3 free
-    __syncwarp();
-    tc_fence_after();
-    if (tid == 0 && it + 2 < n_iter) load_q(it + 2);
+  } else {
+    // =============================== compute ===============================
+    const int q = warp & 3, hc = warp >> 2;
+    const int row_local = q * 32 + lane;       // TMEM lane == key row inside the block
+    const int kv_seq = kv0 + row_local;        // key position inside the sequence
+    const uint32_t lane_base = (q * 32u) << 16;
+    auto load_stats = [&](int it) {  // 128 of the compute threads
+      if (tid < 128) {
+        const int h = iter_head(it);
+        const size_t base = static_cast<size_t>(h) * Ttot + tok0 + iter_qrow(it);
+        sStat[(it & 1) * 128 + tid] = (tid < 64) ? lse2[base + tid] : delta[base + tid - 64] * scale;
+      }
+    };
+    load_stats(0);
+    compute_bar_sync();
 
-    const float* st = sStat + tb * 128;
-    const bool diag = (q_seq0 < kv0 + BWD_BKV);  // some (q, kv) pairs of this block are masked
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int it = 0; it < n_iter; ++it) {
+      const int tb = it & 1;
+      const int q_seq0 = iter_qrow(it);
+      if (it + 1 < n_iter) load_stats(it + 1);  // other buffer; published by this iteration's bar.sync
+      mbar_wait(&bar_s[tb], (it >> 1) & 1);
+      if (it > 0) mbar_wait(bar_d, (it - 1) & 1);  // dV/dK(it-1) retired: sP, sdS free
+      __syncwarp();
+      tc_fence_after();
       uint32_t s_r[32], dp_r[32];
-      tmem_ld32(tmem_base + tb * 64 + lane_base + half * 32, s_r);
-      tmem_ld32(tmem_base + 128 + tb * 64 + lane_base + half * 32, dp_r);
+      tmem_ld32(tmem_base + tb * 64 + lane_base + hc * 32, s_r);
+      tmem_ld32(tmem_base + 128 + tb * 64 + lane_base + hc * 32, dp_r);
       tmem_ld_wait();
+      const float4* st_lse = reinterpret_cast<const float4*>(sStat + tb * 128 + hc * 32);
+      const float4* st_dl = reinterpret_cast<const float4*>(sStat + tb * 128 + 64 + hc * 32);
+      const bool diag = (q_seq0 < kv0 + BWD_BKV);  // some (q, kv) pairs of this block are masked
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
+        const float4 l0 = st_lse[c8 * 2], l1 = st_lse[c8 * 2 + 1];
+        const float4 d0 = st_dl[c8 * 2], d1 = st_dl[c8 * 2 + 1];
+        const float lse8[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const float dl8[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
         float p[8], ds[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int c = half * 32 + c8 * 8 + e;  // query column inside the block
-          float pv = exp2f(__uint_as_float(s_r[c8 * 8 + e]) * scale_log2 - st[c]);
+          const int c = hc * 32 + c8 * 8 + e;  // query column inside the block
+          float pv = ex2(fmaf(__uint_as_float(s_r[c8 * 8 + e]), scale_log2, -lse8[e]));
           if (diag && (q_seq0 + c < kv_seq)) pv = 0.f;
           p[e] = pv;
-          ds[e] = pv * (__uint_as_float(dp_r[c8 * 8 + e]) - st[64 + c]) * scale;
+          // dS = P (dP - delta) * scale, with delta*scale precomputed
+          ds[e] = pv * fmaf(__uint_as_float(dp_r[c8 * 8 + e]), scale, -dl8[e]);
         }
-        const uint32_t off = sw128_offset(row_local, half * 4 + c8);
+        const uint32_t off = sw128_offset(row_local, hc * 4 + c8);
         *reinterpret_cast<uint4*>(sP + off) = pack8(p);
         *reinterpret_cast<uint4*>(sdS + off) = pack8(ds);
       }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+      compute_bar_sync();  // stats(it+1) visible; stats(it) no longer read
     }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
 
-    if (tid == 0) {
-      tc_fence_after();
-      const int qb = it % 3;
-      // dV += P^T dO, dK += dS^T Q : A K-major [128 kv x 64 q], B MN-major (N = dh, K = q rows)
-#pragma unroll
-      for (int k = 0; k < BWD_BQ / 16; ++k) {
-        const uint64_t dp = make_smem_desc(smem_u32(sP) + k * 32, 16, 1024);
-        const uint64_t ddo = make_smem_desc(smem_u32(sdO + qb * 2 * ATOM64) + k * 2048, ATOM64, 1024);
-        tc_mma_bf16(tmem_dV, dp, ddo, idesc_dv, (it | k) != 0);
-      }
-#pragma unroll
-      for (int k = 0; k < BWD_BQ / 16; ++k) {
-        const uint64_t dds = make_smem_desc(smem_u32(sdS) + k * 32, 16, 1024);
-        const uint64_t dq = make_smem_desc(smem_u32(sQ + qb * 2 * ATOM64) + k * 2048, ATOM64, 1024);
-        tc_mma_bf16(tmem_dK, dds, dq, idesc_dv, (it | k) != 0);
-      }
-      tc_commit(bar_d);
-    }
-  }
-
-  mbar_wait(bar_d, (n_iter - 1) & 1);
-  __syncwarp();
-  tc_fence_after();
-  // dV, dK: lane = key row, 128 dh columns each
-  bf16* dvrow = dqkv + static_cast<size_t>(tok0 + kv_seq) * ld_qkv + v_off + hk * DH;
-  bf16* dkrow = dqkv + static_cast<size_t>(tok0 + kv_seq) * ld_qkv + k_off + hk * DH;
-#pragma unroll
-  for (int c = 0; c < DH / 32; ++c) {
-    uint32_t r[32];
-    tmem_ld32(tmem_dV + lane_base + c * 32, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float o8[8] = {__uint_as_float(r[i * 8 + 0]), __uint_as_float(r[i * 8 + 1]),
-                           __uint_as_float(r[i * 8 + 2]), __uint_as_float(r[i * 8 + 3]),
-                           __uint_as_float(r[i * 8 + 4]), __uint_as_float(r[i * 8 + 5]),
-                           __uint_as_float(r[i * 8 + 6]), __uint_as_float(r[i * 8 + 7])};
-      reinterpret_cast<uint4*>(dvrow + c * 32)[i] = pack8(o8);
-    }
-    tmem_ld32(tmem_dK + lane_base + c * 32, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float o8[8] = {__uint_as_float(r[i * 8 + 0]), __uint_as_float(r[i * 8 + 1]),
-                           __uint_as_float(r[i * 8 + 2]), __uint_as_float(r[i * 8 + 3]),
-                           __uint_as_float(r[i * 8 + 4]), __uint_as_float(r[i * 8 + 5]),
-                           __uint_as_float(r[i * 8 + 6]), __uint_as_float(r[i * 8 + 7])};
-      reinterpret_cast<uint4*>(dkrow + c * 32)[i] = pack8(o8);
-    }
+    mbar_wait(bar_d, (n_iter - 1) & 1);
+    __syncwarp();
+    tc_fence_after();
+    // dV, dK: lane = key row; this thread stores 64 of the 128 dh columns of each
+    bf16* dvrow = dqkv + static_cast<size_t>(tok0 + kv_seq) * ld_qkv + v_off + hk * DH + hc * 64;
+    bf16* dkrow = dqkv + static_cast<size_t>(tok0 + kv_seq) * ld_qkv + k_off + hk * DH + hc * 64;
+    tmem_row64_to_global(tmem_dV + lane_base + hc * 64, dvrow, 1.f);
+    tmem_row64_to_global(tmem_dK + lane_base + hc * 64, dkrow, 1.f);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, KV_TMEM_COLS);
   }
@@ -492,7 +524,7 @@ constexpr int DQ_SMEM = 2 * ATOM128 /*Q*/ + 2 * ATOM128 /*dO*/ + 3 * 2 * ATOM64 
 // S[2]: [0,64) [64,128)   dP[2]: [128,192) [192,256)   dQ: [256,384)
 constexpr int DQ_TMEM_COLS = 512;
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const float* __restrict__ lse2, const float* __restrict__ delta,
                    bf16* __restrict__ dqkv, int ld_qkv, int k_off, int v_off, int B, int S, int H,
@@ -505,10 +537,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* sV = sK + 3 * 2 * ATOM64;
   uint8_t* sdS = sV + 3 * 2 * ATOM64;      // dS [128 q x 64 kv]
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(sdS + ATOM128);
-  uint64_t* bar_kv = bar_q + 1;  // [3]
-  uint64_t* bar_s = bar_kv + 3;  // [2]
+  uint64_t* bar_kv = bar_q + 1;   // [3]
+  uint64_t* bar_s = bar_kv + 3;   // [2]
   uint64_t* bar_dq = bar_s + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_dq + 1);
+  uint64_t* bar_p = bar_dq + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_p + 1);
 
   const int nq = S / DQ_BQ;
   const int bh = blockIdx.x % (B * H);
@@ -518,7 +551,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const int tok0 = b * S;
   const int q0 = qi * DQ_BQ;
   const int njb = 2 * qi + 2;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -527,135 +560,118 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     for (int i = 0; i < 3; ++i) mbar_init(&bar_kv[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&bar_s[i], 1);
     mbar_init(bar_dq, 1);
+    mbar_init(bar_p, NCOMPUTE);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, DQ_TMEM_COLS);
+  if (warp == 8) tmem_alloc(tmem_slot, DQ_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_dQ = tmem_base + 256;
 
-  auto load_kv = [&](int j) {
-    const int buf = j % 3;
-    mbar_arrive_expect_tx(&bar_kv[buf], 4 * ATOM64);
+  if (warp == 8) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, DQ_BKV, false, false);  // S, dP
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, DH, false, true);      // dQ
+      auto load_kv = [&](int j) {
+        const int buf = j % 3;
+        mbar_arrive_expect_tx(&bar_kv[buf], 4 * ATOM64);
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      tma_load_2d(sK + (buf * 2 + a) * ATOM64, &tm_qkv, &bar_kv[buf], k_off + hk * DH + a * 64,
-                  tok0 + j * DQ_BKV);
-      tma_load_2d(sV + (buf * 2 + a) * ATOM64, &tm_qkv, &bar_kv[buf], v_off + hk * DH + a * 64,
-                  tok0 + j * DQ_BKV);
-    }
-  };
-  constexpr uint32_t idesc_s = make_idesc_bf16(128, DQ_BKV, false, false);  // S, dP
-  constexpr uint32_t idesc_dq = make_idesc_bf16(128, DH, false, true);      // dQ
-  auto issue_scores = [&](int j) {  // S(j) = Q K^T, dP(j) = dO V^T -> TMEM buffers j & 1
-    const int kb = j % 3;
-    mma_kmajor_dh(tmem_base + (j & 1) * 64, smem_u32(sQ), ATOM128, smem_u32(sK + kb * 2 * ATOM64),
-                  ATOM64, idesc_s);
-    mma_kmajor_dh(tmem_base + 128 + (j & 1) * 64, smem_u32(sdO), ATOM128,
-                  smem_u32(sV + kb * 2 * ATOM64), ATOM64, idesc_s);
-    tc_commit(&bar_s[j & 1]);
-  };
-
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, 4 * ATOM128);
+        for (int a = 0; a < 2; ++a) {
+          tma_load_2d(sK + (buf * 2 + a) * ATOM64, &tm_qkv, &bar_kv[buf], k_off + hk * DH + a * 64,
+                      tok0 + j * DQ_BKV);
+          tma_load_2d(sV + (buf * 2 + a) * ATOM64, &tm_qkv, &bar_kv[buf], v_off + hk * DH + a * 64,
+                      tok0 + j * DQ_BKV);
+        }
+      };
+      auto issue_scores = [&](int j) {  // S(j) = Q K^T, dP(j) = dO V^T -> TMEM buffers j & 1
+        const int kb = j % 3;
+        mma_kmajor_dh(tmem_base + (j & 1) * 64, smem_u32(sQ), ATOM128, smem_u32(sK + kb * 2 * ATOM64),
+                      ATOM64, idesc_s);
+        mma_kmajor_dh(tmem_base + 128 + (j & 1) * 64, smem_u32(sdO), ATOM128,
+                      smem_u32(sV + kb * 2 * ATOM64), ATOM64, idesc_s);
+        tc_commit(&bar_s[j & 1]);
+      };
+      mbar_arrive_expect_tx(bar_q, 4 * ATOM128);
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        tma_load_2d(sQ + a * ATOM128 + r * ATOM64, &tm_qkv, bar_q, h * DH + a * 64, tok0 + q0 + r * 64);
-        tma_load_2d(sdO + a * ATOM128 + r * ATOM64, &tm_do, bar_q, h * DH + a * 64, tok0 + q0 + r * 64);
-      }
-    load_kv(0);
-    load_kv(1);  // njb >= 2 always
-    mbar_wait(bar_q, 0);
-    mbar_wait(&bar_kv[0], 0);
-    tc_fence_after();
-    issue_scores(0);
-  }
-
-  const int row_local = tid;
-  const int row_seq = q0 + row_local;
-  const uint32_t lane_base = (warp * 32u) << 16;
-  const size_t stat_idx = static_cast<size_t>(h) * (static_cast<size_t>(B) * S) + tok0 + row_seq;
-  const float my_lse = lse2[stat_idx];
-  const float my_delta = delta[stat_idx];
-
-  for (int j = 0; j < njb; ++j) {
-    const int tb = j & 1;
-    if (tid == 0 && j + 1 < njb) {
-      mbar_wait(&bar_kv[(j + 1) % 3], ((j + 1) / 3) & 1);
+        for (int r = 0; r < 2; ++r) {
+          tma_load_2d(sQ + a * ATOM128 + r * ATOM64, &tm_qkv, bar_q, h * DH + a * 64, tok0 + q0 + r * 64);
+          tma_load_2d(sdO + a * ATOM128 + r * ATOM64, &tm_do, bar_q, h * DH + a * 64, tok0 + q0 + r * 64);
+        }
+      load_kv(0);
+      load_kv(1);  // njb >= 2 always
+      if (njb > 2) load_kv(2);
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_kv[0], 0);
       tc_fence_after();
-      issue_scores(j + 1);
+      issue_scores(0);
+      for (int j = 0; j < njb; ++j) {
+        if (j + 1 < njb) {
+          mbar_wait(&bar_kv[(j + 1) % 3], ((j + 1) / 3) & 1);
+          tc_fence_after();
+          issue_scores(j + 1);
+        }
+        mbar_wait(bar_p, j & 1);
+        tc_fence_after();
+        // dQ += dS K : A K-major [128 q x 64 kv], B = K as MN-major (N = dh, K = kv rows)
+        mma_a64_bmn(tmem_dQ, smem_u32(sdS), smem_u32(sK + (j % 3) * 2 * ATOM64), idesc_dq, j != 0);
+        tc_commit(bar_dq);
+        if (j + 3 < njb) {  // block j+3 reuses this iteration's K/V buffer
+          mbar_wait(bar_dq, j & 1);
+          load_kv(j + 3);
+        }
+      }
     }
-    mbar_wait(&bar_s[tb], (j >> 1) & 1);
-    if (j > 0) mbar_wait(bar_dq, (j - 1) & 1);  // dQ MMA (j-1) retired: sdS and K/V buf (j-1)%3 free
-    __syncwarp();
-    tc_fence_after();
-    if (tid == 0 && j + 2 < njb) load_kv(j + 2);
+  } else {
+    const int q = warp & 3, hc = warp >> 2;
+    const int row_local = q * 32 + lane;
+    const int row_seq = q0 + row_local;
+    const uint32_t lane_base = (q * 32u) << 16;
+    const size_t stat_idx = static_cast<size_t>(h) * (static_cast<size_t>(B) * S) + tok0 + row_seq;
+    const float my_lse = lse2[stat_idx];
+    const float my_dl = delta[stat_idx] * scale;
 
-    const int col0 = j * DQ_BKV;
-    const bool diag = (col0 + DQ_BKV - 1) > q0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int j = 0; j < njb; ++j) {
+      const int tb = j & 1;
+      mbar_wait(&bar_s[tb], (j >> 1) & 1);
+      if (j > 0) mbar_wait(bar_dq, (j - 1) & 1);  // dQ MMA (j-1) retired: sdS free
+      __syncwarp();
+      tc_fence_after();
       uint32_t s_r[32], dp_r[32];
-      tmem_ld32(tmem_base + tb * 64 + lane_base + half * 32, s_r);
-      tmem_ld32(tmem_base + 128 + tb * 64 + lane_base + half * 32, dp_r);
+      tmem_ld32(tmem_base + tb * 64 + lane_base + hc * 32, s_r);
+      tmem_ld32(tmem_base + 128 + tb * 64 + lane_base + hc * 32, dp_r);
       tmem_ld_wait();
+      const int col0 = j * DQ_BKV + hc * 32;
+      const bool diag = (j * DQ_BKV + DQ_BKV - 1) > q0;
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         float ds[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int c = half * 32 + c8 * 8 + e;  // key column inside the block
-          float pv = exp2f(__uint_as_float(s_r[c8 * 8 + e]) * scale_log2 - my_lse);
-          if (diag && (col0 + c > row_seq)) pv = 0.f;
-          ds[e] = pv * (__uint_as_float(dp_r[c8 * 8 + e]) - my_delta) * scale;
+          float pv = ex2(fmaf(__uint_as_float(s_r[c8 * 8 + e]), scale_log2, -my_lse));
+          if (diag && (col0 + c8 * 8 + e > row_seq)) pv = 0.f;
+          ds[e] = pv * fmaf(__uint_as_float(dp_r[c8 * 8 + e]), scale, -my_dl);
         }
-        *reinterpret_cast<uint4*>(sdS + sw128_offset(row_local, half * 4 + c8)) = pack8(ds);
+        *reinterpret_cast<uint4*>(sdS + sw128_offset(row_local, hc * 4 + c8)) = pack8(ds);
       }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
     }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
 
-    if (tid == 0) {
-      tc_fence_after();
-      const int kb = j % 3;
-      // dQ += dS K : A K-major [128 q x 64 kv], B = K as MN-major (N = dh, K = kv rows)
-#pragma unroll
-      for (int k = 0; k < DQ_BKV / 16; ++k) {
-        const uint64_t da = make_smem_desc(smem_u32(sdS) + k * 32, 16, 1024);
-        const uint64_t db = make_smem_desc(smem_u32(sK + kb * 2 * ATOM64) + k * 2048, ATOM64, 1024);
-        tc_mma_bf16(tmem_dQ, da, db, idesc_dq, (j | k) != 0);
-      }
-      tc_commit(bar_dq);
-    }
-  }
-
-  mbar_wait(bar_dq, (njb - 1) & 1);
-  __syncwarp();
-  tc_fence_after();
-  bf16* dqrow = dqkv + static_cast<size_t>(tok0 + row_seq) * ld_qkv + h * DH;
-#pragma unroll
-  for (int c = 0; c < DH / 32; ++c) {
-    uint32_t r[32];
-    tmem_ld32(tmem_dQ + lane_base + c * 32, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float o8[8] = {__uint_as_float(r[i * 8 + 0]), __uint_as_float(r[i * 8 + 1]),
-                           __uint_as_float(r[i * 8 + 2]), __uint_as_float(r[i * 8 + 3]),
-                           __uint_as_float(r[i * 8 + 4]), __uint_as_float(r[i * 8 + 5]),
-                           __uint_as_float(r[i * 8 + 6]), __uint_as_float(r[i * 8 + 7])};
-      reinterpret_cast<uint4*>(dqrow + c * 32)[i] = pack8(o8);
-    }
+    mbar_wait(bar_dq, (njb - 1) & 1);
+    __syncwarp();
+    tc_fence_after();
+    bf16* dqrow = dqkv + static_cast<size_t>(tok0 + row_seq) * ld_qkv + h * DH + hc * 64;
+    tmem_row64_to_global(tmem_dQ + lane_base + hc * 64, dqrow, 1.f);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, DQ_TMEM_COLS);
   }
@@ -681,8 +697,8 @@ void attention_fwd(const void* qkv, int ld_qkv, int k_off, int v_off, void* out,
   }
   const int grid = (S / FWD_BQ) * B * H;
   const float scale_log2 = scale * 1.4426950408889634f;
-  attn_fwd_kernel<<<grid, 128, FWD_SMEM, s>>>(tm, static_cast<bf16*>(out), ld_out, lse2, k_off,
-                                              v_off, B, S, H, Hkv, scale_log2);
+  attn_fwd_kernel<<<grid, NTHREADS, FWD_SMEM, s>>>(tm, static_cast<bf16*>(out), ld_out, lse2, k_off,
+                                                   v_off, B, S, H, Hkv, scale_log2);
   B200W_CUDA(cudaGetLastError());
 }
 
@@ -703,11 +719,11 @@ void attention_bwd(const void* qkv, int ld_qkv, int k_off, int v_off, const void
     attr = true;
   }
   const float scale_log2 = scale * 1.4426950408889634f;
-  attn_bwd_dkdv_kernel<<<(S / BWD_BKV) * B * Hkv, 128, KV_SMEM, s>>>(
+  attn_bwd_dkdv_kernel<<<(S / BWD_BKV) * B * Hkv, NTHREADS, KV_SMEM, s>>>(
       tm_qkv, tm_do, lse2, delta, static_cast<bf16*>(dqkv), ld_qkv, k_off, v_off, B, S, H, Hkv, scale,
       scale_log2);
   B200W_CUDA(cudaGetLastError());
-  attn_bwd_dq_kernel<<<(S / DQ_BQ) * B * H, 128, DQ_SMEM, s>>>(
+  attn_bwd_dq_kernel<<<(S / DQ_BQ) * B * H, NTHREADS, DQ_SMEM, s>>>(
       tm_qkv, tm_do, lse2, delta, static_cast<bf16*>(dqkv), ld_qkv, k_off, v_off, B, S, H, Hkv, scale,
       scale_log2);
   B200W_CUDA(cudaGetLastError());

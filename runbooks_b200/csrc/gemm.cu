@@ -495,6 +495,12 @@ void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int 
                   (reinterpret_cast<uintptr_t>(D) & 15) == 0,
               "operands must be 16-byte aligned");
   if (block_n == 0) {
+    // Large problems: CTA pairs (256 x 256 tiles, cta_group::2) — measured 8-11 % faster than the
+    // single-CTA kernel at Llama-2-7B shapes (profiles/r01_perf_probe_pair.json).
+    const long tiles_pair = static_cast<long>((M + 255) / 256) * ((N + 255) / 256);
+    if (M >= 256 && N >= 256 && tiles_pair >= sm_count() / 2) block_n = 512;
+  }
+  if (block_n == 0) {
     // 256-wide tiles halve A re-reads; fall back to 128 when that would leave SMs idle.
     const long tiles256 = static_cast<long>((M + 127) / 128) * ((N + 255) / 256);
     block_n = (N >= 256 && tiles256 >= sm_count()) ? 256 : 128;

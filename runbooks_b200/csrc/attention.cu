@@ -2,9 +2,11 @@
 // Oracle: F.scaled_dot_product_attention(q, k, v, is_causal=True) as called by HF
 // LlamaAttention with _attn_implementation == "sdpa" (SURVEY.md §8 a7).
 //
-// Common structure of the three kernels (CTA = 9 warps):
-//   warp 8        control: every TMA load and every tcgen05.mma is issued by its lane 0, which
-//                 also owns all the "is this buffer free" waits;
+// Common structure of the three kernels (CTA = 10 warps):
+//   warp 9        TMA producer (lane 0): every load, gated by per-buffer "free" mbarriers;
+//   warp 8        MMA issuer (lane 0): a lean in-order stream of tcgen05.mma with precomputed
+//                 descriptor words (profiles/r01_ncu_attention_v3.txt: a single control thread doing
+//                 both jobs executed ~380 SASS instructions per block and WAS the bottleneck);
 //   warps 0..7    compute: a TMEM lane is a matrix row; warp w touches lane quarter (w & 3) and
 //                 column half (w >> 2) of each 64-column score block, i.e. TWO threads per row, so
 //                 every SM sub-partition has >= 2 warps of MUFU/FMA work to overlap;
@@ -34,7 +36,7 @@ constexpr int DH = 128;
 constexpr int ATOM64 = 64 * 128;    // bytes of a [64 rows x 128 B] swizzle-atom column
 constexpr int ATOM128 = 128 * 128;  // bytes of a [128 rows x 128 B] one
 constexpr int NCOMPUTE = 256;
-constexpr int NTHREADS = 288;
+constexpr int NTHREADS = 320;  // 8 compute warps + MMA warp (8) + TMA warp (9)
 constexpr float LAZY_RESCALE_LOG2 = 8.f;
 
 __device__ __forceinline__ void require_1024_aligned(const void* p) {
@@ -52,27 +54,54 @@ __device__ __forceinline__ void compute_bar_sync() {  // the 256 compute threads
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
-// K-major operands whose rows are 128 B (64 elements) wide, 2 atoms side by side along the
-// contraction (dh = 128), `*_atom_bytes` apart. Issues dh/16 = 8 MMAs into tmem_d.
-__device__ __forceinline__ void mma_kmajor_dh(uint32_t tmem_d, uint32_t a_base, uint32_t a_atom_bytes,
-                                              uint32_t b_base, uint32_t b_atom_bytes, uint32_t idesc) {
+// The MMA-issuing thread is a single in-order instruction stream: everything it executes per
+// MMA delays the tensor pipe. Descriptors are therefore kept as precomputed 32-bit halves — the
+// high word is a constant per layout, the low word is (smem address >> 4) | LBO field, and
+// stepping along K is one integer add.
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024, version 1, SW128
+__device__ __forceinline__ uint32_t desc_lo_k(uint32_t smem_addr) {   // K-major (LBO unused = 16)
+  return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t smem_addr) {  // MN-major, atoms ATOM64 apart
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((ATOM64 >> 4) << 16);
+}
+template <bool ACC>
+__device__ __forceinline__ void mma_raw(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(ACC ? 1u : 0u)
+      : "memory");
+}
+__device__ __forceinline__ void mma_raw_dyn(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                            uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// K-major x K-major over dh = 128: operands are 2 atoms along the contraction, `*_atom16` apart
+// (in 16-byte units). a_lo / b_lo: desc_lo_k() of the first atom. 8 MMAs, the first overwrites.
+__device__ __forceinline__ void mma_kmajor_dh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_atom16,
+                                              uint32_t b_lo, uint32_t b_atom16, uint32_t idesc) {
+  mma_raw<false>(tmem_d, a_lo, b_lo, idesc);
 #pragma unroll
-  for (int k = 0; k < DH / 16; ++k) {
-    const uint32_t ko = (k % 4) * 32;
-    const uint64_t da = make_smem_desc(a_base + (k / 4) * a_atom_bytes + ko, 16, 1024);
-    const uint64_t db = make_smem_desc(b_base + (k / 4) * b_atom_bytes + ko, 16, 1024);
-    tc_mma_bf16(tmem_d, da, db, idesc, k != 0);
-  }
+  for (int k = 1; k < DH / 16; ++k)
+    mma_raw<true>(tmem_d, a_lo + (k / 4) * a_atom16 + (k % 4) * 2, b_lo + (k / 4) * b_atom16 + (k % 4) * 2,
+                  idesc);
 }
 // D (+)= A[128 x 64, K-major, one atom] * B[MN-major: N = dh (2 atoms, ATOM64 apart), K = 64 rows]
-__device__ __forceinline__ void mma_a64_bmn(uint32_t tmem_d, uint32_t a_base, uint32_t b_base,
-                                            uint32_t idesc, bool accumulate_first) {
+// a_lo: desc_lo_k(A), b_lo: desc_lo_mn(B). 4 MMAs.
+__device__ __forceinline__ void mma_a64_bmn(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                            uint32_t accumulate_first) {
+  mma_raw_dyn(tmem_d, a_lo, b_lo, idesc, accumulate_first);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint64_t da = make_smem_desc(a_base + k * 32, 16, 1024);
-    const uint64_t db = make_smem_desc(b_base + k * 2048, ATOM64, 1024);
-    tc_mma_bf16(tmem_d, da, db, idesc, accumulate_first || k != 0);
-  }
+  for (int k = 1; k < 4; ++k) mma_raw<true>(tmem_d, a_lo + k * 2, b_lo + k * (2048 >> 4), idesc);
 }
 
 __device__ __forceinline__ uint4 pack8(const float (&p)[8]) {
@@ -123,7 +152,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
   uint64_t* bar_s = bar_v + 2;  // [2] S(j) in TMEM
   uint64_t* bar_o = bar_s + 2;  //     PV(j) retired
   uint64_t* bar_p = bar_o + 1;  //     P(j) in smem (256 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_p + 1);
+  uint64_t* bar_vfree = bar_p + 1;  // [2] PV that read V buffer b retired (for the TMA warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_vfree + 2);
 
   const int nq = S / FWD_BQ;
   const int bh = blockIdx.x % (B * H);
@@ -142,6 +172,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
       mbar_init(&bar_k[i], 1);
       mbar_init(&bar_v[i], 1);
       mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_vfree[i], 1);
     }
     mbar_init(bar_o, 1);
     mbar_init(bar_p, NCOMPUTE);
@@ -154,11 +185,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + 128;
 
-  if (warp == 8) {
-    // =============================== control ===============================
+  if (warp == 9) {
+    // =============================== TMA producer ===============================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, FWD_BKV, false, false);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, DH, false, true);
       auto load_k = [&](int j) {
         const int buf = j & 1;
         mbar_arrive_expect_tx(&bar_k[buf], 2 * ATOM64);
@@ -175,11 +204,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
           tma_load_2d(sV + (buf * 2 + a) * ATOM64, &tm_qkv, &bar_v[buf], v_off + hk * DH + a * 64,
                       tok0 + j * FWD_BKV);
       };
-      auto issue_s = [&](int j) {  // S(j) = Q K(j)^T -> TMEM S[j & 1]
-        mma_kmajor_dh(tmem_base + (j & 1) * 64, smem_u32(sQ), ATOM128,
-                      smem_u32(sK + (j & 1) * 2 * ATOM64), ATOM64, idesc_s);
-        tc_commit(&bar_s[j & 1]);
-      };
       mbar_arrive_expect_tx(bar_q, 2 * ATOM128);
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -191,28 +215,41 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
       load_v(0);
       load_k(1);  // njb >= 2 always
       load_v(1);
+      for (int j = 0; j + 2 < njb; ++j) {
+        const int buf = j & 1;
+        mbar_wait(&bar_s[buf], (j >> 1) & 1);      // S(j) retired: its K buffer is free
+        load_k(j + 2);
+        mbar_wait(&bar_vfree[buf], (j >> 1) & 1);  // PV(j) retired: its V buffer is free
+        load_v(j + 2);
+      }
+    }
+  } else if (warp == 8) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, FWD_BKV, false, false);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, DH, false, true);
+      constexpr uint32_t BUF16 = (2 * ATOM64) >> 4, A128 = ATOM128 >> 4, A64 = ATOM64 >> 4;
+      const uint32_t q_lo = desc_lo_k(smem_u32(sQ)), k_lo = desc_lo_k(smem_u32(sK));
+      const uint32_t p_lo = desc_lo_k(smem_u32(sP)), v_lo = desc_lo_mn(smem_u32(sV));
       mbar_wait(bar_q, 0);
       mbar_wait(&bar_k[0], 0);
       tc_fence_after();
-      issue_s(0);
+      mma_kmajor_dh(tmem_base, q_lo, A128, k_lo, A64, idesc_s);  // S(0)
+      tc_commit(&bar_s[0]);
       for (int j = 0; j < njb; ++j) {
-        const int buf = j & 1;
+        const uint32_t buf = j & 1;
         if (j + 1 < njb) {  // S buffer buf^1 was drained by the compute warps before bar_p(j-1)
           mbar_wait(&bar_k[buf ^ 1], ((j + 1) >> 1) & 1);
           tc_fence_after();
-          issue_s(j + 1);
+          mma_kmajor_dh(tmem_base + (buf ^ 1) * 64, q_lo, A128, k_lo + (buf ^ 1) * BUF16, A64, idesc_s);
+          tc_commit(&bar_s[buf ^ 1]);
         }
         mbar_wait(bar_p, j & 1);  // P(j) written (and S(j) drained)
         mbar_wait(&bar_v[buf], (j >> 1) & 1);
         tc_fence_after();
-        mma_a64_bmn(tmem_O, smem_u32(sP), smem_u32(sV + buf * 2 * ATOM64), idesc_o, j != 0);
+        mma_a64_bmn(tmem_O, p_lo, v_lo + buf * BUF16, idesc_o, j != 0);
         tc_commit(bar_o);
-        if (j + 2 < njb) {
-          mbar_wait(&bar_s[buf], (j >> 1) & 1);  // S(j) retired: K buffer free
-          load_k(j + 2);
-          mbar_wait(bar_o, j & 1);               // PV(j) retired: V buffer free
-          load_v(j + 2);
-        }
+        tc_commit(&bar_vfree[buf]);
       }
     }
   } else {
@@ -348,7 +385,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   uint64_t* bar_s = bar_q + 3;   // [2] S^T, dP^T (it) in TMEM
   uint64_t* bar_d = bar_s + 2;   //     dV/dK MMAs (it) retired
   uint64_t* bar_p = bar_d + 1;   //     P^T, dS^T (it) in smem (256 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_p + 1);
+  uint64_t* bar_qfree = bar_p + 1;  // [3] MMAs that read Q/dO buffer b retired (for the TMA warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qfree + 3);
 
   const int G = H / Hkv;
   const int jb = blockIdx.x / (B * Hkv);  // earliest key blocks (longest query loops) first
@@ -365,7 +403,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
     mbar_init(bar_kv, 1);
-    for (int i = 0; i < 3; ++i) mbar_init(&bar_q[i], 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&bar_q[i], 1);
+      mbar_init(&bar_qfree[i], 1);
+    }
     for (int i = 0; i < 2; ++i) mbar_init(&bar_s[i], 1);
     mbar_init(bar_d, 1);
     mbar_init(bar_p, NCOMPUTE);
@@ -381,13 +422,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   auto iter_head = [&](int it) { return hk * G + it / nqb; };
   auto iter_qrow = [&](int it) { return (2 * jb + it % nqb) * BWD_BQ; };  // inside the sequence
 
-  if (warp == 8) {
-    // =============================== control ===============================
+  if (warp == 9) {
+    // =============================== TMA producer ===============================
     if (lane == 0) {
-      constexpr uint32_t idesc_st = make_idesc_bf16(128, BWD_BQ, false, false);  // S^T, dP^T
-      constexpr uint32_t idesc_dv = make_idesc_bf16(128, DH, false, true);       // dV, dK
-      auto load_q = [&](int it) {
-        const int buf = it % 3;
+      auto load_q = [&](int it, int buf) {
         mbar_arrive_expect_tx(&bar_q[buf], 4 * ATOM64);
         const int h = iter_head(it), row = tok0 + iter_qrow(it);
 #pragma unroll
@@ -395,14 +433,6 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           tma_load_2d(sQ + (buf * 2 + a) * ATOM64, &tm_qkv, &bar_q[buf], h * DH + a * 64, row);
           tma_load_2d(sdO + (buf * 2 + a) * ATOM64, &tm_do, &bar_q[buf], h * DH + a * 64, row);
         }
-      };
-      auto issue_scores = [&](int it) {  // S^T(it) = K Q^T, dP^T(it) = V dO^T -> TMEM buffers it & 1
-        const int qb = it % 3;
-        mma_kmajor_dh(tmem_base + (it & 1) * 64, smem_u32(sK), ATOM128,
-                      smem_u32(sQ + qb * 2 * ATOM64), ATOM64, idesc_st);
-        mma_kmajor_dh(tmem_base + 128 + (it & 1) * 64, smem_u32(sV), ATOM128,
-                      smem_u32(sdO + qb * 2 * ATOM64), ATOM64, idesc_st);
-        tc_commit(&bar_s[it & 1]);
       };
       mbar_arrive_expect_tx(bar_kv, 4 * ATOM128);
 #pragma unroll
@@ -414,30 +444,54 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           tma_load_2d(sV + a * ATOM128 + r * ATOM64, &tm_qkv, bar_kv, v_off + hk * DH + a * 64,
                       tok0 + kv0 + r * 64);
         }
-      load_q(0);
-      if (n_iter > 1) load_q(1);
-      if (n_iter > 2) load_q(2);
+      load_q(0, 0);
+      if (n_iter > 1) load_q(1, 1);
+      if (n_iter > 2) load_q(2, 2);
+      int buf = 0;
+      uint32_t par = 0;
+      for (int it = 0; it + 3 < n_iter; ++it) {  // block it+3 reuses block it's buffer
+        mbar_wait(&bar_qfree[buf], par);
+        load_q(it + 3, buf);
+        if (++buf == 3) { buf = 0; par ^= 1; }
+      }
+    }
+  } else if (warp == 8) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_st = make_idesc_bf16(128, BWD_BQ, false, false);  // S^T, dP^T
+      constexpr uint32_t idesc_dv = make_idesc_bf16(128, DH, false, true);       // dV, dK
+      constexpr uint32_t BUF16 = (2 * ATOM64) >> 4, A128 = ATOM128 >> 4, A64 = ATOM64 >> 4;
+      const uint32_t k_lo = desc_lo_k(smem_u32(sK)), v_lo = desc_lo_k(smem_u32(sV));
+      const uint32_t q_lo = desc_lo_k(smem_u32(sQ)), do_lo = desc_lo_k(smem_u32(sdO));
+      const uint32_t q_mn = desc_lo_mn(smem_u32(sQ)), do_mn = desc_lo_mn(smem_u32(sdO));
+      const uint32_t p_lo = desc_lo_k(smem_u32(sP)), ds_lo = desc_lo_k(smem_u32(sdS));
+      auto issue_scores = [&](uint32_t tb, uint32_t qb) {  // S^T = K Q^T, dP^T = V dO^T -> TMEM bufs tb
+        mma_kmajor_dh(tmem_base + tb * 64, k_lo, A128, q_lo + qb * BUF16, A64, idesc_st);
+        mma_kmajor_dh(tmem_base + 128 + tb * 64, v_lo, A128, do_lo + qb * BUF16, A64, idesc_st);
+        tc_commit(&bar_s[tb]);
+      };
       mbar_wait(bar_kv, 0);
       mbar_wait(&bar_q[0], 0);
       tc_fence_after();
-      issue_scores(0);
+      issue_scores(0, 0);
+      uint32_t qb = 0, qpar = 0;  // buffer / parity of block `it`
       for (int it = 0; it < n_iter; ++it) {
+        uint32_t nqb_ = qb + 1, npar = qpar;
+        if (nqb_ == 3) { nqb_ = 0; npar ^= 1; }
         if (it + 1 < n_iter) {  // TMEM score buffers (it+1)&1 were drained before bar_p(it-1)
-          mbar_wait(&bar_q[(it + 1) % 3], ((it + 1) / 3) & 1);
+          mbar_wait(&bar_q[nqb_], npar);
           tc_fence_after();
-          issue_scores(it + 1);
+          issue_scores((it + 1) & 1, nqb_);
         }
         mbar_wait(bar_p, it & 1);
         tc_fence_after();
-        const int qb = it % 3;
         // dV += P^T dO, dK += dS^T Q : A K-major [128 kv x 64 q], B MN-major (N = dh, K = q rows)
-        mma_a64_bmn(tmem_dV, smem_u32(sP), smem_u32(sdO + qb * 2 * ATOM64), idesc_dv, it != 0);
-        mma_a64_bmn(tmem_dK, smem_u32(sdS), smem_u32(sQ + qb * 2 * ATOM64), idesc_dv, it != 0);
+        mma_a64_bmn(tmem_dV, p_lo, do_mn + qb * BUF16, idesc_dv, it != 0);
+        mma_a64_bmn(tmem_dK, ds_lo, q_mn + qb * BUF16, idesc_dv, it != 0);
         tc_commit(bar_d);
-        if (it + 3 < n_iter) {  // block it+3 reuses this iteration's Q/dO buffer
-          mbar_wait(bar_d, it & 1);
-          load_q(it + 3);
-        }
+        tc_commit(&bar_qfree[qb]);
+        qb = nqb_;
+        qpar = npar;
       }
     }
   } else {
@@ -446,20 +500,22 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const int row_local = q * 32 + lane;       // TMEM lane == key row inside the block
     const int kv_seq = kv0 + row_local;        // key position inside the sequence
     const uint32_t lane_base = (q * 32u) << 16;
-    auto load_stats = [&](int it) {  // 128 of the compute threads
-      if (tid < 128) {
-        const int h = iter_head(it);
-        const size_t base = static_cast<size_t>(h) * Ttot + tok0 + iter_qrow(it);
-        sStat[(it & 1) * 128 + tid] = (tid < 64) ? lse2[base + tid] : delta[base + tid - 64] * scale;
-      }
+    // lse / delta*scale of the 64 query rows of a block: fetched into a register one iteration
+    // ahead by 128 of the compute threads, parked in smem just before the per-iteration bar.sync
+    auto fetch_stat = [&](int it) -> float {
+      const int h = iter_head(it);
+      const size_t base = static_cast<size_t>(h) * Ttot + tok0 + iter_qrow(it);
+      return (tid < 64) ? lse2[base + tid] : delta[base + tid - 64] * scale;
     };
-    load_stats(0);
+    if (tid < 128) sStat[tid] = fetch_stat(0);
     compute_bar_sync();
 
     for (int it = 0; it < n_iter; ++it) {
       const int tb = it & 1;
       const int q_seq0 = iter_qrow(it);
-      if (it + 1 < n_iter) load_stats(it + 1);  // other buffer; published by this iteration's bar.sync
+      float stat_next = 0.f;
+      const bool have_next = (it + 1 < n_iter) && tid < 128;
+      if (have_next) stat_next = fetch_stat(it + 1);  // latency hidden behind this block's math
       mbar_wait(&bar_s[tb], (it >> 1) & 1);
       if (it > 0) mbar_wait(bar_d, (it - 1) & 1);  // dV/dK(it-1) retired: sP, sdS free
       __syncwarp();
@@ -494,6 +550,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_p);
+      if (have_next) sStat[(tb ^ 1) * 128 + tid] = stat_next;
       compute_bar_sync();  // stats(it+1) visible; stats(it) no longer read
     }
 
@@ -541,7 +598,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint64_t* bar_s = bar_kv + 3;   // [2]
   uint64_t* bar_dq = bar_s + 2;
   uint64_t* bar_p = bar_dq + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_p + 1);
+  uint64_t* bar_kvfree = bar_p + 1;  // [3] MMAs that read K/V buffer b retired (for the TMA warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kvfree + 3);
 
   const int nq = S / DQ_BQ;
   const int bh = blockIdx.x % (B * H);
@@ -557,7 +615,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
     mbar_init(bar_q, 1);
-    for (int i = 0; i < 3; ++i) mbar_init(&bar_kv[i], 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&bar_kv[i], 1);
+      mbar_init(&bar_kvfree[i], 1);
+    }
     for (int i = 0; i < 2; ++i) mbar_init(&bar_s[i], 1);
     mbar_init(bar_dq, 1);
     mbar_init(bar_p, NCOMPUTE);
@@ -570,12 +631,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_dQ = tmem_base + 256;
 
-  if (warp == 8) {
+  if (warp == 9) {
+    // =============================== TMA producer ===============================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, DQ_BKV, false, false);  // S, dP
-      constexpr uint32_t idesc_dq = make_idesc_bf16(128, DH, false, true);      // dQ
-      auto load_kv = [&](int j) {
-        const int buf = j % 3;
+      auto load_kv = [&](int j, int buf) {
         mbar_arrive_expect_tx(&bar_kv[buf], 4 * ATOM64);
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
@@ -585,14 +644,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                       tok0 + j * DQ_BKV);
         }
       };
-      auto issue_scores = [&](int j) {  // S(j) = Q K^T, dP(j) = dO V^T -> TMEM buffers j & 1
-        const int kb = j % 3;
-        mma_kmajor_dh(tmem_base + (j & 1) * 64, smem_u32(sQ), ATOM128, smem_u32(sK + kb * 2 * ATOM64),
-                      ATOM64, idesc_s);
-        mma_kmajor_dh(tmem_base + 128 + (j & 1) * 64, smem_u32(sdO), ATOM128,
-                      smem_u32(sV + kb * 2 * ATOM64), ATOM64, idesc_s);
-        tc_commit(&bar_s[j & 1]);
-      };
       mbar_arrive_expect_tx(bar_q, 4 * ATOM128);
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -601,28 +652,52 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           tma_load_2d(sQ + a * ATOM128 + r * ATOM64, &tm_qkv, bar_q, h * DH + a * 64, tok0 + q0 + r * 64);
           tma_load_2d(sdO + a * ATOM128 + r * ATOM64, &tm_do, bar_q, h * DH + a * 64, tok0 + q0 + r * 64);
         }
-      load_kv(0);
-      load_kv(1);  // njb >= 2 always
-      if (njb > 2) load_kv(2);
+      load_kv(0, 0);
+      load_kv(1, 1);  // njb >= 2 always
+      if (njb > 2) load_kv(2, 2);
+      int buf = 0;
+      uint32_t par = 0;
+      for (int j = 0; j + 3 < njb; ++j) {  // block j+3 reuses block j's buffer
+        mbar_wait(&bar_kvfree[buf], par);
+        load_kv(j + 3, buf);
+        if (++buf == 3) { buf = 0; par ^= 1; }
+      }
+    }
+  } else if (warp == 8) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, DQ_BKV, false, false);  // S, dP
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, DH, false, true);      // dQ
+      constexpr uint32_t BUF16 = (2 * ATOM64) >> 4, A128 = ATOM128 >> 4, A64 = ATOM64 >> 4;
+      const uint32_t q_lo = desc_lo_k(smem_u32(sQ)), do_lo = desc_lo_k(smem_u32(sdO));
+      const uint32_t k_lo = desc_lo_k(smem_u32(sK)), v_lo = desc_lo_k(smem_u32(sV));
+      const uint32_t k_mn = desc_lo_mn(smem_u32(sK)), ds_lo = desc_lo_k(smem_u32(sdS));
+      auto issue_scores = [&](uint32_t tb, uint32_t kb) {  // S = Q K^T, dP = dO V^T -> TMEM bufs tb
+        mma_kmajor_dh(tmem_base + tb * 64, q_lo, A128, k_lo + kb * BUF16, A64, idesc_s);
+        mma_kmajor_dh(tmem_base + 128 + tb * 64, do_lo, A128, v_lo + kb * BUF16, A64, idesc_s);
+        tc_commit(&bar_s[tb]);
+      };
       mbar_wait(bar_q, 0);
       mbar_wait(&bar_kv[0], 0);
       tc_fence_after();
-      issue_scores(0);
+      issue_scores(0, 0);
+      uint32_t kb = 0, kpar = 0;  // buffer / parity of block j
       for (int j = 0; j < njb; ++j) {
+        uint32_t nkb = kb + 1, npar = kpar;
+        if (nkb == 3) { nkb = 0; npar ^= 1; }
         if (j + 1 < njb) {
-          mbar_wait(&bar_kv[(j + 1) % 3], ((j + 1) / 3) & 1);
+          mbar_wait(&bar_kv[nkb], npar);
           tc_fence_after();
-          issue_scores(j + 1);
+          issue_scores((j + 1) & 1, nkb);
         }
         mbar_wait(bar_p, j & 1);
         tc_fence_after();
         // dQ += dS K : A K-major [128 q x 64 kv], B = K as MN-major (N = dh, K = kv rows)
-        mma_a64_bmn(tmem_dQ, smem_u32(sdS), smem_u32(sK + (j % 3) * 2 * ATOM64), idesc_dq, j != 0);
+        mma_a64_bmn(tmem_dQ, ds_lo, k_mn + kb * BUF16, idesc_dq, j != 0);
         tc_commit(bar_dq);
-        if (j + 3 < njb) {  // block j+3 reuses this iteration's K/V buffer
-          mbar_wait(bar_dq, j & 1);
-          load_kv(j + 3);
-        }
+        tc_commit(&bar_kvfree[kb]);
+        kb = nkb;
+        kpar = npar;
       }
     }
   } else {

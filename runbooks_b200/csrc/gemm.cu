@@ -18,6 +18,8 @@
 
 namespace b200w {
 
+static int pick_n_fast(int M, int N, int K);
+
 namespace {
 
 constexpr int BLOCK_M = 128;
@@ -35,24 +37,36 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <typename OutT>
-__device__ __forceinline__ void store_chunk32(OutT* drow, const OutT* crow, const float (&v)[32],
-                                              int ncols_valid, bool has_c);
+// ---- epilogue helpers ------------------------------------------------------------------------
+// One thread owns one output row; a "chunk" is 32 consecutive columns of it. The optional addend C
+// (residual stream / running gradient) is fetched into registers one chunk AHEAD of its use, so
+// its global-memory latency sits under the previous chunk's tcgen05.ld + stores instead of in
+// front of them (profiles/r01_ncu_gemm_pair.txt: the synchronous version lost 20 points of
+// tensor-pipe activity on accumulating wgrads).
+template <typename OutT> struct CChunk;
+template <> struct CChunk<__nv_bfloat16> { using vec = uint4; uint4 v[4]; };   // 32 bf16
+template <> struct CChunk<float> { using vec = float4; float4 v[8]; };          // 32 fp32
 
-template <>
-__device__ __forceinline__ void store_chunk32<__nv_bfloat16>(__nv_bfloat16* drow,
-                                                             const __nv_bfloat16* crow,
-                                                             const float (&v)[32], int ncols_valid,
-                                                             bool has_c) {
+template <typename OutT>
+__device__ __forceinline__ void load_c_chunk(CChunk<OutT>& c, const OutT* crow, int ncols_valid) {
+  if (ncols_valid >= 32) {
+    using vec = typename CChunk<OutT>::vec;
+    const vec* p = reinterpret_cast<const vec*>(crow);
+#pragma unroll
+    for (int i = 0; i < static_cast<int>(sizeof(c.v) / sizeof(c.v[0])); ++i) c.v[i] = p[i];
+  }
+}
+
+__device__ __forceinline__ void store_chunk32(__nv_bfloat16* drow, const __nv_bfloat16* crow,
+                                              const CChunk<__nv_bfloat16>& cc, const float (&v)[32],
+                                              int ncols_valid, bool has_c) {
   if (ncols_valid >= 32) {
     uint4 out[4];
     uint32_t* o = reinterpret_cast<uint32_t*>(out);
     if (has_c) {
-      const uint4* c4 = reinterpret_cast<const uint4*>(crow);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        uint4 c = c4[i];
-        const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
+        const uint32_t cw[4] = {cc.v[i].x, cc.v[i].y, cc.v[i].z, cc.v[i].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float2 f = unpack_bf16x2(cw[j]);
@@ -78,18 +92,15 @@ __device__ __forceinline__ void store_chunk32<__nv_bfloat16>(__nv_bfloat16* drow
   }
 }
 
-template <>
-__device__ __forceinline__ void store_chunk32<float>(float* drow, const float* crow,
-                                                     const float (&v)[32], int ncols_valid,
-                                                     bool has_c) {
+__device__ __forceinline__ void store_chunk32(float* drow, const float* crow, const CChunk<float>& cc,
+                                              const float (&v)[32], int ncols_valid, bool has_c) {
   if (ncols_valid >= 32) {
     float4* d4 = reinterpret_cast<float4*>(drow);
-    const float4* c4 = reinterpret_cast<const float4*>(crow);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       if (has_c) {
-        float4 c = c4[i];
+        const float4 c = cc.v[i];
         o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
       }
       d4[i] = o;
@@ -101,10 +112,34 @@ __device__ __forceinline__ void store_chunk32<float>(float* drow, const float* c
   }
 }
 
+// TMEM accumulator rows -> global for one 128 x NCOLS tile half owned by this warp's lane quarter.
+template <int NCOLS, typename OutT>
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_row_addr, OutT* drow, const OutT* crow,
+                                              bool row_ok, int ncols_total) {
+  const bool has_c = crow != nullptr;
+  CChunk<OutT> cc_next;
+  if (has_c && row_ok) load_c_chunk<OutT>(cc_next, crow, ncols_total);
+#pragma unroll 1
+  for (int c = 0; c < NCOLS / 32; ++c) {
+    const CChunk<OutT> cc = cc_next;
+    const int ncols = ncols_total - c * 32;
+    if (has_c && row_ok && c + 1 < NCOLS / 32) load_c_chunk<OutT>(cc_next, crow + (c + 1) * 32, ncols - 32);
+    uint32_t r[32];
+    tmem_ld32(tmem_row_addr + c * 32, r);
+    tmem_ld_wait();
+    if (row_ok && ncols > 0) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      store_chunk32(drow + c * 32, has_c ? crow + c * 32 : nullptr, cc, v, ncols, has_c);
+    }
+  }
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 OutT* D, const OutT* C, int M, int N, int K, int ldd) {
+                 OutT* D, const OutT* C, int M, int N, int K, int ldd, int n_fast) {
   using cfg = Cfg<BLOCK_N>;
   constexpr int STAGES = cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -149,8 +184,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % num_m) * BLOCK_M;  // M fastest: concurrent CTAs share B tiles via L2
-        const int n0 = (tile / num_m) * BLOCK_N;
+        // raster order: the operand that does NOT fit in L2 is made the slow index (launch())
+        const int m0 = (n_fast ? tile / num_n : tile % num_m) * BLOCK_M;
+        const int n0 = (n_fast ? tile % num_n : tile / num_m) * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * cfg::STAGE_BYTES;
@@ -217,8 +253,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % num_m) * BLOCK_M;
-      const int n0 = (tile / num_m) * BLOCK_N;
+      const int m0 = (n_fast ? tile / num_n : tile % num_m) * BLOCK_M;
+      const int n0 = (n_fast ? tile % num_n : tile / num_m) * BLOCK_N;
       mbar_wait(&tfull_bar[acc], acc_phase);
       __syncwarp();
       tc_fence_after();
@@ -226,20 +262,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = row < M;
       OutT* drow = D + static_cast<size_t>(row) * ldd + n0;
       const OutT* crow = C ? C + static_cast<size_t>(row) * ldd + n0 : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_addr(tmem_base, q * 32, acc * BLOCK_N + c * 32), r);
-        tmem_ld_wait();
-        const int ncols = N - (n0 + c * 32);
-        if (row_ok && ncols > 0) {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          store_chunk32<OutT>(drow + c * 32, crow ? crow + c * 32 : nullptr, v, ncols,
-                              crow != nullptr);
-        }
-      }
+      epilogue_tile<BLOCK_N, OutT>(tmem_addr(tmem_base, q * 32, acc * BLOCK_N), drow, crow, row_ok, N - n0);
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -270,7 +293,7 @@ constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256;
 template <bool A_MN, bool B_MN, typename OutT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      OutT* D, const OutT* C, int M, int N, int K, int ldd) {
+                      OutT* D, const OutT* C, int M, int N, int K, int ldd, int n_fast) {
   constexpr int STAGES = PAIR_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -317,8 +340,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile % num_m) * 256 + rank * 128;          // my 128 rows of A
-        const int n0 = (tile / num_m) * PAIR_N + rank * (PAIR_N / 2);  // my half of B
+        const int m0 = (n_fast ? tile / num_n : tile % num_m) * 256 + rank * 128;  // my 128 rows of A
+        const int n0 = (n_fast ? tile % num_n : tile / num_m) * PAIR_N + rank * (PAIR_N / 2);  // my B half
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * PAIR_STAGE_BYTES;
@@ -382,8 +405,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m0 = (tile % num_m) * 256 + rank * 128;
-      const int n0 = (tile / num_m) * PAIR_N;
+      const int m0 = (n_fast ? tile / num_n : tile % num_m) * 256 + rank * 128;
+      const int n0 = (n_fast ? tile % num_n : tile / num_m) * PAIR_N;
       mbar_wait(&tfull_bar[acc], acc_phase);
       __syncwarp();
       tc_fence_after();
@@ -391,20 +414,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const bool row_ok = row < M;
       OutT* drow = D + static_cast<size_t>(row) * ldd + n0;
       const OutT* crow = C ? C + static_cast<size_t>(row) * ldd + n0 : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < PAIR_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_addr(tmem_base, q * 32, acc * PAIR_N + c * 32), r);
-        tmem_ld_wait();
-        const int ncols = N - (n0 + c * 32);
-        if (row_ok && ncols > 0) {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          store_chunk32<OutT>(drow + c * 32, crow ? crow + c * 32 : nullptr, v, ncols,
-                              crow != nullptr);
-        }
-      }
+      epilogue_tile<PAIR_N, OutT>(tmem_addr(tmem_base, q * 32, acc * PAIR_N), drow, crow, row_ok, N - n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA thread waits on it
@@ -437,7 +447,8 @@ void launch_pair(const void* A, const void* B, OutT* D, const OutT* C, int M, in
   const int num_tiles = ((M + 255) / 256) * ((N + PAIR_N - 1) / PAIR_N);
   const int max_clusters = sm_count() / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-  kern<<<clusters * 2, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(tmA, tmB, D, C, M, N, K, ldd);
+  kern<<<clusters * 2, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(tmA, tmB, D, C, M, N, K, ldd,
+                                                                pick_n_fast(M, N, K));
   B200W_CUDA(cudaGetLastError());
 }
 
@@ -468,7 +479,8 @@ void launch(const void* A, const void* B, OutT* D, const OutT* C, int M, int N, 
   }
   const int num_tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, cfg::SMEM_BYTES, stream>>>(tmA, tmB, D, C, M, N, K, ldd);
+  kern<<<grid, GEMM_THREADS, cfg::SMEM_BYTES, stream>>>(tmA, tmB, D, C, M, N, K, ldd,
+                                                        pick_n_fast(M, N, K));
   B200W_CUDA(cudaGetLastError());
 }
 
@@ -482,6 +494,17 @@ void dispatch_major(bool a_mn, bool b_mn, const void* A, const void* B, OutT* D,
 }
 
 }  // namespace
+
+// Tile raster order. M-fastest re-reads A once per wave of N-tiles unless A stays in L2; N-fastest
+// does the same to B. Keep the order whose re-streamed operand fits in L2, else re-stream the
+// smaller one. (profiles/r01_ncu_gemm_pair.txt: wgrad of gate|up read 2.9 GB for 214 MB of
+// operands with the wrong order.)
+static int pick_n_fast(int M, int N, int K) {
+  const double a_bytes = 2.0 * M * K, b_bytes = 2.0 * N * K, l2_budget = 64e6;
+  if (a_bytes <= l2_budget) return 0;
+  if (b_bytes <= l2_budget) return 1;
+  return b_bytes < a_bytes ? 1 : 0;
+}
 
 // Public launcher (C++). out_fp32: D/C are float, else bf16. C may alias D (accumulate in place).
 // block_n: 0 = auto, else 128 or 256.

@@ -38,15 +38,18 @@ def main():
     shapes = {
         "fwd_qkv": (T, 3 * d, d, 0, 0), "fwd_gateup": (T, 2 * f, d, 0, 0), "fwd_down": (T, d, f, 0, 0),
         "fwd_lmhead": (T, V, d, 0, 0), "dgrad_gateup": (T, d, 2 * f, 0, 1), "dgrad_down": (T, f, d, 0, 1),
-        "wgrad_gateup": (2 * f, d, T, 1, 1), "wgrad_down": (d, f, T, 1, 1), "square_8k": (8192, 8192, 8192, 0, 0),
+        "wgrad_gateup": (2 * f, d, T, 1, 1), "wgrad_gateup_acc": (2 * f, d, T, 1, 1), "wgrad_down": (d, f, T, 1, 1),
+        "wgrad_down_acc": (d, f, T, 1, 1), "wgrad_lmhead_acc": (V, d, T, 1, 1), "dgrad_qkv": (T, d, 3 * d, 0, 1),
+        "square_8k": (8192, 8192, 8192, 0, 0),
     }
     for name, (M, N, K, a_mn, b_mn) in shapes.items():
         A = torch.randn((K, M) if a_mn else (M, K), device="cuda").bfloat16()
         B = torch.randn((K, N) if b_mn else (N, K), device="cuda").bfloat16()
         wg = name.startswith("wgrad")
         D = torch.empty(M, N, device="cuda", dtype=torch.float32 if wg else torch.bfloat16)
-        for bn in (256, 512):
-            t = timeit(lambda: call(e, "b200w_op_gemm", A, a_mn, A.shape[1], B, b_mn, B.shape[1], D, None,
+        for bn in (512,):
+            Cacc = D if name.endswith("_acc") else None
+            t = timeit(lambda: call(e, "b200w_op_gemm", A, a_mn, A.shape[1], B, b_mn, B.shape[1], D, Cacc,
                                     1 if wg else 0, N, M, N, K, bn))
             tf = 2.0 * M * N * K / t / 1e12
             out[f"gemm_{name}_bn{bn}"] = dict(ms=t * 1e3, tflops=tf)

@@ -361,7 +361,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
 // ==========================================================================================
 constexpr int BWD_BKV = 128, BWD_BQ = 64;
 constexpr int KV_SMEM = 2 * ATOM128 /*K*/ + 2 * ATOM128 /*V*/ + 3 * 2 * ATOM64 /*Q x3*/ +
-                        3 * 2 * ATOM64 /*dO x3*/ + ATOM128 /*P^T*/ + ATOM128 /*dS^T*/ +
+                        3 * 2 * ATOM64 /*dO x3*/ + 2 * ATOM128 /*P^T x2*/ + 2 * ATOM128 /*dS^T x2*/ +
                         2 * 2 * 64 * 4 /*lse, delta x2*/ + 256;
 // S^T[2]: [0,64) [64,128)   dP^T[2]: [128,192) [192,256)   dV: [256,384)   dK: [384,512)
 constexpr int KV_TMEM_COLS = 512;
@@ -377,14 +377,14 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   uint8_t* sV = sK + 2 * ATOM128;
   uint8_t* sQ = sV + 2 * ATOM128;           // 3 bufs x 2 atoms x [64 q x 128 B]
   uint8_t* sdO = sQ + 3 * 2 * ATOM64;
-  uint8_t* sP = sdO + 3 * 2 * ATOM64;       // P^T  [128 kv x 64 q]
-  uint8_t* sdS = sP + ATOM128;              // dS^T [128 kv x 64 q]
-  float* sStat = reinterpret_cast<float*>(sdS + ATOM128);  // [2 bufs][lse 64 | delta*scale 64]
+  uint8_t* sP = sdO + 3 * 2 * ATOM64;       // 2 bufs x P^T  [128 kv x 64 q]
+  uint8_t* sdS = sP + 2 * ATOM128;          // 2 bufs x dS^T [128 kv x 64 q]
+  float* sStat = reinterpret_cast<float*>(sdS + 2 * ATOM128);  // [2 bufs][lse 64 | delta*scale 64]
   uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sStat + 2 * 128);
   uint64_t* bar_q = bar_kv + 1;  // [3]
   uint64_t* bar_s = bar_q + 3;   // [2] S^T, dP^T (it) in TMEM
-  uint64_t* bar_d = bar_s + 2;   //     dV/dK MMAs (it) retired
-  uint64_t* bar_p = bar_d + 1;   //     P^T, dS^T (it) in smem (256 arrivals)
+  uint64_t* bar_d = bar_s + 2;   // [2] dV/dK MMAs that read P/dS buffer b retired
+  uint64_t* bar_p = bar_d + 2;   //     P^T, dS^T (it) in smem (256 arrivals)
   uint64_t* bar_qfree = bar_p + 1;  // [3] MMAs that read Q/dO buffer b retired (for the TMA warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qfree + 3);
 
@@ -407,8 +407,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       mbar_init(&bar_q[i], 1);
       mbar_init(&bar_qfree[i], 1);
     }
-    for (int i = 0; i < 2; ++i) mbar_init(&bar_s[i], 1);
-    mbar_init(bar_d, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_d[i], 1);
+    }
     mbar_init(bar_p, NCOMPUTE);
     fence_barrier_init();
   }
@@ -486,9 +488,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         mbar_wait(bar_p, it & 1);
         tc_fence_after();
         // dV += P^T dO, dK += dS^T Q : A K-major [128 kv x 64 q], B MN-major (N = dh, K = q rows)
-        mma_a64_bmn(tmem_dV, p_lo, do_mn + qb * BUF16, idesc_dv, it != 0);
-        mma_a64_bmn(tmem_dK, ds_lo, q_mn + qb * BUF16, idesc_dv, it != 0);
-        tc_commit(bar_d);
+        const uint32_t pb = (it & 1) * A128;  // P/dS staging buffer of this block
+        mma_a64_bmn(tmem_dV, p_lo + pb, do_mn + qb * BUF16, idesc_dv, it != 0);
+        mma_a64_bmn(tmem_dK, ds_lo + pb, q_mn + qb * BUF16, idesc_dv, it != 0);
+        tc_commit(&bar_d[it & 1]);
         tc_commit(&bar_qfree[qb]);
         qb = nqb_;
         qpar = npar;
@@ -505,9 +508,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     auto fetch_stat = [&](int it) -> float {
       const int h = iter_head(it);
       const size_t base = static_cast<size_t>(h) * Ttot + tok0 + iter_qrow(it);
-      return (tid < 64) ? lse2[base + tid] : delta[base + tid - 64] * scale;
+      return (tid < 64) ? lse2[base + tid] : delta[base + tid - 64];
     };
-    if (tid < 128) sStat[tid] = fetch_stat(0);
+    const float stat_mul = (tid < 64) ? 1.f : scale;  // delta is kept pre-multiplied by the scale
+    if (tid < 128) sStat[tid] = fetch_stat(0) * stat_mul;
     compute_bar_sync();
 
     for (int it = 0; it < n_iter; ++it) {
@@ -517,13 +521,14 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       const bool have_next = (it + 1 < n_iter) && tid < 128;
       if (have_next) stat_next = fetch_stat(it + 1);  // latency hidden behind this block's math
       mbar_wait(&bar_s[tb], (it >> 1) & 1);
-      if (it > 0) mbar_wait(bar_d, (it - 1) & 1);  // dV/dK(it-1) retired: sP, sdS free
       __syncwarp();
       tc_fence_after();
       uint32_t s_r[32], dp_r[32];
       tmem_ld32(tmem_base + tb * 64 + lane_base + hc * 32, s_r);
       tmem_ld32(tmem_base + 128 + tb * 64 + lane_base + hc * 32, dp_r);
       tmem_ld_wait();
+      // staging buffer tb was last read by the dV/dK MMAs of block it-2
+      if (it >= 2) mbar_wait(&bar_d[tb], ((it >> 1) - 1) & 1);
       const float4* st_lse = reinterpret_cast<const float4*>(sStat + tb * 128 + hc * 32);
       const float4* st_dl = reinterpret_cast<const float4*>(sStat + tb * 128 + 64 + hc * 32);
       const bool diag = (q_seq0 < kv0 + BWD_BKV);  // some (q, kv) pairs of this block are masked
@@ -543,18 +548,18 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           // dS = P (dP - delta) * scale, with delta*scale precomputed
           ds[e] = pv * fmaf(__uint_as_float(dp_r[c8 * 8 + e]), scale, -dl8[e]);
         }
-        const uint32_t off = sw128_offset(row_local, hc * 4 + c8);
+        const uint32_t off = tb * ATOM128 + sw128_offset(row_local, hc * 4 + c8);
         *reinterpret_cast<uint4*>(sP + off) = pack8(p);
         *reinterpret_cast<uint4*>(sdS + off) = pack8(ds);
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_p);
-      if (have_next) sStat[(tb ^ 1) * 128 + tid] = stat_next;
+      if (have_next) sStat[(tb ^ 1) * 128 + tid] = stat_next * stat_mul;
       compute_bar_sync();  // stats(it+1) visible; stats(it) no longer read
     }
 
-    mbar_wait(bar_d, (n_iter - 1) & 1);
+    mbar_wait(&bar_d[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);  // commits are cumulative
     __syncwarp();
     tc_fence_after();
     // dV, dK: lane = key row; this thread stores 64 of the 128 dh columns of each
@@ -577,7 +582,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 // ==========================================================================================
 constexpr int DQ_BQ = 128, DQ_BKV = 64;
 constexpr int DQ_SMEM = 2 * ATOM128 /*Q*/ + 2 * ATOM128 /*dO*/ + 3 * 2 * ATOM64 /*K x3*/ +
-                        3 * 2 * ATOM64 /*V x3*/ + ATOM128 /*dS*/ + 256;
+                        3 * 2 * ATOM64 /*V x3*/ + 2 * ATOM128 /*dS x2*/ + 256;
 // S[2]: [0,64) [64,128)   dP[2]: [128,192) [192,256)   dQ: [256,384)
 constexpr int DQ_TMEM_COLS = 512;
 
@@ -592,12 +597,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* sdO = sQ + 2 * ATOM128;
   uint8_t* sK = sdO + 2 * ATOM128;         // 3 bufs x 2 atoms x [64 kv x 128 B]
   uint8_t* sV = sK + 3 * 2 * ATOM64;
-  uint8_t* sdS = sV + 3 * 2 * ATOM64;      // dS [128 q x 64 kv]
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sdS + ATOM128);
+  uint8_t* sdS = sV + 3 * 2 * ATOM64;      // 2 bufs x dS [128 q x 64 kv]
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sdS + 2 * ATOM128);
   uint64_t* bar_kv = bar_q + 1;   // [3]
   uint64_t* bar_s = bar_kv + 3;   // [2]
-  uint64_t* bar_dq = bar_s + 2;
-  uint64_t* bar_p = bar_dq + 1;
+  uint64_t* bar_dq = bar_s + 2;   // [2] dQ MMAs that read dS buffer b retired
+  uint64_t* bar_p = bar_dq + 2;
   uint64_t* bar_kvfree = bar_p + 1;  // [3] MMAs that read K/V buffer b retired (for the TMA warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kvfree + 3);
 
@@ -619,8 +624,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       mbar_init(&bar_kv[i], 1);
       mbar_init(&bar_kvfree[i], 1);
     }
-    for (int i = 0; i < 2; ++i) mbar_init(&bar_s[i], 1);
-    mbar_init(bar_dq, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_dq[i], 1);
+    }
     mbar_init(bar_p, NCOMPUTE);
     fence_barrier_init();
   }
@@ -693,8 +700,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         mbar_wait(bar_p, j & 1);
         tc_fence_after();
         // dQ += dS K : A K-major [128 q x 64 kv], B = K as MN-major (N = dh, K = kv rows)
-        mma_a64_bmn(tmem_dQ, ds_lo, k_mn + kb * BUF16, idesc_dq, j != 0);
-        tc_commit(bar_dq);
+        mma_a64_bmn(tmem_dQ, ds_lo + (j & 1) * A128, k_mn + kb * BUF16, idesc_dq, j != 0);
+        tc_commit(&bar_dq[j & 1]);
         tc_commit(&bar_kvfree[kb]);
         kb = nkb;
         kpar = npar;
@@ -712,13 +719,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     for (int j = 0; j < njb; ++j) {
       const int tb = j & 1;
       mbar_wait(&bar_s[tb], (j >> 1) & 1);
-      if (j > 0) mbar_wait(bar_dq, (j - 1) & 1);  // dQ MMA (j-1) retired: sdS free
       __syncwarp();
       tc_fence_after();
       uint32_t s_r[32], dp_r[32];
       tmem_ld32(tmem_base + tb * 64 + lane_base + hc * 32, s_r);
       tmem_ld32(tmem_base + 128 + tb * 64 + lane_base + hc * 32, dp_r);
       tmem_ld_wait();
+      if (j >= 2) mbar_wait(&bar_dq[tb], ((j >> 1) - 1) & 1);  // dS buffer tb: read by dQ MMA (j-2)
       const int col0 = j * DQ_BKV + hc * 32;
       const bool diag = (j * DQ_BKV + DQ_BKV - 1) > q0;
 #pragma unroll
@@ -730,14 +737,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           if (diag && (col0 + c8 * 8 + e > row_seq)) pv = 0.f;
           ds[e] = pv * fmaf(__uint_as_float(dp_r[c8 * 8 + e]), scale, -my_dl);
         }
-        *reinterpret_cast<uint4*>(sdS + sw128_offset(row_local, hc * 4 + c8)) = pack8(ds);
+        *reinterpret_cast<uint4*>(sdS + tb * ATOM128 + sw128_offset(row_local, hc * 4 + c8)) = pack8(ds);
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_p);
     }
 
-    mbar_wait(bar_dq, (njb - 1) & 1);
+    mbar_wait(&bar_dq[(njb - 1) & 1], ((njb - 1) >> 1) & 1);  // commits are cumulative
     __syncwarp();
     tc_fence_after();
     bf16* dqrow = dqkv + static_cast<size_t>(tok0 + row_seq) * ld_qkv + h * DH + hc * 64;

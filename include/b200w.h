@@ -138,6 +138,41 @@ B200W_API int b200w_forward(b200w_ctx* ctx, const int32_t* ids, const int32_t* l
 B200W_API int64_t b200w_launch_count(const b200w_ctx* ctx);
 B200W_API int64_t b200w_device_bytes(const b200w_ctx* ctx);
 
+/* ---- Server decode path (server_controller.go:149-173 starts the container
+ * that runs this loop; oracle: HF FalconForCausalLM / LlamaForCausalLM .generate(do_sample=False)) */
+#define B200W_FAMILY_LLAMA 0
+#define B200W_FAMILY_FALCON 1
+typedef struct {
+  int32_t family;            /* B200W_FAMILY_*                                                  */
+  int32_t vocab_size;
+  int32_t hidden_size;
+  int32_t intermediate_size; /* Llama: intermediate_size; Falcon: ffn_hidden_size (4 * hidden)  */
+  int32_t num_layers;
+  int32_t num_heads;
+  int32_t num_kv_heads;      /* Falcon-7B multi_query: 1                                        */
+  int32_t head_dim;          /* 64 or 128                                                       */
+  int32_t max_ctx;           /* KV-cache length per slot                                        */
+  float norm_eps;
+  float rope_theta;
+  int32_t tie_embeddings;    /* lm_head shares the embedding matrix (Falcon)                    */
+} b200w_infer_arch;
+/* bf16 weights + a KV cache of max_batch slots x max_ctx positions. Parameter names are the HF
+ * checkpoint keys of the family ("transformer.h.0.self_attention.query_key_value.weight", ...). */
+B200W_API int b200w_infer_init(b200w_ctx* ctx, const b200w_infer_arch* arch, int max_batch);
+B200W_API int b200w_infer_param_count(b200w_ctx* ctx, int64_t* n_tensors, int64_t* n_elements);
+B200W_API int b200w_infer_param_info(b200w_ctx* ctx, int64_t index, char* name, size_t name_cap, int64_t* rows,
+                           int64_t* cols);
+B200W_API int b200w_infer_load_tensor(b200w_ctx* ctx, const char* name, const void* host, b200w_dtype dtype,
+                            int64_t n_elements);
+B200W_API int b200w_infer_init_random(b200w_ctx* ctx, uint64_t seed, float std);
+/* One decode step for n rows (HOST int32 arrays): row i feeds `tokens[i]` at `positions[i]` into
+ * cache slot `slots[i]` (K/V appended there) and attends to that slot's positions [0, pos].
+ * next_tokens (HOST, n): greedy argmax of the new logits; logits_out: HOST float [n, vocab] or NULL.
+ * Prompt ingestion is the same call with the outputs of all but the last prompt token ignored. */
+B200W_API int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* positions,
+                     const int32_t* slots, int n, int32_t* next_tokens, float* logits_out);
+B200W_API int64_t b200w_infer_device_bytes(b200w_ctx* ctx);
+
 /* ---- per-kernel hooks for the parity tests (DEVICE pointers, bf16 unless noted) ------------ */
 /* D[M,N] = opA[M,K] opB[N,K]^T (+C). a_mn / b_mn: operand stored [K,M] / [K,N] row-major.
  * out_f32: D and C are fp32. C may be NULL or alias D. block_n: 0 auto, 128, 256. */

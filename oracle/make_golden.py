@@ -158,7 +158,38 @@ def run_ops():
     print(f"ops -> {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def run_falcon():
+    """Tiny falcon-7b-layout model: prompt logits + greedy generation from the real HF classes."""
+    from transformers import FalconConfig, FalconForCausalLM
+    from oracle import falcon_oracle as FO
+
+    a = FO.FalconArch(vocab_size=512, hidden_size=256, num_layers=2, num_heads=4, head_dim=64)
+    params = FO.seeded_params(a, 21)
+    cfg = FalconConfig(vocab_size=a.vocab_size, hidden_size=a.hidden_size, num_hidden_layers=a.num_layers,
+                       num_attention_heads=a.num_heads, multi_query=True, parallel_attn=True, bias=False,
+                       new_decoder_architecture=False, alibi=False, layer_norm_epsilon=1e-5,
+                       max_position_embeddings=256, tie_word_embeddings=True, hidden_dropout=0.0,
+                       attention_dropout=0.0)
+    cfg._attn_implementation = "sdpa"
+    model = FalconForCausalLM(cfg).float().eval()
+    sd = {k: torch.tensor(v) for k, v in params.items()}
+    sd["lm_head.weight"] = sd["transformer.word_embeddings.weight"]
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("rotary" in m or "inv_freq" in m for m in missing), (missing, unexpected)
+    rng = np.random.default_rng(77)
+    prompts = rng.integers(0, a.vocab_size, size=(3, 24), dtype=np.int64)
+    with torch.no_grad():
+        logits = model(torch.tensor(prompts)).logits.numpy()
+        gen = model.generate(torch.tensor(prompts), max_new_tokens=12, do_sample=False,
+                             pad_token_id=0).numpy()[:, prompts.shape[1]:]
+    path = os.path.join(OUT, "falcon_tiny.npz")
+    np.savez_compressed(path, arch=np.array([a.vocab_size, a.hidden_size, a.num_layers, a.num_heads, a.head_dim]),
+                        seed=np.int64(21), prompts=prompts, logits=logits.astype(np.float32), generated=gen)
+    print(f"falcon -> {path} ({os.path.getsize(path) / 1024:.0f} KiB); generated[0] = {gen[0].tolist()}")
+
+
 if __name__ == "__main__":
     run_ops()
+    run_falcon()
     for name, (a, B, seed) in CASES.items():
         run_case(name, a, B, seed)

@@ -30,6 +30,15 @@ class Arch(C.Structure):
     ]
 
 
+class InferArch(C.Structure):
+    _fields_ = [
+        ("family", C.c_int32), ("vocab_size", C.c_int32), ("hidden_size", C.c_int32),
+        ("intermediate_size", C.c_int32), ("num_layers", C.c_int32), ("num_heads", C.c_int32),
+        ("num_kv_heads", C.c_int32), ("head_dim", C.c_int32), ("max_ctx", C.c_int32),
+        ("norm_eps", C.c_float), ("rope_theta", C.c_float), ("tie_embeddings", C.c_int32),
+    ]
+
+
 class HParams(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("weight_decay", C.c_float), ("max_grad_norm", C.c_float)]
@@ -63,6 +72,13 @@ PROTOTYPES = {
     "b200w_forward": (C.c_int, [c_ctx, vp, vp, C.c_int, vp, vp, f32p]),
     "b200w_launch_count": (C.c_int64, [c_ctx]),
     "b200w_device_bytes": (C.c_int64, [c_ctx]),
+    "b200w_infer_init": (C.c_int, [c_ctx, C.POINTER(InferArch), C.c_int]),
+    "b200w_infer_param_count": (C.c_int, [c_ctx, i64p, i64p]),
+    "b200w_infer_param_info": (C.c_int, [c_ctx, C.c_int64, C.c_char_p, C.c_size_t, i64p, i64p]),
+    "b200w_infer_load_tensor": (C.c_int, [c_ctx, C.c_char_p, vp, C.c_int, C.c_int64]),
+    "b200w_infer_init_random": (C.c_int, [c_ctx, C.c_uint64, C.c_float]),
+    "b200w_infer_step": (C.c_int, [c_ctx, vp, vp, vp, C.c_int, vp, vp]),
+    "b200w_infer_device_bytes": (C.c_int64, [c_ctx]),
     "b200w_op_gemm": (C.c_int, [c_ctx, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "b200w_op_embed_fwd": (C.c_int, [c_ctx, vp, vp, vp, C.c_int, C.c_int, C.c_int]),

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200w.so")
-SOURCES = ["host_common.cu", "gemm.cu", "attention.cu", "ops.cu", "engine.cu"]
+SOURCES = ["host_common.cu", "gemm.cu", "attention.cu", "ops.cu", "engine.cu", "infer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

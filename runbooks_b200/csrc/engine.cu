@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/b200w.h"
+#include "ctx_access.h"
 #include "host_common.h"
 #include "ops.h"
 #include "ptx.cuh"
@@ -151,6 +152,10 @@ struct b200w_ctx {
   std::vector<cudaEvent_t> prof_events;  // pairs
   size_t prof_used = 0;
   double prof_flops = 0;
+
+  // ---- inference engine (infer.cu) ----
+  void* infer = nullptr;
+  void (*infer_destroy)(void*) = nullptr;
 
   // ---- DP ----
   void* comm = nullptr;
@@ -515,6 +520,25 @@ void optimizer_step(b200w_ctx* c, float lr) {
 
 }  // namespace
 
+// ---- ctx_access.h ----------------------------------------------------------------------------
+int ctx_device(b200w_ctx* c) { return c->device; }
+cudaStream_t ctx_stream(b200w_ctx* c) { return c->stream; }
+void ctx_set_error(b200w_ctx* c, const char* msg) { c->err = msg ? msg : ""; }
+int64_t& ctx_launches(b200w_ctx* c) { return c->launches; }
+void* ctx_infer_slot(b200w_ctx* c) { return c->infer; }
+void ctx_set_infer(b200w_ctx* c, void* p, void (*destroy)(void*)) {
+  c->infer = p;
+  c->infer_destroy = destroy;
+}
+void ctx_fill_normal(b200w_ctx* c, void* w_bf16, size_t n, uint64_t seed, float std) {
+  init_normal_kernel<<<sm_count() * 8, 256, 0, c->stream>>>(nullptr, static_cast<bf16*>(w_bf16), n, seed, std);
+  B200W_CUDA(cudaGetLastError());
+}
+void ctx_fill_const(b200w_ctx* c, void* w_bf16, size_t n, float value) {
+  fill_kernel<<<64, 256, 0, c->stream>>>(nullptr, static_cast<bf16*>(w_bf16), n, value);
+  B200W_CUDA(cudaGetLastError());
+}
+
 // ============================================================================================
 // C ABI
 // ============================================================================================
@@ -561,6 +585,7 @@ void b200w_destroy(b200w_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   if (ctx->comm) nccl().CommDestroy(ctx->comm);
+  if (ctx->infer && ctx->infer_destroy) ctx->infer_destroy(ctx->infer);
   ctx->free_all();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->host_scal) cudaFreeHost(ctx->host_scal);

@@ -188,14 +188,32 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
   }
 }
 
-// dw[c] += sum_b dw_partial[b][c]
+// dw[c] += sum_b dw_partial[b][c]. Block = 32 columns x 8 row-lanes: each thread walks every 8th
+// partial row with 4 independent accumulators, so ~32 loads are in flight per warp instead of 1.
 __global__ void rmsnorm_dw_reduce_kernel(const float* __restrict__ dw_partial, float* __restrict__ dw,
                                          int nblocks, int d) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d) return;
-  float acc = 0.f;
-  for (int b = 0; b < nblocks; ++b) acc += dw_partial[static_cast<size_t>(b) * d + c];
-  dw[c] += acc;
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < d) {
+    int b = ry;
+    for (; b + 24 < nblocks; b += 32) {
+      a0 += dw_partial[static_cast<size_t>(b) * d + c];
+      a1 += dw_partial[static_cast<size_t>(b + 8) * d + c];
+      a2 += dw_partial[static_cast<size_t>(b + 16) * d + c];
+      a3 += dw_partial[static_cast<size_t>(b + 24) * d + c];
+    }
+    for (; b < nblocks; b += 8) a0 += dw_partial[static_cast<size_t>(b) * d + c];
+  }
+  red[ry][cx] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (ry == 0 && c < d) {
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc += red[r][cx];
+    dw[c] += acc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -522,7 +540,7 @@ void rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd
   else
     rmsnorm_bwd_kernel<4><<<grid, NORM_THREADS, 0, s>>>(dyp, xp, wp, rstd, rp, dxp, dw_partial, T, d);
   B200W_CUDA(cudaGetLastError());
-  rmsnorm_dw_reduce_kernel<<<(d + 255) / 256, 256, 0, s>>>(dw_partial, dw, grid, d);
+  rmsnorm_dw_reduce_kernel<<<(d + 31) / 32, 256, 0, s>>>(dw_partial, dw, grid, d);
   B200W_CUDA(cudaGetLastError());
 }
 

@@ -32,8 +32,10 @@ template <int BLOCK_N>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
+  // 4 x 48 KB, 6 x 32 KB, 8 x 24 KB, 9 x 20 KB: the narrow tiles exist for decode (M <= 128), where
+  // the job is to keep every SM streaming weights, not to feed the tensor pipe
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128) ? 6 : (BLOCK_N == 64) ? 8 : 9;
+  static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;  // two accumulator stages
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -487,6 +489,11 @@ void launch(const void* A, const void* B, OutT* D, const OutT* C, int M, int N, 
 template <int BLOCK_N, typename OutT>
 void dispatch_major(bool a_mn, bool b_mn, const void* A, const void* B, OutT* D, const OutT* C,
                     int M, int N, int K, int lda, int ldb, int ldd, cudaStream_t s) {
+  if constexpr (BLOCK_N < 128) {  // decode tiles: weights are always K-major there
+    B200W_CHECK(!a_mn && !b_mn, "narrow tiles support K-major operands only");
+    launch<BLOCK_N, false, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
+    return;
+  }
   if (!a_mn && !b_mn) launch<BLOCK_N, false, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
   else if (!a_mn && b_mn) launch<BLOCK_N, false, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
   else if (a_mn && b_mn) launch<BLOCK_N, true, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
@@ -524,9 +531,14 @@ void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int 
     if (M >= 256 && N >= 256 && tiles_pair >= sm_count() / 2) block_n = 512;
   }
   if (block_n == 0) {
-    // 256-wide tiles halve A re-reads; fall back to 128 when that would leave SMs idle.
-    const long tiles256 = static_cast<long>((M + 127) / 128) * ((N + 255) / 256);
-    block_n = (N >= 256 && tiles256 >= sm_count()) ? 256 : 128;
+    // widest tile that still gives every SM a tile; K-major-only narrow tiles when M fits one tile
+    const long m_tiles = (M + 127) / 128;
+    const bool narrow_ok = !a_mn && !b_mn && !out_fp32;
+    block_n = narrow_ok ? 32 : 128;
+    for (int bn : {256, 128, 64}) {
+      if (bn < 128 && !narrow_ok) break;
+      if (N >= bn && m_tiles * ((N + bn - 1) / bn) >= sm_count()) { block_n = bn; break; }
+    }
   }
   if (block_n == 512) {  // CTA-pair kernel: 256 x 256 tiles on tcgen05.mma.cta_group::2
     if (out_fp32)
@@ -537,7 +549,18 @@ void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int 
                                    static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb, ldd, stream);
     return;
   }
-  B200W_CHECK(block_n == 128 || block_n == 256, "block_n must be 0, 128, 256 or 512 (CTA pair)");
+  B200W_CHECK(block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256,
+              "block_n must be 0, 32, 64, 128, 256 or 512 (CTA pair)");
+  if (block_n < 128) {
+    B200W_CHECK(!out_fp32, "narrow tiles write bf16");
+    if (block_n == 64)
+      dispatch_major<64, __nv_bfloat16>(a_mn, b_mn, A, B, static_cast<__nv_bfloat16*>(D),
+                                        static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb, ldd, stream);
+    else
+      dispatch_major<32, __nv_bfloat16>(a_mn, b_mn, A, B, static_cast<__nv_bfloat16*>(D),
+                                        static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb, ldd, stream);
+    return;
+  }
   if (out_fp32) {
     if (block_n == 256)
       dispatch_major<256, float>(a_mn, b_mn, A, B, static_cast<float*>(D),

@@ -87,6 +87,17 @@ def test_gemm_llama_shapes(engine, block_n):
         assert err < 2e-5
 
 
+@pytest.mark.parametrize("block_n", [32, 64])
+@pytest.mark.parametrize("M,N,K", [(32, 4544, 1024), (7, 328, 136), (128, 96, 64)])
+def test_gemm_narrow_decode_tiles(engine, M, N, K, block_n):
+    """Decode-shaped GEMMs: a handful of rows, narrow N tiles so that every SM streams weights."""
+    Ad, Bd, ref = _operands(M, N, K, 0, 0, seed=6)
+    res = torch.randn(M, N, generator=torch.Generator().manual_seed(7)).bfloat16()
+    D = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    call(engine, "b200w_op_gemm", Ad, 0, K, Bd, 0, K, D, dev(res), 0, N, M, N, K, block_n)
+    assert rel_err(D.float(), ref + res.float()) < 3e-3
+
+
 def test_gemm_rejects_bad_arguments(engine):
     from runbooks_b200._lib import B200WError
     A = torch.zeros(128, 60, device="cuda", dtype=torch.bfloat16)  # lda not a multiple of 8

@@ -55,7 +55,7 @@ def test_serve_falcon_over_http(tmp_path):
     else:
         pytest.fail("server never became ready")
     words = [f"w{i}" for i in np.random.default_rng(1).integers(0, 500, size=10)]
-    prompt_ids = [vocab[w] for w in words]                # no bos: tokenizer has none configured
+    prompt_ids = [0] + [vocab[w] for w in words]          # the server prepends the tokenizer's <s> (id 0)
     ref, ref_logits = FO.greedy(params, prompt_ids, 8, a)
 
     def complete(prompt, n):
@@ -71,7 +71,7 @@ def test_serve_falcon_over_http(tmp_path):
     [t.start() for t in ths]
     [t.join() for t in ths]
     for o in outs:
-        assert o["object"] == "text_completion" and o["usage"]["prompt_tokens"] == 10
+        assert o["object"] == "text_completion" and o["usage"]["prompt_tokens"] == 11
         got = [vocab.get(w, 2) for w in o["choices"][0]["text"].split()]
         stop = ref.index(1) if 1 in ref else len(ref)     # eos ends generation and is not echoed
         margin = np.diff(np.sort(ref_logits, axis=-1)[:, -2:], axis=-1)[:, 0]

@@ -189,10 +189,13 @@ def run_reference(args):
 PER_DEVICE_BATCH = 8
 
 
+MICRO_BATCH = 1
+
+
 def workload_config(n_gpus: int):
     return dict(workload="Llama-2-7B bf16 causal-LM fine-tune, seq 4096 (BASELINE.json configs[1])",
                 global_batch=PER_DEVICE_BATCH * n_gpus, seq_len=4096, per_device_batch=PER_DEVICE_BATCH,
-                micro_batch=1, parallelism=f"dp{n_gpus}", optimizer="AdamW fp32 master, clip 1.0",
+                micro_batch=MICRO_BATCH, parallelism=f"dp{n_gpus}", optimizer="AdamW fp32 master, clip 1.0",
                 l2="working set (13.5 GB bf16 weights + activations per micro-step) >> 126 MB L2; no flush needed")
 
 
@@ -223,7 +226,7 @@ def run_ours(args):
         arch.num_layers = args.layers
     S, nseq = arch.max_seq_len, args.per_device_batch
     e = Engine(local)
-    e.init_model(arch, micro_batch=1, training=True)
+    e.init_model(arch, micro_batch=args.micro_batch, training=True)
     e.init_random(seed=0, std=0.02)          # identical replicas: same seed on every rank
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8)
@@ -323,16 +326,20 @@ def run_ours(args):
 
 
 def main():
+    global MICRO_BATCH
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--per-device-batch", type=int, default=PER_DEVICE_BATCH)
+    ap.add_argument("--micro-batch", type=int, default=MICRO_BATCH,
+                    help="sequences per accumulation micro-step (activation memory scales with it)")
     ap.add_argument("--layers", type=int, default=0, help="development only: fewer layers")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    MICRO_BATCH = args.micro_batch
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -919,6 +919,27 @@ int b200w_op_gemm(b200w_ctx* ctx, const void* A, int a_mn, int lda, const void* 
   HOOK(gemm_bf16(A, a_mn != 0, lda, B, b_mn != 0, ldb, D, C, out_f32 != 0, ldd, M, N, K, block_n,
                  ctx->stream));
 }
+int b200w_op_gemm_decode(b200w_ctx* ctx, const void* X, const void* W, void* out, const void* C, int M,
+                         int N, int K, int split_k) {
+  return guarded(ctx, [&] {
+    float* ws = nullptr;
+    unsigned* cnt = nullptr;
+    if (split_k) {
+      B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws), static_cast<size_t>(M) * N * 4));
+      B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&cnt), ((N + 127) / 128) * 4));
+      B200W_CUDA(cudaMemsetAsync(ws, 0, static_cast<size_t>(M) * N * 4, ctx->stream));
+      B200W_CUDA(cudaMemsetAsync(cnt, 0, ((N + 127) / 128) * 4, ctx->stream));
+    }
+    try {
+      gemm_decode(X, W, out, C, ws, cnt, M, N, K, N, ctx->stream);
+      gemm_decode(X, W, out, C, ws, cnt, M, N, K, N, ctx->stream);  // twice: the scratch must come back clean
+      ctx->launches += 2;
+      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    } catch (...) { cudaFree(ws); cudaFree(cnt); throw; }
+    cudaFree(ws);
+    cudaFree(cnt);
+  });
+}
 int b200w_op_embed_fwd(b200w_ctx* ctx, const int32_t* ids, const void* table, void* out, int T, int d,
                        int vocab) {
   HOOK(embed_fwd(ids, table, out, T, d, vocab, ctx->stream));

@@ -502,6 +502,182 @@ void dispatch_major(bool a_mn, bool b_mn, const void* A, const void* B, OutT* D,
 
 }  // namespace
 
+// ==========================================================================================
+// Decode GEMM ("swap-AB"): out[M, N] = X[M, K] W[N, K]^T (+ C) for M <= 128 rows (a decode batch).
+// The weights are the 128-row A operand and the batch is a narrow B operand (UMMA N = MPAD), so
+// every byte a pipeline stage holds is a weight byte streamed from HBM — the job here is HBM
+// bandwidth, not tensor throughput. Grid = (N tiles, K splits): the 36-tile projections of a
+// 7B model are split along K so that all SMs stream. Partial sums meet in an fp32 workspace
+// through red.global.add; the last CTA of a tile finalises it and leaves the workspace zeroed.
+// ==========================================================================================
+template <int MPAD>
+struct DecodeCfg {
+  static constexpr int B_STAGE_BYTES = MPAD * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int MPAD>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                   __nv_bfloat16* out, const __nv_bfloat16* C, float* ws, unsigned* counters, int M,
+                   int N, int K, int ldo, int kb_per_split) {
+  using cfg = DecodeCfg<MPAD>;
+  constexpr int STAGES = cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* done_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  uint32_t* last_flag = tmem_slot + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BLOCK_M;            // 128 output features
+  const int num_kb_total = (K + BLOCK_K - 1) / BLOCK_K;
+  const int kb0 = blockIdx.y * kb_per_split;
+  const int kb1 = min(num_kb_total, kb0 + kb_per_split);
+  const int nkb = kb1 - kb0;
+  const bool split = gridDim.y > 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, MPAD < 32 ? 32 : MPAD);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * cfg::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], cfg::STAGE_BYTES);
+        tma_load_2d(sa, &tmW, &full_bar[stage], kb * BLOCK_K, n0);                   // weights
+        tma_load_2d(sa + A_STAGE_BYTES, &tmX, &full_bar[stage], kb * BLOCK_K, 0);    // batch rows
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, MPAD, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * cfg::STAGE_BYTES);
+        const uint64_t da = make_smem_desc(sa, 16, 1024);
+        const uint64_t db = make_smem_desc(sa + A_STAGE_BYTES, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+          tc_mma_bf16(tmem_base, desc_advance(da, k * UMMA_K * 2), desc_advance(db, k * UMMA_K * 2), idesc,
+                      (i | k) != 0);
+        tc_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(done_bar);
+    }
+  } else if (warp >= 4) {
+    // lane of TMEM = output feature n; column = batch row b
+    const int q = warp & 3;
+    const int n = n0 + q * 32 + lane;
+    const bool n_ok = n < N;
+    mbar_wait(done_bar, 0);
+    __syncwarp();
+    tc_fence_after();
+    uint32_t r[32];
+#pragma unroll 1
+    for (int c = 0; c < MPAD / 32; ++c) {
+      tmem_ld32(tmem_addr(tmem_base, q * 32, c * 32), r);
+      tmem_ld_wait();
+      if (n_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int b = c * 32 + j;
+          if (b < M) {
+            const float v = __uint_as_float(r[j]);
+            if (split) atomicAdd(ws + static_cast<size_t>(b) * N + n, v);  // 32 lanes -> 128 B, coalesced
+            else {
+              const float cv = C ? __bfloat162float(C[static_cast<size_t>(b) * ldo + n]) : 0.f;
+              out[static_cast<size_t>(b) * ldo + n] = __float2bfloat16_rn(v + cv);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (split) {
+    // last CTA of this N tile finalises it and leaves workspace + counter clean for the next GEMM
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *last_flag = (atomicAdd(&counters[blockIdx.x], 1u) == gridDim.y - 1) ? 1u : 0u;
+    __syncthreads();
+    if (*last_flag) {
+      __threadfence();
+      for (int i = threadIdx.x; i < M * BLOCK_M; i += blockDim.x) {
+        const int b = i / BLOCK_M, n = n0 + i % BLOCK_M;
+        if (n < N) {
+          float* p = ws + static_cast<size_t>(b) * N + n;
+          const float v = __ldcg(p);
+          *p = 0.f;
+          const float cv = C ? __bfloat162float(C[static_cast<size_t>(b) * ldo + n]) : 0.f;
+          out[static_cast<size_t>(b) * ldo + n] = __float2bfloat16_rn(v + cv);
+        }
+      }
+      if (threadIdx.x == 0) counters[blockIdx.x] = 0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, MPAD < 32 ? 32 : MPAD);
+  }
+}
+
+template <int MPAD>
+void launch_decode(const void* X, const void* W, void* out, const void* C, float* ws, unsigned* counters,
+                   int M, int N, int K, int ldo, cudaStream_t stream) {
+  using cfg = DecodeCfg<MPAD>;
+  CUtensorMap tmW = make_tmap_bf16_2d(W, N, K, K, BLOCK_M, BLOCK_K);
+  CUtensorMap tmX = make_tmap_bf16_2d(X, M, K, K, MPAD, BLOCK_K);
+  auto kern = gemm_decode_kernel<MPAD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200W_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int n_tiles = (N + BLOCK_M - 1) / BLOCK_M;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  // split K until every SM has a CTA, keeping at least 8 K-blocks per split
+  int splits = 1;
+  if (ws && counters) {
+    splits = sm_count() / n_tiles;
+    if (splits > num_kb / 8) splits = num_kb / 8;
+    if (splits < 1) splits = 1;
+  }
+  const int per = (num_kb + splits - 1) / splits;
+  splits = (num_kb + per - 1) / per;
+  kern<<<dim3(n_tiles, splits), GEMM_THREADS, cfg::SMEM_BYTES, stream>>>(
+      tmW, tmX, static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(C), ws, counters, M, N,
+      K, ldo, per);
+  B200W_CUDA(cudaGetLastError());
+}
+
 // Tile raster order. M-fastest re-reads A once per wave of N-tiles unless A stays in L2; N-fastest
 // does the same to B. Keep the order whose re-streamed operand fits in L2, else re-stream the
 // smaller one. (profiles/r01_ncu_gemm_pair.txt: wgrad of gate|up read 2.9 GB for 214 MB of
@@ -511,6 +687,18 @@ static int pick_n_fast(int M, int N, int K) {
   if (a_bytes <= l2_budget) return 0;
   if (b_bytes <= l2_budget) return 1;
   return b_bytes < a_bytes ? 1 : 0;
+}
+
+// out[M, N] = X[M, K] W[N, K]^T (+ C), M <= 128: the decode-time projection. ws: zeroed fp32
+// workspace of >= M*N floats and counters: zeroed unsigned[ceil(N/128)] enable split-K (both are
+// left zeroed again); pass nullptr to disable.
+void gemm_decode(const void* X, const void* W, void* out, const void* C, float* ws, unsigned* counters,
+                 int M, int N, int K, int ldo, cudaStream_t stream) {
+  B200W_CHECK(M >= 1 && M <= 128 && N > 0 && K > 0, "decode GEMM handles 1..128 rows");
+  B200W_CHECK(K % 8 == 0, "TMA needs 16-byte aligned row strides");
+  if (M <= 32) launch_decode<32>(X, W, out, C, ws, counters, M, N, K, ldo, stream);
+  else if (M <= 64) launch_decode<64>(X, W, out, C, ws, counters, M, N, K, ldo, stream);
+  else launch_decode<128>(X, W, out, C, ws, counters, M, N, K, ldo, stream);
 }
 
 // Public launcher (C++). out_fp32: D/C are float, else bf16. C may alias D (accumulate in place).

@@ -175,32 +175,59 @@ decode_attn_kernel(const bf16* __restrict__ qkv, int ld, const bf16* __restrict_
     inv_sum[g] = 1.f / block_reduce(s, red, false);
   }
   __syncthreads();
-  // output: thread = (dim, position slice); V element read once for all ng heads
-  constexpr int SLICES = ATT_THREADS / DH;
-  const int dim = tid % DH, sl = tid / DH;
-  float o[ATT_GT];
+  // output: thread = (8 dims via one 16-byte load, position slice); 4 independent positions in
+  // flight per thread; V read once for all ng heads
+  constexpr int DG = DH / 8;                 // 16-byte groups per row
+  constexpr int SLICES = ATT_THREADS / DG;   // 32 (dh 64) or 16 (dh 128) position slices
+  const int dg = tid % DG, sl = tid / DG;
+  float o[ATT_GT][8];
 #pragma unroll
-  for (int g = 0; g < ATT_GT; ++g) o[g] = 0.f;
-  for (int t = sl; t < len; t += SLICES) {
-    const float v = __bfloat162float(vcache[((cbase + t) * Hkv + hk) * DH + dim]);
+  for (int g = 0; g < ATT_GT; ++g)
 #pragma unroll
-    for (int g = 0; g < ATT_GT; ++g)
-      if (g < ng) o[g] += sc[g * sc_stride + t] * v;
-  }
-  __syncthreads();
-  float* so = sq;  // reuse: [SLICES][ATT_GT][DH] <= ATT_GT*DH*SLICES floats? (SLICES*ATT_GT*DH)
-  // sq holds only ATT_GT*DH floats; stage the slices through the (dead) score area instead
-  so = sc;
-  for (int g = 0; g < ng; ++g) so[(sl * ATT_GT + g) * DH + dim] = o[g];
-  __syncthreads();
-  if (sl == 0) {
-    for (int g = 0; g < ng; ++g) {
-      float a = 0.f;
+    for (int e = 0; e < 8; ++e) o[g][e] = 0.f;
+  for (int t0 = sl; t0 < len; t0 += 4 * SLICES) {
+    uint4 vv[4];
 #pragma unroll
-      for (int s2 = 0; s2 < SLICES; ++s2) a += so[(s2 * ATT_GT + g) * DH + dim];
-      out[static_cast<size_t>(r) * (H * DH) + (hk * G + g0 + g) * DH + dim] =
-          __float2bfloat16_rn(a * inv_sum[g]);
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * SLICES;
+      vv[u] = t < len ? *reinterpret_cast<const uint4*>(vcache + ((cbase + t) * Hkv + hk) * DH + dg * 8)
+                      : make_uint4(0, 0, 0, 0);
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * SLICES;
+      if (t < len) {
+        const uint32_t w[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+        float vf[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(w[j]);
+          vf[2 * j] = f.x;
+          vf[2 * j + 1] = f.y;
+        }
+#pragma unroll
+        for (int g = 0; g < ATT_GT; ++g) {
+          const float p = sc[g * sc_stride + t];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[g][e] += p * vf[e];
+        }
+      }
+    }
+  }
+  __syncthreads();  // scores are dead: reuse their space to combine the slices
+  float* so = sc;   // [SLICES][ATT_GT][DH]  (sc_stride >= SLICES * DH / ... checked on the host)
+#pragma unroll
+  for (int g = 0; g < ATT_GT; ++g)
+    if (g < ng) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) so[(sl * ATT_GT + g) * DH + dg * 8 + e] = o[g][e];
+    }
+  __syncthreads();
+  for (int i = tid; i < ng * DH; i += ATT_THREADS) {
+    const int g = i / DH, dim = i % DH;
+    float a = 0.f;
+    for (int s2 = 0; s2 < SLICES; ++s2) a += so[(s2 * ATT_GT + g) * DH + dim];
+    out[static_cast<size_t>(r) * (H * DH) + (hk * G + g0 + g) * DH + dim] = __float2bfloat16_rn(a * inv_sum[g]);
   }
 }
 
@@ -257,6 +284,8 @@ struct Infer {
        *act = nullptr, *logits = nullptr;
   bf16 *kc = nullptr, *vc = nullptr;  // [L][max_batch][max_ctx][Hkv*dh]
   float* inv_freq = nullptr;
+  float* ws = nullptr;          // split-K workspace [max_batch, max N] (kept zeroed)
+  unsigned* counters = nullptr;
   int32_t *tok = nullptr, *pos = nullptr, *slot = nullptr, *next = nullptr;
   std::vector<void*> allocs;
   int64_t bytes = 0;
@@ -389,6 +418,11 @@ int b200w_infer_init(b200w_ctx* ctx, const b200w_infer_arch* arch, int max_batch
     m->slot = m->alloc<int32_t>(B);
     m->next = m->alloc<int32_t>(B);
     m->inv_freq = m->alloc<float>(a.head_dim / 2);
+    const size_t max_n = std::max<size_t>({static_cast<size_t>(a.vocab_size), fmid, qd + 2 * kd, d});
+    m->ws = m->alloc<float>(B * max_n);
+    m->counters = m->alloc<unsigned>((max_n + 127) / 128);
+    B200W_CUDA(cudaMemset(m->ws, 0, B * max_n * sizeof(float)));
+    B200W_CUDA(cudaMemset(m->counters, 0, ((max_n + 127) / 128) * sizeof(unsigned)));
     std::vector<float> inv(a.head_dim / 2);
     for (int i = 0; i < a.head_dim / 2; ++i)
       inv[i] = static_cast<float>(1.0 / pow(static_cast<double>(a.rope_theta), 2.0 * i / a.head_dim));
@@ -489,7 +523,7 @@ int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* posit
     const size_t layer_cache = static_cast<size_t>(m->max_batch) * a.max_ctx * kd;
     const int G = H / Hkv;
     const dim3 agrid(n, Hkv, (G + ATT_GT - 1) / ATT_GT);
-    const int slices = ATT_THREADS / dh;
+    const int slices = ATT_THREADS / (dh / 8);   // staging area: slices * ATT_GT * dh floats
     const int sc_stride = std::max(a.max_ctx, slices * dh);
     const size_t att_smem = (static_cast<size_t>(ATT_GT) * dh + static_cast<size_t>(ATT_GT) * sc_stride + 32) * 4;
     static bool attr = false;
@@ -504,7 +538,7 @@ int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* posit
     bf16* h2 = m->h2;
     embed_fwd(m->tok, m->w + m->p_embed, h, n, d, V, s); ++nl;
     auto gemm = [&](const bf16* A, int K, size_t woff, int N, bf16* D, const bf16* C) {
-      gemm_bf16(A, false, K, m->w + woff, false, K, D, C, false, N, n, N, K, 0, s); ++nl;
+      gemm_decode(A, m->w + woff, D, C, m->ws, m->counters, n, N, K, N, s); ++nl;
     };
     for (int l = 0; l < a.num_layers; ++l) {
       const auto& p = m->lp[l];

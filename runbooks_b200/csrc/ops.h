@@ -13,6 +13,11 @@ void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int 
                const void* C, bool out_fp32, int ldd, int M, int N, int K, int block_n,
                cudaStream_t s);
 
+// out[M, N] = X[M, K] W[N, K]^T (+ C) for a decode batch (M <= 128): swap-AB + split-K streaming
+// kernel. ws / counters: zeroed scratch (M*N floats, ceil(N/128) unsigned), left zeroed; nullable.
+void gemm_decode(const void* X, const void* W, void* out, const void* C, float* ws, unsigned* counters,
+                 int M, int N, int K, int ldo, cudaStream_t s);
+
 // ---- attention.cu --------------------------------------------------------------------------
 // Causal self-attention over packed sequences. qkv: [T, ld_qkv] with q at column 0, k at
 // column k_off, v at column v_off (head h at +h*128); T = B*S; head_dim fixed at 128.

@@ -147,3 +147,21 @@ def test_tokenizer_and_dataset_build(tmp_path):
     assert list(ids[0, :8]) == [0, 4, 5, 6, 12, 7, 8, 1]   # <s> w1 w2 w3 w9 w4 w5 </s>
     per_step, spe, total = worker.plan_steps(len(ids), contract.TrainParams(num_train_epochs=1, per_device_train_batch_size=1), 2)
     assert per_step == 2 and spe == len(ids) // 2 and total == spe
+
+
+def test_serve_arch_from_hf_configs():
+    from runbooks_b200.infer import ServeArch
+    falcon7b = {"model_type": "falcon", "vocab_size": 65024, "hidden_size": 4544, "num_hidden_layers": 32,
+                "num_attention_heads": 71, "multi_query": True, "parallel_attn": True, "bias": False,
+                "alibi": False, "new_decoder_architecture": False, "layer_norm_epsilon": 1e-5}
+    a = ServeArch.from_hf_config(falcon7b)
+    assert (a.family, a.head_dim, a.num_kv_heads, a.intermediate_size, a.tie_embeddings) == ("falcon", 64, 1, 18176, True)
+    assert a == ServeArch.falcon_7b(2048)
+    with pytest.raises(ValueError):
+        ServeArch.from_hf_config(dict(falcon7b, alibi=True))
+    with pytest.raises(ValueError):
+        ServeArch.from_hf_config({"model_type": "opt"})
+    ll = ServeArch.from_hf_config({"model_type": "llama", "vocab_size": 32000, "hidden_size": 4096,
+                                   "intermediate_size": 11008, "num_hidden_layers": 32, "num_attention_heads": 32,
+                                   "rms_norm_eps": 1e-5, "max_position_embeddings": 4096})
+    assert (ll.family, ll.num_kv_heads, ll.head_dim, ll.max_ctx, ll.tie_embeddings) == ("llama", 32, 128, 4096, False)

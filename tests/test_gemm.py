@@ -98,6 +98,20 @@ def test_gemm_narrow_decode_tiles(engine, M, N, K, block_n):
     assert rel_err(D.float(), ref + res.float()) < 3e-3
 
 
+@pytest.mark.parametrize("split_k", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(32, 4544, 1024), (1, 4672, 4544), (7, 328, 136), (100, 520, 2048), (33, 4544, 18176)])
+def test_gemm_decode_swap_ab(engine, M, N, K, split_k):
+    """The decode projection kernel (weights as the A operand, batch as a narrow B, optional split-K
+    through a self-cleaning fp32 workspace) against the same fp32 reference, with a residual."""
+    Ad, Bd, ref = _operands(M, N, K, 0, 0, seed=8)
+    res = torch.randn(M, N, generator=torch.Generator().manual_seed(9)).bfloat16()
+    D = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    call(engine, "b200w_op_gemm_decode", Ad, Bd, D, dev(res), M, N, K, split_k)
+    err = rel_err(D.float(), ref + res.float())
+    print(f"gemm decode M{M} N{N} K{K} split{split_k}: rel_err {err:.3e}")
+    assert err < 3e-3
+
+
 def test_gemm_rejects_bad_arguments(engine):
     from runbooks_b200._lib import B200WError
     A = torch.zeros(128, 60, device="cuda", dtype=torch.bfloat16)  # lda not a multiple of 8

@@ -287,6 +287,9 @@ struct Infer {
   float* ws = nullptr;          // split-K workspace [max_batch, max N] (kept zeroed)
   unsigned* counters = nullptr;
   int32_t *tok = nullptr, *pos = nullptr, *slot = nullptr, *next = nullptr;
+  int32_t* pin = nullptr;  // pinned host staging: tok | pos | slot | next, max_batch each
+  std::unordered_map<int, cudaGraphExec_t> graphs;  // whole decode step per row count
+  std::unordered_map<int, int> warm;
   std::vector<void*> allocs;
   int64_t bytes = 0;
   template <typename T>
@@ -302,6 +305,8 @@ struct Infer {
     return static_cast<T*>(p);
   }
   ~Infer() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    if (pin) cudaFreeHost(pin);
     for (void* p : allocs) cudaFree(p);
   }
 };
@@ -417,6 +422,7 @@ int b200w_infer_init(b200w_ctx* ctx, const b200w_infer_arch* arch, int max_batch
     m->pos = m->alloc<int32_t>(B);
     m->slot = m->alloc<int32_t>(B);
     m->next = m->alloc<int32_t>(B);
+    B200W_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->pin), 4 * B * sizeof(int32_t)));
     m->inv_freq = m->alloc<float>(a.head_dim / 2);
     const size_t max_n = std::max<size_t>({static_cast<size_t>(a.vocab_size), fmid, qd + 2 * kd, d});
     m->ws = m->alloc<float>(B * max_n);
@@ -512,9 +518,10 @@ int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* posit
     }
     cudaStream_t s = ctx_stream(ctx);
     int64_t& nl = ctx_launches(ctx);
-    B200W_CUDA(cudaMemcpyAsync(m->tok, tokens, n * 4, cudaMemcpyHostToDevice, s));
-    B200W_CUDA(cudaMemcpyAsync(m->pos, positions, n * 4, cudaMemcpyHostToDevice, s));
-    B200W_CUDA(cudaMemcpyAsync(m->slot, slots, n * 4, cudaMemcpyHostToDevice, s));
+    const int B = m->max_batch;
+    memcpy(m->pin, tokens, n * 4);
+    memcpy(m->pin + B, positions, n * 4);
+    memcpy(m->pin + 2 * B, slots, n * 4);
     const int d = a.hidden_size, f = a.intermediate_size, H = a.num_heads, Hkv = a.num_kv_heads,
               dh = a.head_dim, V = a.vocab_size;
     const int qd = H * dh, kd = Hkv * dh, qkvd = qd + 2 * kd;
@@ -534,6 +541,15 @@ int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* posit
     }
     B200W_CHECK(att_smem <= 200 * 1024, "max_ctx too large for the decode attention kernel");
 
+    int64_t step_launches = 0;
+    // Everything from the H2D of the three index vectors to the D2H of the argmax, on stream s.
+    // Run eagerly the first time a row count is seen (first-use attribute calls), captured into a
+    // CUDA graph the second time, replayed from then on: ~330 launches become one.
+    auto enqueue = [&]() {
+    int64_t& nl = step_launches;
+    B200W_CUDA(cudaMemcpyAsync(m->tok, m->pin, n * 4, cudaMemcpyHostToDevice, s));
+    B200W_CUDA(cudaMemcpyAsync(m->pos, m->pin + B, n * 4, cudaMemcpyHostToDevice, s));
+    B200W_CUDA(cudaMemcpyAsync(m->slot, m->pin + 2 * B, n * 4, cudaMemcpyHostToDevice, s));
     bf16* h = m->h;
     bf16* h2 = m->h2;
     embed_fwd(m->tok, m->w + m->p_embed, h, n, d, V, s); ++nl;
@@ -579,7 +595,36 @@ int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* posit
     gemm(m->nrm, d, m->p_lm, V, m->logits, nullptr);
     argmax_kernel<<<n, 1024, 0, s>>>(m->logits, V, m->next); ++nl;
     B200W_CUDA(cudaGetLastError());
-    if (next_tokens) B200W_CUDA(cudaMemcpyAsync(next_tokens, m->next, n * 4, cudaMemcpyDeviceToHost, s));
+    B200W_CUDA(cudaMemcpyAsync(m->pin + 3 * B, m->next, n * 4, cudaMemcpyDeviceToHost, s));
+    };
+
+    auto git = m->graphs.find(n);
+    if (git != m->graphs.end()) {
+      B200W_CUDA(cudaGraphLaunch(git->second, s));
+      step_launches = m->warm[n];
+    } else if (m->warm.count(n)) {
+      cudaGraph_t graph = nullptr;
+      B200W_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      try {
+        enqueue();
+      } catch (...) {
+        cudaStreamEndCapture(s, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      B200W_CUDA(cudaStreamEndCapture(s, &graph));
+      cudaGraphExec_t exec = nullptr;
+      B200W_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      m->graphs[n] = exec;
+      B200W_CUDA(cudaGraphLaunch(exec, s));
+    } else {
+      enqueue();
+      m->warm[n] = static_cast<int>(step_launches);
+    }
+    nl += step_launches;
+    B200W_CUDA(cudaStreamSynchronize(s));
+    if (next_tokens) memcpy(next_tokens, m->pin + 3 * B, n * 4);
     if (logits_out) {
       void* tmp = nullptr;
       B200W_CUDA(cudaMalloc(&tmp, static_cast<size_t>(n) * V * 4));

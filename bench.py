@@ -190,6 +190,8 @@ PER_DEVICE_BATCH = 8
 
 
 MICRO_BATCH = 1
+TRAFFIC = dict(bytes=402.0e6, note=("dram__bytes_read+write of the gate|up forward GEMM launch: 241.5 MB + 160.6 MB "
+                                    "vs 394 MB algorithmic (profiles/r01_ncu_gemm_pair.txt)"))
 
 
 def workload_config(n_gpus: int):
@@ -308,7 +310,10 @@ def run_ours(args):
         gpu_launches=int(launches),
         roofline=dict(bound="tensor", achieved=round(achieved, 1) if achieved else None,
                       peak=pk["sustained"], unit="TFLOP/s",
-                      frac=round(achieved / pk["sustained"], 4) if achieved else None, traffic=None,
+                      frac=round(achieved / pk["sustained"], 4) if achieved else None,
+                      # DRAM bytes of ONE launch (gate|up forward, M4096 N22016 K4096) from the committed
+                      # `ncu --set full` capture; its algorithmic bytes are 394 MB (A 33.5 + B 180.4 + D 180.4)
+                      traffic=TRAFFIC["bytes"], traffic_note=TRAFFIC["note"],
                       kernel="gemm_bf16_kernel (tcgen05)", launches=int(gemm_launches),
                       share_of_step=round(gemm_ms / ms, 4),
                       peak_source=f"{pk['source']} sustained cuBLAS bf16 (kernel timed inside a long step)"),

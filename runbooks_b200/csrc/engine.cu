@@ -931,8 +931,8 @@ int b200w_op_gemm_decode(b200w_ctx* ctx, const void* X, const void* W, void* out
       B200W_CUDA(cudaMemsetAsync(cnt, 0, ((N + 127) / 128) * 4, ctx->stream));
     }
     try {
-      gemm_decode(X, W, out, C, ws, cnt, M, N, K, N, ctx->stream);
-      gemm_decode(X, W, out, C, ws, cnt, M, N, K, N, ctx->stream);  // twice: the scratch must come back clean
+      gemm_decode(X, W, out, C, ws, cnt, M, N, K, N, 0, ctx->stream);
+      gemm_decode(X, W, out, C, ws, cnt, M, N, K, N, 0, ctx->stream);  // twice: the scratch must come back clean
       ctx->launches += 2;
       B200W_CUDA(cudaStreamSynchronize(ctx->stream));
     } catch (...) { cudaFree(ws); cudaFree(cnt); throw; }

@@ -510,6 +510,12 @@ void dispatch_major(bool a_mn, bool b_mn, const void* A, const void* B, OutT* D,
 // 7B model are split along K so that all SMs stream. Partial sums meet in an fp32 workspace
 // through red.global.add; the last CTA of a tile finalises it and leaves the workspace zeroed.
 // ==========================================================================================
+// epilogue activation of the decode GEMM: 0 = none, 1 = exact (erf) GeLU — transformers
+// get_activation("gelu"), what FalconMLP applies between its two projections
+__device__ __forceinline__ float decode_act(float x, int act) {
+  return act == 1 ? 0.5f * x * (1.f + erff(x * 0.70710678118654752f)) : x;
+}
+
 template <int MPAD>
 struct DecodeCfg {
   static constexpr int B_STAGE_BYTES = MPAD * BLOCK_K * 2;
@@ -522,7 +528,7 @@ template <int MPAD>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                    __nv_bfloat16* out, const __nv_bfloat16* C, float* ws, unsigned* counters, int M,
-                   int N, int K, int ldo, int kb_per_split) {
+                   int N, int K, int ldo, int kb_per_split, int act) {
   using cfg = DecodeCfg<MPAD>;
   constexpr int STAGES = cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -613,7 +619,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             if (split) atomicAdd(ws + static_cast<size_t>(b) * N + n, v);  // 32 lanes -> 128 B, coalesced
             else {
               const float cv = C ? __bfloat162float(C[static_cast<size_t>(b) * ldo + n]) : 0.f;
-              out[static_cast<size_t>(b) * ldo + n] = __float2bfloat16_rn(v + cv);
+              out[static_cast<size_t>(b) * ldo + n] = __float2bfloat16_rn(decode_act(v + cv, act));
             }
           }
         }
@@ -635,7 +641,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           const float v = __ldcg(p);
           *p = 0.f;
           const float cv = C ? __bfloat162float(C[static_cast<size_t>(b) * ldo + n]) : 0.f;
-          out[static_cast<size_t>(b) * ldo + n] = __float2bfloat16_rn(v + cv);
+          out[static_cast<size_t>(b) * ldo + n] = __float2bfloat16_rn(decode_act(v + cv, act));
         }
       }
       if (threadIdx.x == 0) counters[blockIdx.x] = 0;
@@ -651,7 +657,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
 template <int MPAD>
 void launch_decode(const void* X, const void* W, void* out, const void* C, float* ws, unsigned* counters,
-                   int M, int N, int K, int ldo, cudaStream_t stream) {
+                   int M, int N, int K, int ldo, int act, cudaStream_t stream) {
   using cfg = DecodeCfg<MPAD>;
   CUtensorMap tmW = make_tmap_bf16_2d(W, N, K, K, BLOCK_M, BLOCK_K);
   CUtensorMap tmX = make_tmap_bf16_2d(X, M, K, K, MPAD, BLOCK_K);
@@ -674,7 +680,7 @@ void launch_decode(const void* X, const void* W, void* out, const void* C, float
   splits = (num_kb + per - 1) / per;
   kern<<<dim3(n_tiles, splits), GEMM_THREADS, cfg::SMEM_BYTES, stream>>>(
       tmW, tmX, static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(C), ws, counters, M, N,
-      K, ldo, per);
+      K, ldo, per, act);
   B200W_CUDA(cudaGetLastError());
 }
 
@@ -693,12 +699,12 @@ static int pick_n_fast(int M, int N, int K) {
 // workspace of >= M*N floats and counters: zeroed unsigned[ceil(N/128)] enable split-K (both are
 // left zeroed again); pass nullptr to disable.
 void gemm_decode(const void* X, const void* W, void* out, const void* C, float* ws, unsigned* counters,
-                 int M, int N, int K, int ldo, cudaStream_t stream) {
+                 int M, int N, int K, int ldo, int act, cudaStream_t stream) {
   B200W_CHECK(M >= 1 && M <= 128 && N > 0 && K > 0, "decode GEMM handles 1..128 rows");
   B200W_CHECK(K % 8 == 0, "TMA needs 16-byte aligned row strides");
-  if (M <= 32) launch_decode<32>(X, W, out, C, ws, counters, M, N, K, ldo, stream);
-  else if (M <= 64) launch_decode<64>(X, W, out, C, ws, counters, M, N, K, ldo, stream);
-  else launch_decode<128>(X, W, out, C, ws, counters, M, N, K, ldo, stream);
+  if (M <= 32) launch_decode<32>(X, W, out, C, ws, counters, M, N, K, ldo, act, stream);
+  else if (M <= 64) launch_decode<64>(X, W, out, C, ws, counters, M, N, K, ldo, act, stream);
+  else launch_decode<128>(X, W, out, C, ws, counters, M, N, K, ldo, act, stream);
 }
 
 // Public launcher (C++). out_fp32: D/C are float, else bf16. C may alias D (accumulate in place).

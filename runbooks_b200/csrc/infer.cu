@@ -50,23 +50,61 @@ __device__ float block_reduce(float v, float* red, bool is_max) {
 }
 
 // LayerNorm with bias (oracle: torch.nn.LayerNorm as used by FalconDecoderLayer), fp32 statistics.
-__global__ void layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
-                                 const bf16* __restrict__ b, bf16* __restrict__ y, int d, float eps) {
+// One block per row, the row is read from HBM/L2 once and kept in registers (d <= 256*8*4).
+constexpr int LN_MAXP = 4;
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
+                 bf16* __restrict__ y, int d, float eps) {
   __shared__ float red[32];
   const bf16* xr = x + static_cast<size_t>(blockIdx.x) * d;
+  float v[LN_MAXP][8];
   float s = 0.f;
-  for (int i = threadIdx.x; i < d; i += blockDim.x) s += __bfloat162float(xr[i]);
-  const float mean = block_reduce(s, red, false) / d;
-  float v = 0.f;
-  for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    const float t = __bfloat162float(xr[i]) - mean;
-    v += t * t;
+#pragma unroll
+  for (int p = 0; p < LN_MAXP; ++p) {
+    const int c = (p * 256 + threadIdx.x) * 8;
+    if (c < d) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+      const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(wv[j]);
+        v[p][2 * j] = f.x;
+        v[p][2 * j + 1] = f.y;
+        s += f.x + f.y;
+      }
+    }
   }
-  const float rstd = rsqrtf(block_reduce(v, red, false) / d + eps);
+  const float mean = block_reduce(s, red, false) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int p = 0; p < LN_MAXP; ++p) {
+    const int c = (p * 256 + threadIdx.x) * 8;
+    if (c < d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = v[p][j] - mean;
+        q += t * t;
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_reduce(q, red, false) / d + eps);
   bf16* yr = y + static_cast<size_t>(blockIdx.x) * d;
-  for (int i = threadIdx.x; i < d; i += blockDim.x)
-    yr[i] = __float2bfloat16_rn((__bfloat162float(xr[i]) - mean) * rstd * __bfloat162float(w[i]) +
-                                __bfloat162float(b[i]));
+#pragma unroll
+  for (int p = 0; p < LN_MAXP; ++p) {
+    const int c = (p * 256 + threadIdx.x) * 8;
+    if (c < d) {
+      const uint4 uw = *reinterpret_cast<const uint4*>(w + c);
+      const uint4 ub = *reinterpret_cast<const uint4*>(b + c);
+      const uint32_t ww[4] = {uw.x, uw.y, uw.z, uw.w}, bb[4] = {ub.x, ub.y, ub.z, ub.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fw = unpack_bf16x2(ww[j]), fb = unpack_bf16x2(bb[j]);
+        o[j] = pack_bf16x2((v[p][2 * j] - mean) * rstd * fw.x + fb.x, (v[p][2 * j + 1] - mean) * rstd * fw.y + fb.y);
+      }
+      *reinterpret_cast<uint4*>(yr + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
 }
 
 // exact (erf) GeLU in place — transformers get_activation("gelu")
@@ -397,6 +435,7 @@ int b200w_infer_init(b200w_ctx* ctx, const b200w_infer_arch* arch, int max_batch
     B200W_CHECK(arch->num_heads % arch->num_kv_heads == 0, "heads must be a multiple of kv heads");
     B200W_CHECK(arch->hidden_size % 8 == 0 && arch->intermediate_size % 8 == 0 && arch->vocab_size % 8 == 0,
                 "sizes must be multiples of 8");
+    B200W_CHECK(arch->hidden_size <= 256 * 8 * LN_MAXP, "hidden_size too large for the decode LayerNorm");
     B200W_CHECK(arch->max_ctx >= 1 && arch->max_ctx <= 8192, "max_ctx must be in 1..8192");
     auto m = std::make_unique<Infer>();
     m->a = *arch;
@@ -553,8 +592,8 @@ int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* posit
     bf16* h = m->h;
     bf16* h2 = m->h2;
     embed_fwd(m->tok, m->w + m->p_embed, h, n, d, V, s); ++nl;
-    auto gemm = [&](const bf16* A, int K, size_t woff, int N, bf16* D, const bf16* C) {
-      gemm_decode(A, m->w + woff, D, C, m->ws, m->counters, n, N, K, N, s); ++nl;
+    auto gemm = [&](const bf16* A, int K, size_t woff, int N, bf16* D, const bf16* C, int act = 0) {
+      gemm_decode(A, m->w + woff, D, C, m->ws, m->counters, n, N, K, N, act, s); ++nl;
     };
     for (int l = 0; l < a.num_layers; ++l) {
       const auto& p = m->lp[l];
@@ -578,8 +617,7 @@ int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* posit
         // parallel residual: h' = h + dense(attn) + W2 gelu(W1 ln(h))   (modeling_falcon.py
         // FalconDecoderLayer.forward, parallel_attn branch)
         gemm(m->att, qd, p.wo, d, h2, h);
-        gemm(m->nrm, d, p.w1, f, m->mid, nullptr);
-        gelu_kernel<<<sm_count() * 2, 256, 0, s>>>(m->mid, static_cast<size_t>(n) * f); ++nl;
+        gemm(m->nrm, d, p.w1, f, m->mid, nullptr, /*act=*/1);  // exact GeLU in the GEMM epilogue
         gemm(m->mid, f, p.w2, d, h, h2);
       } else {
         gemm(m->att, qd, p.wo, d, h2, h);

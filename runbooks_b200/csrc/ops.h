@@ -15,8 +15,9 @@ void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int 
 
 // out[M, N] = X[M, K] W[N, K]^T (+ C) for a decode batch (M <= 128): swap-AB + split-K streaming
 // kernel. ws / counters: zeroed scratch (M*N floats, ceil(N/128) unsigned), left zeroed; nullable.
+// act: 0 none, 1 exact GeLU applied to (acc + C).
 void gemm_decode(const void* X, const void* W, void* out, const void* C, float* ws, unsigned* counters,
-                 int M, int N, int K, int ldo, cudaStream_t s);
+                 int M, int N, int K, int ldo, int act, cudaStream_t s);
 
 // ---- attention.cu --------------------------------------------------------------------------
 // Causal self-attention over packed sequences. qkv: [T, ld_qkv] with q at column 0, k at

@@ -50,8 +50,31 @@ __device__ __forceinline__ float ex2(float x) {  // one MUFU.EX2
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void compute_bar_sync() {  // the 256 compute threads only
+__device__ __forceinline__ void compute_bar_sync() {  // the 256 compute threads only (forward)
   asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+// The backward kernels use 16 compute warps (4 threads per row, 16 score columns each): with 2
+// warps per SM sub-partition their ~370-instruction block body ran at 6 cycles per instruction
+// (profiles/r01_ncu_attention_v6.txt) and set the pace instead of the tensor pipe.
+constexpr int BWD_NCOMPUTE = 512;
+constexpr int BWD_NTHREADS = 576;  // + MMA warp (16) + TMA warp (17)
+__device__ __forceinline__ void bwd_compute_bar_sync() {
+  asm volatile("bar.sync 1, 512;" ::: "memory");
+}
+// 32 fp32 TMEM columns of this thread's lane -> bf16 in global memory
+__device__ __forceinline__ void tmem_row32_to_global(uint32_t taddr, __nv_bfloat16* dst) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(__uint_as_float(r[i * 8 + 0]), __uint_as_float(r[i * 8 + 1]));
+    u.y = pack_bf16x2(__uint_as_float(r[i * 8 + 2]), __uint_as_float(r[i * 8 + 3]));
+    u.z = pack_bf16x2(__uint_as_float(r[i * 8 + 4]), __uint_as_float(r[i * 8 + 5]));
+    u.w = pack_bf16x2(__uint_as_float(r[i * 8 + 6]), __uint_as_float(r[i * 8 + 7]));
+    reinterpret_cast<uint4*>(dst)[i] = u;
+  }
 }
 
 // The MMA-issuing thread is a single in-order instruction stream: everything it executes per
@@ -366,7 +389,7 @@ constexpr int KV_SMEM = 2 * ATOM128 /*K*/ + 2 * ATOM128 /*V*/ + 3 * 2 * ATOM64 /
 // S^T[2]: [0,64) [64,128)   dP^T[2]: [128,192) [192,256)   dV: [256,384)   dK: [384,512)
 constexpr int KV_TMEM_COLS = 512;
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(BWD_NTHREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                      const float* __restrict__ lse2, const float* __restrict__ delta,
                      bf16* __restrict__ dqkv, int ld_qkv, int k_off, int v_off, int B, int S, int H,
@@ -411,10 +434,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       mbar_init(&bar_s[i], 1);
       mbar_init(&bar_d[i], 1);
     }
-    mbar_init(bar_p, NCOMPUTE);
+    mbar_init(bar_p, BWD_NCOMPUTE);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, KV_TMEM_COLS);
+  if (warp == 16) tmem_alloc(tmem_slot, KV_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -424,7 +447,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   auto iter_head = [&](int it) { return hk * G + it / nqb; };
   auto iter_qrow = [&](int it) { return (2 * jb + it % nqb) * BWD_BQ; };  // inside the sequence
 
-  if (warp == 9) {
+  if (warp == 17) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       auto load_q = [&](int it, int buf) {
@@ -457,7 +480,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         if (++buf == 3) { buf = 0; par ^= 1; }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 16) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       constexpr uint32_t idesc_st = make_idesc_bf16(128, BWD_BQ, false, false);  // S^T, dP^T
@@ -499,7 +522,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     }
   } else {
     // =============================== compute ===============================
-    const int q = warp & 3, hc = warp >> 2;
+    const int q = warp & 3, hc = warp >> 2;    // hc: which 16 of the block's 64 query columns
     const int row_local = q * 32 + lane;       // TMEM lane == key row inside the block
     const int kv_seq = kv0 + row_local;        // key position inside the sequence
     const uint32_t lane_base = (q * 32u) << 16;
@@ -512,7 +535,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     };
     const float stat_mul = (tid < 64) ? 1.f : scale;  // delta is kept pre-multiplied by the scale
     if (tid < 128) sStat[tid] = fetch_stat(0) * stat_mul;
-    compute_bar_sync();
+    bwd_compute_bar_sync();
 
     for (int it = 0; it < n_iter; ++it) {
       const int tb = it & 1;
@@ -523,32 +546,34 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       mbar_wait(&bar_s[tb], (it >> 1) & 1);
       __syncwarp();
       tc_fence_after();
-      uint32_t s_r[32], dp_r[32];
-      tmem_ld32(tmem_base + tb * 64 + lane_base + hc * 32, s_r);
-      tmem_ld32(tmem_base + 128 + tb * 64 + lane_base + hc * 32, dp_r);
+      uint32_t s_r[16], dp_r[16];
+      tmem_ld16(tmem_base + tb * 64 + lane_base + hc * 16, s_r);
+      tmem_ld16(tmem_base + 128 + tb * 64 + lane_base + hc * 16, dp_r);
       tmem_ld_wait();
       // staging buffer tb was last read by the dV/dK MMAs of block it-2
       if (it >= 2) mbar_wait(&bar_d[tb], ((it >> 1) - 1) & 1);
-      const float4* st_lse = reinterpret_cast<const float4*>(sStat + tb * 128 + hc * 32);
-      const float4* st_dl = reinterpret_cast<const float4*>(sStat + tb * 128 + 64 + hc * 32);
+      const float4* st_lse = reinterpret_cast<const float4*>(sStat + tb * 128 + hc * 16);
+      const float4* st_dl = reinterpret_cast<const float4*>(sStat + tb * 128 + 64 + hc * 16);
       const bool diag = (q_seq0 < kv0 + BWD_BKV);  // some (q, kv) pairs of this block are masked
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
+      for (int c8 = 0; c8 < 2; ++c8) {
         const float4 l0 = st_lse[c8 * 2], l1 = st_lse[c8 * 2 + 1];
         const float4 d0 = st_dl[c8 * 2], d1 = st_dl[c8 * 2 + 1];
         const float lse8[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
         const float dl8[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
         float p[8], ds[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = hc * 32 + c8 * 8 + e;  // query column inside the block
-          float pv = ex2(fmaf(__uint_as_float(s_r[c8 * 8 + e]), scale_log2, -lse8[e]));
-          if (diag && (q_seq0 + c < kv_seq)) pv = 0.f;
-          p[e] = pv;
-          // dS = P (dP - delta) * scale, with delta*scale precomputed
-          ds[e] = pv * fmaf(__uint_as_float(dp_r[c8 * 8 + e]), scale, -dl8[e]);
+        for (int e = 0; e < 8; ++e)
+          p[e] = ex2(fmaf(__uint_as_float(s_r[c8 * 8 + e]), scale_log2, -lse8[e]));
+        if (diag) {  // only the 2 blocks that straddle the diagonal pay for the mask
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (q_seq0 + hc * 16 + c8 * 8 + e < kv_seq) p[e] = 0.f;
         }
-        const uint32_t off = tb * ATOM128 + sw128_offset(row_local, hc * 4 + c8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)  // dS = P (dP - delta) * scale, with delta*scale precomputed
+          ds[e] = p[e] * fmaf(__uint_as_float(dp_r[c8 * 8 + e]), scale, -dl8[e]);
+        const uint32_t off = tb * ATOM128 + sw128_offset(row_local, hc * 2 + c8);
         *reinterpret_cast<uint4*>(sP + off) = pack8(p);
         *reinterpret_cast<uint4*>(sdS + off) = pack8(ds);
       }
@@ -556,22 +581,22 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       tc_fence_before();
       mbar_arrive(bar_p);
       if (have_next) sStat[(tb ^ 1) * 128 + tid] = stat_next * stat_mul;
-      compute_bar_sync();  // stats(it+1) visible; stats(it) no longer read
+      bwd_compute_bar_sync();  // stats(it+1) visible; stats(it) no longer read
     }
 
     mbar_wait(&bar_d[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);  // commits are cumulative
     __syncwarp();
     tc_fence_after();
-    // dV, dK: lane = key row; this thread stores 64 of the 128 dh columns of each
-    bf16* dvrow = dqkv + static_cast<size_t>(tok0 + kv_seq) * ld_qkv + v_off + hk * DH + hc * 64;
-    bf16* dkrow = dqkv + static_cast<size_t>(tok0 + kv_seq) * ld_qkv + k_off + hk * DH + hc * 64;
-    tmem_row64_to_global(tmem_dV + lane_base + hc * 64, dvrow, 1.f);
-    tmem_row64_to_global(tmem_dK + lane_base + hc * 64, dkrow, 1.f);
+    // dV, dK: lane = key row; this thread stores 32 of the 128 dh columns of each
+    bf16* dvrow = dqkv + static_cast<size_t>(tok0 + kv_seq) * ld_qkv + v_off + hk * DH + hc * 32;
+    bf16* dkrow = dqkv + static_cast<size_t>(tok0 + kv_seq) * ld_qkv + k_off + hk * DH + hc * 32;
+    tmem_row32_to_global(tmem_dV + lane_base + hc * 32, dvrow);
+    tmem_row32_to_global(tmem_dK + lane_base + hc * 32, dkrow);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc(tmem_base, KV_TMEM_COLS);
   }
@@ -586,7 +611,7 @@ constexpr int DQ_SMEM = 2 * ATOM128 /*Q*/ + 2 * ATOM128 /*dO*/ + 3 * 2 * ATOM64 
 // S[2]: [0,64) [64,128)   dP[2]: [128,192) [192,256)   dQ: [256,384)
 constexpr int DQ_TMEM_COLS = 512;
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(BWD_NTHREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const float* __restrict__ lse2, const float* __restrict__ delta,
                    bf16* __restrict__ dqkv, int ld_qkv, int k_off, int v_off, int B, int S, int H,
@@ -628,17 +653,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       mbar_init(&bar_s[i], 1);
       mbar_init(&bar_dq[i], 1);
     }
-    mbar_init(bar_p, NCOMPUTE);
+    mbar_init(bar_p, BWD_NCOMPUTE);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, DQ_TMEM_COLS);
+  if (warp == 16) tmem_alloc(tmem_slot, DQ_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_dQ = tmem_base + 256;
 
-  if (warp == 9) {
+  if (warp == 17) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       auto load_kv = [&](int j, int buf) {
@@ -670,7 +695,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         if (++buf == 3) { buf = 0; par ^= 1; }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 16) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, DQ_BKV, false, false);  // S, dP
@@ -721,23 +746,26 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       mbar_wait(&bar_s[tb], (j >> 1) & 1);
       __syncwarp();
       tc_fence_after();
-      uint32_t s_r[32], dp_r[32];
-      tmem_ld32(tmem_base + tb * 64 + lane_base + hc * 32, s_r);
-      tmem_ld32(tmem_base + 128 + tb * 64 + lane_base + hc * 32, dp_r);
+      uint32_t s_r[16], dp_r[16];
+      tmem_ld16(tmem_base + tb * 64 + lane_base + hc * 16, s_r);
+      tmem_ld16(tmem_base + 128 + tb * 64 + lane_base + hc * 16, dp_r);
       tmem_ld_wait();
       if (j >= 2) mbar_wait(&bar_dq[tb], ((j >> 1) - 1) & 1);  // dS buffer tb: read by dQ MMA (j-2)
-      const int col0 = j * DQ_BKV + hc * 32;
+      const int col0 = j * DQ_BKV + hc * 16;
       const bool diag = (j * DQ_BKV + DQ_BKV - 1) > q0;
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        float ds[8];
+      for (int c8 = 0; c8 < 2; ++c8) {
+        float p[8], ds[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float pv = ex2(fmaf(__uint_as_float(s_r[c8 * 8 + e]), scale_log2, -my_lse));
-          if (diag && (col0 + c8 * 8 + e > row_seq)) pv = 0.f;
-          ds[e] = pv * fmaf(__uint_as_float(dp_r[c8 * 8 + e]), scale, -my_dl);
+        for (int e = 0; e < 8; ++e) p[e] = ex2(fmaf(__uint_as_float(s_r[c8 * 8 + e]), scale_log2, -my_lse));
+        if (diag) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (col0 + c8 * 8 + e > row_seq) p[e] = 0.f;
         }
-        *reinterpret_cast<uint4*>(sdS + tb * ATOM128 + sw128_offset(row_local, hc * 4 + c8)) = pack8(ds);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ds[e] = p[e] * fmaf(__uint_as_float(dp_r[c8 * 8 + e]), scale, -my_dl);
+        *reinterpret_cast<uint4*>(sdS + tb * ATOM128 + sw128_offset(row_local, hc * 2 + c8)) = pack8(ds);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -747,13 +775,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     mbar_wait(&bar_dq[(njb - 1) & 1], ((njb - 1) >> 1) & 1);  // commits are cumulative
     __syncwarp();
     tc_fence_after();
-    bf16* dqrow = dqkv + static_cast<size_t>(tok0 + row_seq) * ld_qkv + h * DH + hc * 64;
-    tmem_row64_to_global(tmem_dQ + lane_base + hc * 64, dqrow, 1.f);
+    bf16* dqrow = dqkv + static_cast<size_t>(tok0 + row_seq) * ld_qkv + h * DH + hc * 32;
+    tmem_row32_to_global(tmem_dQ + lane_base + hc * 32, dqrow);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc(tmem_base, DQ_TMEM_COLS);
   }
@@ -801,11 +829,11 @@ void attention_bwd(const void* qkv, int ld_qkv, int k_off, int v_off, const void
     attr = true;
   }
   const float scale_log2 = scale * 1.4426950408889634f;
-  attn_bwd_dkdv_kernel<<<(S / BWD_BKV) * B * Hkv, NTHREADS, KV_SMEM, s>>>(
+  attn_bwd_dkdv_kernel<<<(S / BWD_BKV) * B * Hkv, BWD_NTHREADS, KV_SMEM, s>>>(
       tm_qkv, tm_do, lse2, delta, static_cast<bf16*>(dqkv), ld_qkv, k_off, v_off, B, S, H, Hkv, scale,
       scale_log2);
   B200W_CUDA(cudaGetLastError());
-  attn_bwd_dq_kernel<<<(S / DQ_BQ) * B * H, NTHREADS, DQ_SMEM, s>>>(
+  attn_bwd_dq_kernel<<<(S / DQ_BQ) * B * H, BWD_NTHREADS, DQ_SMEM, s>>>(
       tm_qkv, tm_do, lse2, delta, static_cast<bf16*>(dqkv), ld_qkv, k_off, v_off, B, S, H, Hkv, scale,
       scale_log2);
   B200W_CUDA(cudaGetLastError());

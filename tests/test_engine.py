@@ -131,3 +131,34 @@ def test_engine_rejects_bad_batches():
     with pytest.raises(B200WError):          # every label ignored
         e.train_step(ids, np.full_like(ids, -100))
     e.close()
+
+
+def test_real_width_layer_at_full_sequence_length():
+    """BASELINE's sizes: one decoder layer of true Llama-2-7B width (d 4096, ffn 11008, 32 heads) on
+    a full 4096-token sequence, forward + backward through the engine vs the oracle evaluated in
+    fp32 ON THE SAME GPU (the CPU oracle would need minutes). Small vocabulary keeps it light. This
+    exercises the CTA-pair GEMM, the real attention grid (1024 CTAs) and the S = 4096 RoPE table."""
+    oa = O.Arch(1024, 4096, 11008, 1, 32, 32, 128, 4096, 1e-5, 10000.0)
+    params = O.seeded_params(oa, 31)
+    rng = np.random.default_rng(5)
+    ids = rng.integers(0, oa.vocab_size, size=(1, 4096))
+    labels = ids.copy()
+    labels[0, :500] = -100
+    e = _engine(LlamaArch(1024, 4096, 11008, 1, 32, 32, 128, 4096, 1e-5, 10000.0), params, 1)
+    loss = e.forward_backward(ids, labels)
+    # fp32 reference on the GPU (TF32 off: torch's default for matmul)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    pt = {k: torch.tensor(v, device="cuda", requires_grad=True) for k, v in params.items()}
+    logits = O.forward(pt, torch.tensor(ids, device="cuda"), oa)
+    ref_loss, _ = O.causal_lm_loss(logits, torch.tensor(labels, device="cuda"))
+    ref_loss.backward()
+    print(f"real-width layer: loss {loss:.6f} vs fp32 {float(ref_loss):.6f}")
+    assert abs(loss - float(ref_loss)) < 1e-3 * float(ref_loss)
+    worst = 0.0
+    for name, shape in e.params():
+        g = torch.tensor(e.read_state(name, shape, "grad"))
+        err = rel_err(g, pt[name].grad.cpu())
+        worst = max(worst, err)
+        assert err < 3e-2, (name, err)
+    print(f"real-width layer: worst gradient rel_err {worst:.3e}")
+    e.close()

@@ -460,6 +460,14 @@ long count_valid(const int32_t* labels, int n_seqs, int S) {
 }
 
 void upload_batch(b200w_ctx* c, const int32_t* ids, const int32_t* labels, size_t n_tok) {
+  // nn.Embedding / cross_entropy raise on out-of-range indices; here that would be a device trap
+  // that poisons the CUDA context, so reject bad batches on the host (n_tok integer compares)
+  const int32_t V = c->arch.vocab_size;
+  for (size_t i = 0; i < n_tok; ++i) {
+    if (ids[i] < 0 || ids[i] >= V) throw Error("check failed: token id outside the vocabulary");
+    if (labels[i] != -100 && (labels[i] < 0 || labels[i] >= V))
+      throw Error("check failed: label outside the vocabulary (use -100 to ignore)");
+  }
   ensure_ids(c, n_tok);
   memcpy(c->pinned, ids, n_tok * sizeof(int32_t));
   memcpy(c->pinned + n_tok, labels, n_tok * sizeof(int32_t));

@@ -130,6 +130,14 @@ def test_engine_rejects_bad_batches():
         e.train_step(np.concatenate([ids, ids[:1]]), np.concatenate([ids, ids[:1]]))
     with pytest.raises(B200WError):          # every label ignored
         e.train_step(ids, np.full_like(ids, -100))
+    bad = ids.copy()
+    bad[0, 3] = arch.vocab_size              # nn.Embedding would raise IndexError
+    with pytest.raises(B200WError):
+        e.train_step(bad, ids)
+    with pytest.raises(B200WError):          # label outside the vocabulary
+        e.train_step(ids, bad)
+    loss, _ = e.train_step(ids, ids)         # the context survived the rejected batches
+    assert np.isfinite(loss)
     e.close()
 
 

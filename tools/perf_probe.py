@@ -12,7 +12,9 @@ from runbooks_b200.engine import Engine  # noqa: E402
 from util import call  # noqa: E402
 
 
-def timeit(fn, iters=10, warm=3):
+def timeit(fn, iters=10, warm=3, e=None):
+    """Median DEVICE time of fn(): CUDA events on the library's own stream (b200w_timer_*), L2
+    flushed between iterations."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -21,18 +23,19 @@ def timeit(fn, iters=10, warm=3):
     for _ in range(iters):
         flush.zero_()
         torch.cuda.synchronize()
-        # the library runs on its own stream and synchronises inside the hook: wall-clock the call
-        e0 = torch.cuda.Event(enable_timing=True)
-        import time
-        t0 = time.perf_counter()
+        ENGINE.timer_start()
         fn()
-        ts.append(time.perf_counter() - t0)
+        ts.append(ENGINE.timer_stop() * 1e-3)
     ts.sort()
     return ts[len(ts) // 2]
 
 
+ENGINE = None
+
+
 def main():
-    e = Engine(0)
+    global ENGINE
+    e = ENGINE = Engine(0)
     out = {}
     T, d, f, V = 4096, 4096, 11008, 32000
     shapes = {

@@ -88,43 +88,60 @@ __device__ __forceinline__ uint32_t desc_lo_k(uint32_t smem_addr) {   // K-major
 __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t smem_addr) {  // MN-major, atoms ATOM64 apart
   return ((smem_addr & 0x3FFFFu) >> 4) | ((ATOM64 >> 4) << 16);
 }
+// The MMA warp runs its loop CONVERGENTLY (all 32 lanes: loop control, barrier waits, descriptor
+// arithmetic — ptxas keeps all of it in uniform registers) and each tcgen05 instruction is
+// guarded by an `elect.sync` predicate inside the same asm block, so exactly one lane issues.
+// With the issue code inside an `if (lane == 0)` region ptxas instead wrapped every UTCHMMA in an
+// ELECT / BRA.U.ANY loop with R2UR moves (~12 instructions per MMA) and the issuing thread, not
+// the tensor pipe, paced the kernels (profiles/r01_ncu_attention_v7.txt).
 template <bool ACC>
-__device__ __forceinline__ void mma_raw(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+__device__ __forceinline__ void mma_raw(bool, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
       "setp.ne.b32 p, %5, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
       "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(ACC ? 1u : 0u)
       : "memory");
 }
-__device__ __forceinline__ void mma_raw_dyn(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+__device__ __forceinline__ void mma_raw_dyn(bool, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
                                             uint32_t idesc, uint32_t acc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
       "setp.ne.b32 p, %5, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
       "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(acc)
       : "memory");
 }
 // K-major x K-major over dh = 128: operands are 2 atoms along the contraction, `*_atom16` apart
 // (in 16-byte units). a_lo / b_lo: desc_lo_k() of the first atom. 8 MMAs, the first overwrites.
-__device__ __forceinline__ void mma_kmajor_dh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_atom16,
-                                              uint32_t b_lo, uint32_t b_atom16, uint32_t idesc) {
-  mma_raw<false>(tmem_d, a_lo, b_lo, idesc);
+__device__ __forceinline__ void mma_kmajor_dh(bool leader, uint32_t tmem_d, uint32_t a_lo,
+                                              uint32_t a_atom16, uint32_t b_lo, uint32_t b_atom16,
+                                              uint32_t idesc) {
+  mma_raw<false>(leader, tmem_d, a_lo, b_lo, idesc);
 #pragma unroll
   for (int k = 1; k < DH / 16; ++k)
-    mma_raw<true>(tmem_d, a_lo + (k / 4) * a_atom16 + (k % 4) * 2, b_lo + (k / 4) * b_atom16 + (k % 4) * 2,
-                  idesc);
+    mma_raw<true>(leader, tmem_d, a_lo + (k / 4) * a_atom16 + (k % 4) * 2,
+                  b_lo + (k / 4) * b_atom16 + (k % 4) * 2, idesc);
 }
 // D (+)= A[128 x 64, K-major, one atom] * B[MN-major: N = dh (2 atoms, ATOM64 apart), K = 64 rows]
 // a_lo: desc_lo_k(A), b_lo: desc_lo_mn(B). 4 MMAs.
-__device__ __forceinline__ void mma_a64_bmn(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
-                                            uint32_t accumulate_first) {
-  mma_raw_dyn(tmem_d, a_lo, b_lo, idesc, accumulate_first);
+__device__ __forceinline__ void mma_a64_bmn(bool leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                            uint32_t idesc, uint32_t accumulate_first) {
+  mma_raw_dyn(leader, tmem_d, a_lo, b_lo, idesc, accumulate_first);
 #pragma unroll
-  for (int k = 1; k < 4; ++k) mma_raw<true>(tmem_d, a_lo + k * 2, b_lo + k * (2048 >> 4), idesc);
+  for (int k = 1; k < 4; ++k) mma_raw<true>(leader, tmem_d, a_lo + k * 2, b_lo + k * (2048 >> 4), idesc);
+}
+// convergent: one elected lane commits
+__device__ __forceinline__ void commit_if(bool, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar))
+      : "memory");
 }
 
 __device__ __forceinline__ uint4 pack8(const float (&p)[8]) {
@@ -248,7 +265,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
     }
   } else if (warp == 8) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    {  // the whole warp runs this loop; only `leader` issues
+      const bool leader = lane == 0;
       constexpr uint32_t idesc_s = make_idesc_bf16(128, FWD_BKV, false, false);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, DH, false, true);
       constexpr uint32_t BUF16 = (2 * ATOM64) >> 4, A128 = ATOM128 >> 4, A64 = ATOM64 >> 4;
@@ -257,22 +275,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
       mbar_wait(bar_q, 0);
       mbar_wait(&bar_k[0], 0);
       tc_fence_after();
-      mma_kmajor_dh(tmem_base, q_lo, A128, k_lo, A64, idesc_s);  // S(0)
-      tc_commit(&bar_s[0]);
+      mma_kmajor_dh(leader, tmem_base, q_lo, A128, k_lo, A64, idesc_s);  // S(0)
+      commit_if(leader, &bar_s[0]);
       for (int j = 0; j < njb; ++j) {
         const uint32_t buf = j & 1;
         if (j + 1 < njb) {  // S buffer buf^1 was drained by the compute warps before bar_p(j-1)
           mbar_wait(&bar_k[buf ^ 1], ((j + 1) >> 1) & 1);
           tc_fence_after();
-          mma_kmajor_dh(tmem_base + (buf ^ 1) * 64, q_lo, A128, k_lo + (buf ^ 1) * BUF16, A64, idesc_s);
-          tc_commit(&bar_s[buf ^ 1]);
+          mma_kmajor_dh(leader, tmem_base + (buf ^ 1) * 64, q_lo, A128, k_lo + (buf ^ 1) * BUF16, A64, idesc_s);
+          commit_if(leader, &bar_s[buf ^ 1]);
         }
         mbar_wait(bar_p, j & 1);  // P(j) written (and S(j) drained)
         mbar_wait(&bar_v[buf], (j >> 1) & 1);
         tc_fence_after();
-        mma_a64_bmn(tmem_O, p_lo, v_lo + buf * BUF16, idesc_o, j != 0);
-        tc_commit(bar_o);
-        tc_commit(&bar_vfree[buf]);
+        mma_a64_bmn(leader, tmem_O, p_lo, v_lo + buf * BUF16, idesc_o, j != 0);
+        commit_if(leader, bar_o);
+        commit_if(leader, &bar_vfree[buf]);
       }
     }
   } else {
@@ -482,7 +500,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     }
   } else if (warp == 16) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    {  // the whole warp runs this loop; only `leader` issues
+      const bool leader = lane == 0;
       constexpr uint32_t idesc_st = make_idesc_bf16(128, BWD_BQ, false, false);  // S^T, dP^T
       constexpr uint32_t idesc_dv = make_idesc_bf16(128, DH, false, true);       // dV, dK
       constexpr uint32_t BUF16 = (2 * ATOM64) >> 4, A128 = ATOM128 >> 4, A64 = ATOM64 >> 4;
@@ -491,9 +510,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       const uint32_t q_mn = desc_lo_mn(smem_u32(sQ)), do_mn = desc_lo_mn(smem_u32(sdO));
       const uint32_t p_lo = desc_lo_k(smem_u32(sP)), ds_lo = desc_lo_k(smem_u32(sdS));
       auto issue_scores = [&](uint32_t tb, uint32_t qb) {  // S^T = K Q^T, dP^T = V dO^T -> TMEM bufs tb
-        mma_kmajor_dh(tmem_base + tb * 64, k_lo, A128, q_lo + qb * BUF16, A64, idesc_st);
-        mma_kmajor_dh(tmem_base + 128 + tb * 64, v_lo, A128, do_lo + qb * BUF16, A64, idesc_st);
-        tc_commit(&bar_s[tb]);
+        mma_kmajor_dh(leader, tmem_base + tb * 64, k_lo, A128, q_lo + qb * BUF16, A64, idesc_st);
+        mma_kmajor_dh(leader, tmem_base + 128 + tb * 64, v_lo, A128, do_lo + qb * BUF16, A64, idesc_st);
+        commit_if(leader, &bar_s[tb]);
       };
       mbar_wait(bar_kv, 0);
       mbar_wait(&bar_q[0], 0);
@@ -512,10 +531,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         tc_fence_after();
         // dV += P^T dO, dK += dS^T Q : A K-major [128 kv x 64 q], B MN-major (N = dh, K = q rows)
         const uint32_t pb = (it & 1) * A128;  // P/dS staging buffer of this block
-        mma_a64_bmn(tmem_dV, p_lo + pb, do_mn + qb * BUF16, idesc_dv, it != 0);
-        mma_a64_bmn(tmem_dK, ds_lo + pb, q_mn + qb * BUF16, idesc_dv, it != 0);
-        tc_commit(&bar_d[it & 1]);
-        tc_commit(&bar_qfree[qb]);
+        mma_a64_bmn(leader, tmem_dV, p_lo + pb, do_mn + qb * BUF16, idesc_dv, it != 0);
+        mma_a64_bmn(leader, tmem_dK, ds_lo + pb, q_mn + qb * BUF16, idesc_dv, it != 0);
+        commit_if(leader, &bar_d[it & 1]);
+        commit_if(leader, &bar_qfree[qb]);
         qb = nqb_;
         qpar = npar;
       }
@@ -697,7 +716,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
   } else if (warp == 16) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    {  // the whole warp runs this loop; only `leader` issues
+      const bool leader = lane == 0;
       constexpr uint32_t idesc_s = make_idesc_bf16(128, DQ_BKV, false, false);  // S, dP
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, DH, false, true);      // dQ
       constexpr uint32_t BUF16 = (2 * ATOM64) >> 4, A128 = ATOM128 >> 4, A64 = ATOM64 >> 4;
@@ -705,9 +725,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const uint32_t k_lo = desc_lo_k(smem_u32(sK)), v_lo = desc_lo_k(smem_u32(sV));
       const uint32_t k_mn = desc_lo_mn(smem_u32(sK)), ds_lo = desc_lo_k(smem_u32(sdS));
       auto issue_scores = [&](uint32_t tb, uint32_t kb) {  // S = Q K^T, dP = dO V^T -> TMEM bufs tb
-        mma_kmajor_dh(tmem_base + tb * 64, q_lo, A128, k_lo + kb * BUF16, A64, idesc_s);
-        mma_kmajor_dh(tmem_base + 128 + tb * 64, do_lo, A128, v_lo + kb * BUF16, A64, idesc_s);
-        tc_commit(&bar_s[tb]);
+        mma_kmajor_dh(leader, tmem_base + tb * 64, q_lo, A128, k_lo + kb * BUF16, A64, idesc_s);
+        mma_kmajor_dh(leader, tmem_base + 128 + tb * 64, do_lo, A128, v_lo + kb * BUF16, A64, idesc_s);
+        commit_if(leader, &bar_s[tb]);
       };
       mbar_wait(bar_q, 0);
       mbar_wait(&bar_kv[0], 0);
@@ -725,9 +745,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         mbar_wait(bar_p, j & 1);
         tc_fence_after();
         // dQ += dS K : A K-major [128 q x 64 kv], B = K as MN-major (N = dh, K = kv rows)
-        mma_a64_bmn(tmem_dQ, ds_lo + (j & 1) * A128, k_mn + kb * BUF16, idesc_dq, j != 0);
-        tc_commit(&bar_dq[j & 1]);
-        tc_commit(&bar_kvfree[kb]);
+        mma_a64_bmn(leader, tmem_dQ, ds_lo + (j & 1) * A128, k_mn + kb * BUF16, idesc_dq, j != 0);
+        commit_if(leader, &bar_dq[j & 1]);
+        commit_if(leader, &bar_kvfree[kb]);
         kb = nkb;
         kpar = npar;
       }

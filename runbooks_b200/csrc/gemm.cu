@@ -215,12 +215,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: convergent warp, elect.sync-predicated issue ==========
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
       // K-major: next UMMA_K = +32 B inside the atom row. MN-major: next 16 K-rows = +2048 B.
-      constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);
-      constexpr uint32_t b_kstep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+      constexpr uint32_t a_kstep = (A_MN ? (UMMA_K * 128) : (UMMA_K * 2)) >> 4;
+      constexpr uint32_t b_kstep = (B_MN ? (UMMA_K * 128) : (UMMA_K * 2)) >> 4;
       constexpr uint32_t a_lbo = A_MN ? (BLOCK_K * 128) : 16;
       constexpr uint32_t b_lbo = B_MN ? (BLOCK_K * 128) : 16;
       int stage = 0;
@@ -235,17 +235,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * cfg::STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
-          const uint64_t da = make_smem_desc(sa, a_lbo, 1024);
-          const uint64_t db = make_smem_desc(sb, b_lbo, 1024);
+          const uint32_t a_lo = make_desc_lo(sa, a_lbo), b_lo = make_desc_lo(sa + A_STAGE_BYTES, b_lbo);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            tc_mma_bf16(tmem_d, desc_advance(da, k * a_kstep), desc_advance(db, k * b_kstep), idesc,
-                        (kb | k) != 0);
-          tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+            tc_mma_bf16_elect(tmem_d, a_lo + k * a_kstep, b_lo + k * b_kstep, idesc, (kb | k) != 0);
+          tc_commit_elect(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull_bar[acc]);
+        tc_commit_elect(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -370,10 +367,10 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {  // CTA-uniform: the whole warp of the leader CTA runs the loop, one lane issues
       constexpr uint32_t idesc = make_idesc_bf16(256, PAIR_N, A_MN, B_MN);
-      constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);
-      constexpr uint32_t b_kstep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+      constexpr uint32_t a_kstep = (A_MN ? (UMMA_K * 128) : (UMMA_K * 2)) >> 4;
+      constexpr uint32_t b_kstep = (B_MN ? (UMMA_K * 128) : (UMMA_K * 2)) >> 4;
       constexpr uint32_t a_lbo = A_MN ? (BLOCK_K * 128) : 16;
       constexpr uint32_t b_lbo = B_MN ? (BLOCK_K * 128) : 16;
       int stage = 0;
@@ -388,17 +385,14 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * PAIR_STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
-          const uint64_t da = make_smem_desc(sa, a_lbo, 1024);
-          const uint64_t db = make_smem_desc(sb, b_lbo, 1024);
+          const uint32_t a_lo = make_desc_lo(sa, a_lbo), b_lo = make_desc_lo(sa + A_STAGE_BYTES, b_lbo);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            tc_mma_bf16_pair(tmem_d, desc_advance(da, k * a_kstep), desc_advance(db, k * b_kstep),
-                             idesc, (kb | k) != 0);
-          tc_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs
+            tc_mma_bf16_pair_elect(tmem_d, a_lo + k * a_kstep, b_lo + k * b_kstep, idesc, (kb | k) != 0);
+          tc_commit_pair_elect(&empty_bar[stage]);  // frees the slot in both CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit_pair(&tfull_bar[acc]);
+        tc_commit_pair_elect(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -578,7 +572,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, MPAD, false, false);
       int stage = 0;
       uint32_t phase = 0;
@@ -586,16 +580,14 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * cfg::STAGE_BYTES);
-        const uint64_t da = make_smem_desc(sa, 16, 1024);
-        const uint64_t db = make_smem_desc(sa + A_STAGE_BYTES, 16, 1024);
+        const uint32_t a_lo = make_desc_lo(sa, 16), b_lo = make_desc_lo(sa + A_STAGE_BYTES, 16);
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-          tc_mma_bf16(tmem_base, desc_advance(da, k * UMMA_K * 2), desc_advance(db, k * UMMA_K * 2), idesc,
-                      (i | k) != 0);
-        tc_commit(&empty_bar[stage]);
+          tc_mma_bf16_elect(tmem_base, a_lo + k * 2, b_lo + k * 2, idesc, (i | k) != 0);
+        tc_commit_elect(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      tc_commit(done_bar);
+      tc_commit_elect(done_bar);
     }
   } else if (warp >= 4) {
     // lane of TMEM = output feature n; column = batch row b

@@ -116,6 +116,48 @@ __device__ __forceinline__ void mma_raw_dyn(bool, uint32_t tmem_d, uint32_t a_lo
       "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(acc)
       : "memory");
 }
+// A operand from TMEM (bf16 pairs, 8 columns per K = 16 step; lane = row), B from smem.
+// Operands that are constant for a CTA (Q, dO) or produced by the compute warps (P, dS) live in
+// TMEM so that they cost no shared-memory bandwidth: at 128 B/clk that, not the tensor pipe,
+// was what bounded these kernels.
+template <bool ACC>
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(ACC ? 1u : 0u)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_dyn(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,
+                                           uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D = A[128 x dh, TMEM] * B[K-major, 2 atoms `b_atom16` apart]^T : 8 MMAs, the first overwrites
+__device__ __forceinline__ void mma_ts_kmajor_dh(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo,
+                                                 uint32_t b_atom16, uint32_t idesc) {
+  mma_ts<false>(tmem_d, tmem_a, b_lo, idesc);
+#pragma unroll
+  for (int k = 1; k < DH / 16; ++k)
+    mma_ts<true>(tmem_d, tmem_a + k * 8, b_lo + (k / 4) * b_atom16 + (k % 4) * 2, idesc);
+}
+// D (+)= A[128 x 64, TMEM] * B[MN-major: N = dh (2 atoms, ATOM64 apart), K = 64 rows] : 4 MMAs
+__device__ __forceinline__ void mma_ts_a64_bmn(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,
+                                               uint32_t accumulate_first) {
+  mma_ts_dyn(tmem_d, tmem_a, b_lo, idesc, accumulate_first);
+#pragma unroll
+  for (int k = 1; k < 4; ++k) mma_ts<true>(tmem_d, tmem_a + k * 8, b_lo + k * (2048 >> 4), idesc);
+}
+
 // K-major x K-major over dh = 128: operands are 2 atoms along the contraction, `*_atom16` apart
 // (in 16-byte units). a_lo / b_lo: desc_lo_k() of the first atom. 8 MMAs, the first overwrites.
 __device__ __forceinline__ void mma_kmajor_dh(bool leader, uint32_t tmem_d, uint32_t a_lo,
@@ -625,30 +667,30 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 // backward, part 2: dQ
 // ==========================================================================================
 constexpr int DQ_BQ = 128, DQ_BKV = 64;
-constexpr int DQ_SMEM = 2 * ATOM128 /*Q*/ + 2 * ATOM128 /*dO*/ + 3 * 2 * ATOM64 /*K x3*/ +
-                        3 * 2 * ATOM64 /*V x3*/ + 2 * ATOM128 /*dS x2*/ + 256;
-// S[2]: [0,64) [64,128)   dP[2]: [128,192) [192,256)   dQ: [256,384)
+// operands need 96 KB; asking for > half of the SM's shared memory keeps one CTA per SM, which the
+// 512-column TMEM allocation assumes (a second resident CTA would only spin in tcgen05.alloc)
+constexpr int DQ_SMEM = 120 * 1024;
+static_assert(3 * 2 * ATOM64 + 3 * 2 * ATOM64 + 256 <= DQ_SMEM, "dQ kernel shared memory");
+// S[2]: [0,64) [64,128)   dP[2]: [128,192) [192,256) (dS bf16 re-uses the first 32 columns of the
+// dP buffer it was computed from)   dQ: [256,384)   Q bf16: [384,448)   dO bf16: [448,512)
 constexpr int DQ_TMEM_COLS = 512;
 
 __global__ void __launch_bounds__(BWD_NTHREADS, 1)
-attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                   const float* __restrict__ lse2, const float* __restrict__ delta,
-                   bf16* __restrict__ dqkv, int ld_qkv, int k_off, int v_off, int B, int S, int H,
-                   int Hkv, float scale, float scale_log2) {
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __restrict__ qkv,
+                   const bf16* __restrict__ dout, int ld_out, const float* __restrict__ lse2,
+                   const float* __restrict__ delta, bf16* __restrict__ dqkv, int ld_qkv, int k_off,
+                   int v_off, int B, int S, int H, int Hkv, float scale, float scale_log2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   require_1024_aligned(smem);
-  uint8_t* sQ = smem;                      // 2 atoms x [128 q x 128 B]
-  uint8_t* sdO = sQ + 2 * ATOM128;
-  uint8_t* sK = sdO + 2 * ATOM128;         // 3 bufs x 2 atoms x [64 kv x 128 B]
+  uint8_t* sK = smem;                      // 3 bufs x 2 atoms x [64 kv x 128 B]
   uint8_t* sV = sK + 3 * 2 * ATOM64;
-  uint8_t* sdS = sV + 3 * 2 * ATOM64;      // 2 bufs x dS [128 q x 64 kv]
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sdS + 2 * ATOM128);
-  uint64_t* bar_kv = bar_q + 1;   // [3]
-  uint64_t* bar_s = bar_kv + 3;   // [2]
-  uint64_t* bar_dq = bar_s + 2;   // [2] dQ MMAs that read dS buffer b retired
-  uint64_t* bar_p = bar_dq + 2;
-  uint64_t* bar_kvfree = bar_p + 1;  // [3] MMAs that read K/V buffer b retired (for the TMA warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kvfree + 3);
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sV + 3 * 2 * ATOM64);  // [3]
+  uint64_t* bar_s = bar_kv + 3;       // [2] S, dP (j) in TMEM
+  uint64_t* bar_dq = bar_s + 2;       //     dQ MMAs of the last block retired
+  uint64_t* bar_p = bar_dq + 1;       //     dS (j) in TMEM (512 arrivals)
+  uint64_t* bar_kvfree = bar_p + 1;   // [3] MMAs that read K/V buffer b retired (for the TMA warp)
+  uint64_t* bar_qready = bar_kvfree + 3;  // Q, dO rows are in TMEM (512 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qready + 1);
 
   const int nq = S / DQ_BQ;
   const int bh = blockIdx.x % (B * H);
@@ -662,17 +704,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
-    tma_prefetch_desc(&tm_do);
-    mbar_init(bar_q, 1);
     for (int i = 0; i < 3; ++i) {
       mbar_init(&bar_kv[i], 1);
       mbar_init(&bar_kvfree[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_dq[i], 1);
-    }
+    for (int i = 0; i < 2; ++i) mbar_init(&bar_s[i], 1);
+    mbar_init(bar_dq, 1);
     mbar_init(bar_p, BWD_NCOMPUTE);
+    mbar_init(bar_qready, BWD_NCOMPUTE);
     fence_barrier_init();
   }
   if (warp == 16) tmem_alloc(tmem_slot, DQ_TMEM_COLS);
@@ -680,7 +719,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_dQ = tmem_base + 256;
+  const uint32_t tmem_dQ = tmem_base + 256, tmem_Q = tmem_base + 384, tmem_dO = tmem_base + 448;
 
   if (warp == 17) {
     // =============================== TMA producer ===============================
@@ -695,14 +734,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                       tok0 + j * DQ_BKV);
         }
       };
-      mbar_arrive_expect_tx(bar_q, 4 * ATOM128);
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          tma_load_2d(sQ + a * ATOM128 + r * ATOM64, &tm_qkv, bar_q, h * DH + a * 64, tok0 + q0 + r * 64);
-          tma_load_2d(sdO + a * ATOM128 + r * ATOM64, &tm_do, bar_q, h * DH + a * 64, tok0 + q0 + r * 64);
-        }
       load_kv(0, 0);
       load_kv(1, 1);  // njb >= 2 always
       if (njb > 2) load_kv(2, 2);
@@ -715,21 +746,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
     }
   } else if (warp == 16) {
-    // =============================== MMA issuer ===============================
-    {  // the whole warp runs this loop; only `leader` issues
-      const bool leader = lane == 0;
+    // =============================== MMA issuer (convergent warp) ===============================
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, DQ_BKV, false, false);  // S, dP
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, DH, false, true);      // dQ
-      constexpr uint32_t BUF16 = (2 * ATOM64) >> 4, A128 = ATOM128 >> 4, A64 = ATOM64 >> 4;
-      const uint32_t q_lo = desc_lo_k(smem_u32(sQ)), do_lo = desc_lo_k(smem_u32(sdO));
+      constexpr uint32_t BUF16 = (2 * ATOM64) >> 4, A64 = ATOM64 >> 4;
       const uint32_t k_lo = desc_lo_k(smem_u32(sK)), v_lo = desc_lo_k(smem_u32(sV));
-      const uint32_t k_mn = desc_lo_mn(smem_u32(sK)), ds_lo = desc_lo_k(smem_u32(sdS));
+      const uint32_t k_mn = desc_lo_mn(smem_u32(sK));
       auto issue_scores = [&](uint32_t tb, uint32_t kb) {  // S = Q K^T, dP = dO V^T -> TMEM bufs tb
-        mma_kmajor_dh(leader, tmem_base + tb * 64, q_lo, A128, k_lo + kb * BUF16, A64, idesc_s);
-        mma_kmajor_dh(leader, tmem_base + 128 + tb * 64, do_lo, A128, v_lo + kb * BUF16, A64, idesc_s);
-        commit_if(leader, &bar_s[tb]);
+        mma_ts_kmajor_dh(tmem_base + tb * 64, tmem_Q, k_lo + kb * BUF16, A64, idesc_s);
+        mma_ts_kmajor_dh(tmem_base + 128 + tb * 64, tmem_dO, v_lo + kb * BUF16, A64, idesc_s);
+        commit_if(true, &bar_s[tb]);
       };
-      mbar_wait(bar_q, 0);
+      mbar_wait(bar_qready, 0);
       mbar_wait(&bar_kv[0], 0);
       tc_fence_after();
       issue_scores(0, 0);
@@ -737,26 +766,44 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       for (int j = 0; j < njb; ++j) {
         uint32_t nkb = kb + 1, npar = kpar;
         if (nkb == 3) { nkb = 0; npar ^= 1; }
-        if (j + 1 < njb) {
+        if (j + 1 < njb) {  // TMEM buffers (j+1)&1 hold dS(j-1): its dQ MMA was issued last iteration
           mbar_wait(&bar_kv[nkb], npar);
           tc_fence_after();
           issue_scores((j + 1) & 1, nkb);
         }
         mbar_wait(bar_p, j & 1);
         tc_fence_after();
-        // dQ += dS K : A K-major [128 q x 64 kv], B = K as MN-major (N = dh, K = kv rows)
-        mma_a64_bmn(leader, tmem_dQ, ds_lo + (j & 1) * A128, k_mn + kb * BUF16, idesc_dq, j != 0);
-        commit_if(leader, &bar_dq[j & 1]);
-        commit_if(leader, &bar_kvfree[kb]);
+        // dQ += dS K : A = dS (bf16 in TMEM, over dP buffer j&1), B = K as MN-major (N = dh, K = kv rows)
+        mma_ts_a64_bmn(tmem_dQ, tmem_base + 128 + (j & 1) * 64, k_mn + kb * BUF16, idesc_dq, j != 0);
+        if (j + 1 == njb) commit_if(true, bar_dq);
+        commit_if(true, &bar_kvfree[kb]);
         kb = nkb;
         kpar = npar;
       }
     }
   } else {
+    // =============================== compute (16 warps: 4 threads per query row) =================
     const int q = warp & 3, hc = warp >> 2;
     const int row_local = q * 32 + lane;
     const int row_seq = q0 + row_local;
     const uint32_t lane_base = (q * 32u) << 16;
+    // this thread's 32 of the 128 dh elements of its Q and dO rows -> TMEM (16 packed columns each)
+    {
+      const uint4* qsrc = reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(tok0 + row_seq) * ld_qkv + h * DH + hc * 32);
+      const uint4* dsrc = reinterpret_cast<const uint4*>(dout + static_cast<size_t>(tok0 + row_seq) * ld_out + h * DH + hc * 32);
+      uint32_t rq[16], rd[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 a = qsrc[i], d4 = dsrc[i];
+        rq[i * 4 + 0] = a.x; rq[i * 4 + 1] = a.y; rq[i * 4 + 2] = a.z; rq[i * 4 + 3] = a.w;
+        rd[i * 4 + 0] = d4.x; rd[i * 4 + 1] = d4.y; rd[i * 4 + 2] = d4.z; rd[i * 4 + 3] = d4.w;
+      }
+      tmem_st16(tmem_Q + lane_base + hc * 16, rq);
+      tmem_st16(tmem_dO + lane_base + hc * 16, rd);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_qready);
+    }
     const size_t stat_idx = static_cast<size_t>(h) * (static_cast<size_t>(B) * S) + tok0 + row_seq;
     const float my_lse = lse2[stat_idx];
     const float my_dl = delta[stat_idx] * scale;
@@ -770,9 +817,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tmem_ld16(tmem_base + tb * 64 + lane_base + hc * 16, s_r);
       tmem_ld16(tmem_base + 128 + tb * 64 + lane_base + hc * 16, dp_r);
       tmem_ld_wait();
-      if (j >= 2) mbar_wait(&bar_dq[tb], ((j >> 1) - 1) & 1);  // dS buffer tb: read by dQ MMA (j-2)
       const int col0 = j * DQ_BKV + hc * 16;
       const bool diag = (j * DQ_BKV + DQ_BKV - 1) > q0;
+      uint32_t dsp[8];
 #pragma unroll
       for (int c8 = 0; c8 < 2; ++c8) {
         float p[8], ds[8];
@@ -785,14 +832,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) ds[e] = p[e] * fmaf(__uint_as_float(dp_r[c8 * 8 + e]), scale, -my_dl);
-        *reinterpret_cast<uint4*>(sdS + tb * ATOM128 + sw128_offset(row_local, hc * 2 + c8)) = pack8(ds);
+        const uint4 u = pack8(ds);
+        dsp[c8 * 4 + 0] = u.x; dsp[c8 * 4 + 1] = u.y; dsp[c8 * 4 + 2] = u.z; dsp[c8 * 4 + 3] = u.w;
       }
-      fence_proxy_async_smem();
+      // dS overwrites columns of the dP buffer that the other three threads of this row read:
+      // wait until the whole lane quarter has its dP values in registers
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+      tmem_st8(tmem_base + 128 + tb * 64 + lane_base + hc * 8, dsp);
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_p);
     }
 
-    mbar_wait(&bar_dq[(njb - 1) & 1], ((njb - 1) >> 1) & 1);  // commits are cumulative
+    mbar_wait(bar_dq, 0);
     __syncwarp();
     tc_fence_after();
     bf16* dqrow = dqkv + static_cast<size_t>(tok0 + row_seq) * ld_qkv + h * DH + hc * 32;
@@ -854,8 +906,8 @@ void attention_bwd(const void* qkv, int ld_qkv, int k_off, int v_off, const void
       scale_log2);
   B200W_CUDA(cudaGetLastError());
   attn_bwd_dq_kernel<<<(S / DQ_BQ) * B * H, BWD_NTHREADS, DQ_SMEM, s>>>(
-      tm_qkv, tm_do, lse2, delta, static_cast<bf16*>(dqkv), ld_qkv, k_off, v_off, B, S, H, Hkv, scale,
-      scale_log2);
+      tm_qkv, static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout), ld_out, lse2, delta,
+      static_cast<bf16*>(dqkv), ld_qkv, k_off, v_off, B, S, H, Hkv, scale, scale_log2);
   B200W_CUDA(cudaGetLastError());
 }
 

@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from runbooks_b200.engine import Engine  # noqa: E402
 from util import call  # noqa: E402
+from bench import ClockSampler  # noqa: E402  (numbers from different boxes are only comparable with clocks)
 
 
 def timeit(fn, iters=10, warm=3, e=None):
@@ -35,8 +36,15 @@ ENGINE = None
 
 def main():
     global ENGINE
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", choices=("all", "gemm", "attn"), default="all")
+    ap.add_argument("--out", default="gpurun_out/perf_probe.json")
+    args = ap.parse_args()
     e = ENGINE = Engine(0)
     out = {}
+    clocks = ClockSampler(0)
+    clocks.start()
     T, d, f, V = 4096, 4096, 11008, 32000
     shapes = {
         "fwd_qkv": (T, 3 * d, d, 0, 0), "fwd_gateup": (T, 2 * f, d, 0, 0), "fwd_down": (T, d, f, 0, 0),
@@ -45,6 +53,8 @@ def main():
         "wgrad_down_acc": (d, f, T, 1, 1), "wgrad_lmhead_acc": (V, d, T, 1, 1), "dgrad_qkv": (T, d, 3 * d, 0, 1),
         "square_8k": (8192, 8192, 8192, 0, 0),
     }
+    if args.only == "attn":
+        shapes = {}
     for name, (M, N, K, a_mn, b_mn) in shapes.items():
         A = torch.randn((K, M) if a_mn else (M, K), device="cuda").bfloat16()
         B = torch.randn((K, N) if b_mn else (N, K), device="cuda").bfloat16()
@@ -58,6 +68,8 @@ def main():
             out[f"gemm_{name}_bn{bn}"] = dict(ms=t * 1e3, tflops=tf)
             print(f"gemm {name:14s} bn{bn} M{M} N{N} K{K}: {t * 1e3:8.3f} ms  {tf:7.1f} TF/s", flush=True)
         del A, B, D
+    if args.only == "gemm":
+        return finish(out, clocks, args.out)
     # attention, one 4096-token sequence, 32 heads
     B_, S, H = 1, 4096, 32
     qkv = torch.randn(B_ * S, 3 * H * 128, device="cuda").bfloat16()
@@ -75,8 +87,14 @@ def main():
                             H * 128, lse, delta, dqkv, B_, S, H, H, 128 ** -0.5))
     out["attn_bwd"] = dict(ms=t * 1e3, tflops=2.5 * fl / t / 1e12)
     print(f"attention bwd S{S} H{H}: {t * 1e3:.3f} ms  {2.5 * fl / t / 1e12:.1f} TF/s (causal flops)", flush=True)
-    os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/perf_probe.json", "w"), indent=1)
+    finish(out, clocks, args.out)
+
+
+def finish(out, clocks, path):
+    out["clocks"] = clocks.stop()
+    print("clocks", out["clocks"], flush=True)
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    json.dump(out, open(path, "w"), indent=1)
 
 
 if __name__ == "__main__":

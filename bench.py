@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -183,7 +184,7 @@ def run_reference(args):
                                   sample=sample),
                 e2e=dict(value=round(value, 3), unit="tokens/s", h2d_bytes_per_step=0,
                          d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 PER_DEVICE_BATCH = 8
@@ -244,6 +245,13 @@ def run_ours(args):
     n_valid = nseq * (S - 1)                  # labels = ids, packed: S-1 targets per sequence
     tokens_per_step = nseq * S
 
+    def require_finite(where, loss_v, gn_v):
+        # NaN operands toggle no tensor-core inputs: the chip leaves its power cap and the step
+        # "speeds up". Such a run is not a measurement; fail loudly instead of printing a number.
+        # (loss / grad-norm are global values, identical on every rank, so all ranks stop together)
+        if not (math.isfinite(loss_v) and math.isfinite(gn_v)):
+            raise SystemExit(f"bench.py: {where}: loss={loss_v} grad_norm={gn_v} not finite; no result printed")
+
     def barrier():
         e.sync()
         torch.cuda.synchronize()
@@ -254,6 +262,7 @@ def run_ours(args):
     for i in range(args.warmup):
         ids = host_ids[i].numpy()
         loss, gn = e.train_step(ids, ids, lr=5e-5)
+    require_finite("warm-up", loss, gn)
     barrier()
 
     # ---- timed region 1: inputs resident in HBM ----
@@ -274,6 +283,7 @@ def run_ours(args):
     e.profile_gemm(False)
     launches = e.launch_count() - launches0
     loss_res, gn_res = e.read_scalars()
+    require_finite("resident timed region", loss_res, gn_res)
 
     # ---- timed region 2: end to end through the host-buffer API ----
     barrier()
@@ -284,6 +294,7 @@ def run_ours(args):
         loss, gn = e.train_step(ids, ids, lr=5e-5)   # H2D of ids+labels, D2H of loss/grad-norm inside
     ms_e2e = e.timer_stop()
     wall_e2e = (time.perf_counter() - t_wall) * 1e3
+    require_finite("e2e timed region", loss, gn)
     barrier()
     ms_e2e = max(ms_e2e, wall_e2e)  # host-side work (pinned staging, sync) counts end to end
 
@@ -326,12 +337,33 @@ def run_ours(args):
     )
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line), flush=True)
+    emit(line)
     e.close()
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version
+    banner with printf), so fd 1 is pointed at stderr for the whole run and the JSON line goes to
+    the saved original."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
     global MICRO_BATCH
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)

@@ -107,15 +107,21 @@ B200W_API int b200w_comm_init(b200w_ctx* ctx, int rank, int nranks, const void* 
 /* ids/labels: HOST int32 [n_seqs, max_seq_len]; n_seqs must be a multiple of micro_batch (the
  * step runs n_seqs / micro_batch accumulation micro-steps, which equals one HF batch of n_seqs
  * sequences: loss = sum(nll) / num_valid_tokens, HF loss_utils.py:28-42). labels follow the HF
- * convention (unshifted; -100 ignored). With a communicator, gradients are averaged over ranks
- * (DDP semantics) by a bucketed all-reduce overlapped with the last micro-step's backward.
- * Order inside: fwd, loss, bwd, [all-reduce], global-norm clip, AdamW. loss_out / gnorm_out:
- * HOST floats (this rank's mean loss; global pre-clip gradient norm). */
+ * convention (unshifted; -100 ignored). With a communicator the step is HF Trainer's DDP step
+ * with TrainingArguments' default average_tokens_across_devices=True (transformers 5.5
+ * trainer.py:2013-2018, 2140-2143): the target count is summed over the ranks first (one 8-byte
+ * all-reduce and a host sync per step), every rank back-propagates sum(nll_rank) / n_global, and
+ * the per-layer gradient all-reduce (sum), overlapped with the last micro-step's backward, yields
+ * the gradient of the GLOBAL batch's token mean -- what one process computes on all the sequences.
+ * Every rank must therefore call with the same n_seqs. Order inside: [count all-reduce], fwd,
+ * loss, bwd, [gradient + loss all-reduce], global-norm clip, AdamW. loss_out / gnorm_out: HOST
+ * floats (global token-mean loss; global pre-clip gradient norm), identical on every rank. */
 B200W_API int b200w_train_step(b200w_ctx* ctx, const int32_t* ids, const int32_t* labels, int n_seqs, float lr,
                      float* loss_out, float* gnorm_out);
 /* The same step with the batch already resident in HBM (DEVICE int32 pointers) and no host
- * synchronisation: nothing crosses PCIe. n_valid = number of non-ignored shifted labels (what
- * b200w_train_step counts on the host). Read loss / grad-norm later with b200w_read_scalars. */
+ * synchronisation on one GPU: nothing crosses PCIe. n_valid = THIS rank's number of non-ignored
+ * shifted labels (what b200w_train_step counts on the host); with a communicator it is summed
+ * over the ranks as above. Read loss / grad-norm later with b200w_read_scalars. */
 B200W_API int b200w_train_step_resident(b200w_ctx* ctx, const int32_t* ids_dev, const int32_t* labels_dev,
                               int n_seqs, int64_t n_valid, float lr);
 B200W_API int b200w_read_scalars(b200w_ctx* ctx, float* loss_out, float* gnorm_out);
@@ -126,7 +132,8 @@ B200W_API int b200w_timer_stop(b200w_ctx* ctx, float* ms_out);
  * (2*M*N*K per launch) and launch count since profiling was enabled. */
 B200W_API int b200w_profile_gemm(b200w_ctx* ctx, int enable);
 B200W_API int b200w_profile_read(b200w_ctx* ctx, double* ms_out, double* flops_out, int64_t* launches_out);
-/* Forward + loss + backward only (no optimiser step): fills gradients for inspection. */
+/* Forward + loss + backward only (no optimiser step): fills gradients for inspection (with a
+ * communicator: the all-reduced global-batch gradients, one all-reduce after the backward). */
 B200W_API int b200w_forward_backward(b200w_ctx* ctx, const int32_t* ids, const int32_t* labels, int n_seqs,
                            float* loss_out);
 /* Forward only; logits_out: HOST float [n_seqs * max_seq_len, vocab] or NULL; per-token nll
@@ -209,6 +216,11 @@ B200W_API int b200w_op_adamw(b200w_ctx* ctx, float* master, float* m, float* v, 
                    float gscale);
 /* returns sqrt(sum g^2) in *norm_out (HOST) */
 B200W_API int b200w_op_grad_norm(b200w_ctx* ctx, const float* g, int64_t n, float* norm_out);
+/* Robustness hook: overwrites ALL shared memory (227 KB) and all 512 TMEM columns of every SM with
+ * `pattern` (e.g. 0x7FC07FC0: NaN as bf16 pairs and as fp32). A kernel may never depend on on-chip
+ * state left by whatever ran before it (another library's kernel, e.g. NCCL's, leaves arbitrary
+ * bits there): tests poison, run an op, and require results bit-identical to the clean run. */
+B200W_API int b200w_op_poison_onchip(b200w_ctx* ctx, uint32_t pattern);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,7 @@ PROTOTYPES = {
     "b200w_op_adamw": (C.c_int, [c_ctx, vp, vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float,
                                  C.c_float, C.c_float, C.c_float, C.c_int, C.c_float]),
     "b200w_op_grad_norm": (C.c_int, [c_ctx, vp, C.c_int64, f32p]),
+    "b200w_op_poison_onchip": (C.c_int, [c_ctx, C.c_uint32]),
 }
 
 _lib: Optional[C.CDLL] = None

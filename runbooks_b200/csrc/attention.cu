@@ -117,9 +117,11 @@ __device__ __forceinline__ void mma_raw_dyn(bool, uint32_t tmem_d, uint32_t a_lo
       : "memory");
 }
 // A operand from TMEM (bf16 pairs, 8 columns per K = 16 step; lane = row), B from smem.
-// Operands that are constant for a CTA (Q, dO) or produced by the compute warps (P, dS) live in
-// TMEM so that they cost no shared-memory bandwidth: at 128 B/clk that, not the tensor pipe,
-// was what bounded these kernels.
+// Used by the dQ kernel for Q, dO (constant per CTA) and dS (written by the compute warps with
+// tcgen05.st over the dP columns they just consumed). Measured effect (same-box ncu A/B,
+// profiles/r01_attn_ab_v9.txt): kernel 234 -> 212 us with the tensor-core smem pipe at 25 % busy,
+// i.e. smem bandwidth was NOT the binding limit; the per-block softmax/dS phase of the compute
+// warps is.
 template <bool ACC>
 __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc) {
   asm volatile(

@@ -7,6 +7,7 @@
 // step in oracle/ (SURVEY.md §8c): loss.backward(); clip_grad_norm_(1.0); AdamW.step().
 #include <dlfcn.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <memory>
@@ -36,7 +37,7 @@ struct NcclApi {
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
-constexpr int kNcclFloat32 = 7, kNcclSum = 0;
+constexpr int kNcclInt64 = 4, kNcclFloat32 = 7, kNcclSum = 0;
 
 NcclApi& nccl() {
   static NcclApi api;
@@ -91,6 +92,33 @@ __global__ void init_normal_kernel(float* master, bf16* w, size_t n, uint64_t se
     w[i] = __float2bfloat16_rn(r);
   }
 }
+// Fills this SM's shared memory and all 512 TMEM columns with `pattern` (b200w_op_poison_onchip).
+constexpr int POISON_SMEM = 227 * 1024 - 64;
+__global__ void __launch_bounds__(128, 1) poison_onchip_kernel(uint32_t pattern) {
+  extern __shared__ __align__(16) uint32_t poison_sm[];
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < POISON_SMEM / 4; i += blockDim.x) poison_sm[i] = pattern;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(&slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = slot + ((warp * 32u) << 16);
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = pattern;
+  for (int col = 0; col < 512; col += 32) tmem_st32(base + col, r);
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(slot, 512);
+  }
+  // keep the smem stores alive
+  if (poison_sm[(threadIdx.x * 977) % (POISON_SMEM / 4)] != pattern) __trap();
+}
+
 __global__ void fill_kernel(float* master, bf16* w, size_t n, float val) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -142,6 +170,7 @@ struct b200w_ctx {
        *dattn = nullptr, *dqkv = nullptr;
   float *delta = nullptr, *dw_partial = nullptr;
   float* scal = nullptr;    // [0] loss, [1] gscale, [2] gnorm
+  long long* cnt_dev = nullptr;  // valid-target count, summed over the ranks (HF num_items_in_batch)
   double* sumsq = nullptr;
   float* host_scal = nullptr;  // pinned [4]
   float* hook_scal = nullptr;
@@ -290,6 +319,7 @@ void alloc_activations(b200w_ctx* c) {
   c->nll = c->alloc<float>(T);
   c->targets = c->alloc<int32_t>(T);
   c->scal = c->alloc<float>(8);
+  c->cnt_dev = c->alloc<long long>(1);
   c->sumsq = c->alloc<double>(1);
   if (c->training) {
     c->dh_a = c->alloc<bf16>(T * d);
@@ -376,12 +406,33 @@ void loss_micro(b200w_ctx* c, const int32_t* labels, int nseq, float inv_n) {
   reduce_sum_f32(c->nll, c->scal + 0, T, inv_n, s); ++c->launches;
 }
 
+// B200W_AR_MODE (debugging aid, same arithmetic in every mode):
+//   overlap (default)  per-layer all-reduce on comm_stream, concurrent with the rest of the backward
+//   sync               as overlap, but the host drains c->stream before enqueuing each all-reduce
+//   serial             per-layer, but c->stream waits for each all-reduce: never concurrent with compute
+//   end                one all-reduce of the whole gradient after the backward
+enum class ArMode { Overlap, Sync, Serial, End };
+ArMode ar_mode() {
+  const char* m = getenv("B200W_AR_MODE");
+  const std::string v = m ? m : "";
+  if (v == "end") return ArMode::End;
+  if (v == "sync") return ArMode::Sync;
+  if (v == "serial") return ArMode::Serial;
+  return ArMode::Overlap;
+}
+
 void allreduce_range(b200w_ctx* c, size_t off, size_t count) {
+  const ArMode mode = ar_mode();
+  if (mode == ArMode::Sync) B200W_CUDA(cudaStreamSynchronize(c->stream));
   B200W_CUDA(cudaEventRecord(c->ev_grad, c->stream));
   B200W_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_grad, 0));
   B200W_NCCL(nccl().AllReduce(c->g + off, c->g + off, count, kNcclFloat32, kNcclSum, c->comm,
                               c->comm_stream));
   ++c->launches;
+  if (mode == ArMode::Serial) {
+    B200W_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
+    B200W_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+  }
 }
 
 // backward of one micro-batch. first: overwrite gradients instead of accumulating.
@@ -477,14 +528,42 @@ void upload_batch(b200w_ctx* c, const int32_t* ids, const int32_t* labels, size_
                              cudaMemcpyHostToDevice, c->stream));
 }
 
-// forward + loss + backward over a batch that is already on the device
+// HF Trainer under DDP (transformers 5.5 trainer.py:2140-2143, average_tokens_across_devices = True,
+// the TrainingArguments default): num_items_in_batch is gathered and SUMMED over the ranks, each
+// rank's loss is sum(nll_r) / n_global * world (trainer.py:2013-2018) and DDP's mean removes the
+// factor again, so the gradient is that of sum(nll over all ranks) / n_global -- the same number a
+// single process computes on the global batch. Per-rank normalisation would differ whenever the
+// ranks hold different numbers of target tokens (prompt-masked rows).
+long global_valid(b200w_ctx* c, long nvalid_local) {
+  if (!c->comm) return nvalid_local;
+  long long* host = reinterpret_cast<long long*>(c->host_scal + 4);
+  *host = nvalid_local;
+  // every NCCL call of this context goes to comm_stream (one stream per communicator); the count
+  // comes from the host, so nothing on c->stream has to be waited for
+  cudaStream_t cs = c->comm_stream;
+  B200W_CUDA(cudaMemcpyAsync(c->cnt_dev, host, sizeof(long long), cudaMemcpyHostToDevice, cs));
+  B200W_NCCL(nccl().AllReduce(c->cnt_dev, c->cnt_dev, 1, kNcclInt64, kNcclSum, c->comm, cs));
+  B200W_CUDA(cudaMemcpyAsync(host, c->cnt_dev, sizeof(long long), cudaMemcpyDeviceToHost, cs));
+  B200W_CUDA(cudaStreamSynchronize(cs));
+  ++c->launches;
+  return static_cast<long>(*host);
+}
+
+bool ar_overlap_enabled() { return ar_mode() != ArMode::End; }
+
+// forward + loss + backward over a batch that is already on the device. nvalid = this rank's count
+// of target tokens; with a communicator the gradients returned are those of the GLOBAL batch
+// (sum over ranks of sum(nll) / n_global), all-reduced, and scal[0] is the global loss.
 void fwd_bwd_device(b200w_ctx* c, const int32_t* ids_dev, const int32_t* labels_dev, int n_seqs,
                     long nvalid, bool allow_overlap) {
   const int S = c->arch.max_seq_len, mb = c->micro_batch;
   B200W_CHECK(c->has_model && c->training, "model not initialised for training");
   B200W_CHECK(n_seqs > 0 && n_seqs % mb == 0, "n_seqs must be a positive multiple of micro_batch");
-  B200W_CHECK(nvalid > 0, "batch has no valid target token");
-  const float inv_n = 1.f / static_cast<float>(nvalid);
+  B200W_CHECK(nvalid >= 0, "negative target count");
+  const long n_global = global_valid(c, nvalid);
+  B200W_CHECK(n_global > 0, "batch has no valid target token");
+  const float inv_n = 1.f / static_cast<float>(n_global);
+  allow_overlap = allow_overlap && ar_overlap_enabled();
   B200W_CUDA(cudaMemsetAsync(c->scal, 0, 8 * sizeof(float), c->stream));
   B200W_CUDA(cudaMemsetAsync(c->g, 0, c->n_zero_prefix * sizeof(float), c->stream));
   const int n_micro = n_seqs / mb;
@@ -496,7 +575,12 @@ void fwd_bwd_device(b200w_ctx* c, const int32_t* ids_dev, const int32_t* labels_
     const bool ar = allow_overlap && c->comm && mi == n_micro - 1;
     backward_micro(c, mids, mb, mi == 0, ar);
   }
-  if (allow_overlap && c->comm) {
+  if (c->comm) {
+    if (!allow_overlap) allreduce_range(c, 0, c->n_elems);
+    // the logged loss is the global token mean: sum the per-rank partials sum(nll_r) / n_global.
+    // (comm_stream already waits for the end of the backward: the last allreduce_range did that)
+    B200W_NCCL(nccl().AllReduce(c->scal, c->scal, 1, kNcclFloat32, kNcclSum, c->comm, c->comm_stream));
+    ++c->launches;
     B200W_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
     B200W_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
   }
@@ -517,9 +601,9 @@ void optimizer_step(b200w_ctx* c, float lr) {
   cudaStream_t s = c->stream;
   B200W_CUDA(cudaMemsetAsync(c->sumsq, 0, sizeof(double), s));
   grad_sumsq(c->g, c->n_elems, c->sumsq, s); ++c->launches;
-  // the all-reduce summed the ranks: DDP averages, so fold 1/nranks into the gradient scale
-  clip_coef(c->sumsq, c->hp.max_grad_norm, 1.f / static_cast<float>(c->nranks), c->scal + 1,
-            c->scal + 2, s); ++c->launches;
+  // the all-reduce summed per-rank partials that were already divided by the GLOBAL target count
+  // (fwd_bwd_device), which is HF's DDP result: no 1/nranks here
+  clip_coef(c->sumsq, c->hp.max_grad_norm, 1.f, c->scal + 1, c->scal + 2, s); ++c->launches;
   c->step += 1;
   adamw_step(c->master, c->m, c->v, c->g, c->w, c->n_elems, lr, c->hp.beta1, c->hp.beta2, c->hp.eps,
              c->hp.weight_decay, c->step, c->scal + 1, s);
@@ -1030,6 +1114,20 @@ int b200w_op_adamw(b200w_ctx* ctx, float* master, float* m, float* v, const floa
     B200W_CUDA(cudaStreamSynchronize(ctx->stream));
   });
 }
+int b200w_op_poison_onchip(b200w_ctx* ctx, uint32_t pattern) {
+  return guarded(ctx, [&] {
+    static bool attr = false;
+    if (!attr) {
+      B200W_CUDA(cudaFuncSetAttribute(poison_onchip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POISON_SMEM));
+      attr = true;
+    }
+    // one CTA per SM at a time (smem-limited); several waves so that every SM is visited
+    poison_onchip_kernel<<<sm_count() * 4, 128, POISON_SMEM, ctx->stream>>>(pattern);
+    B200W_CUDA(cudaGetLastError());
+    B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
 int b200w_op_grad_norm(b200w_ctx* ctx, const float* g, int64_t n, float* norm_out) {
   return guarded(ctx, [&] {
     double* ss = nullptr;

@@ -64,6 +64,9 @@ if __name__ == "__main__":
         b = torch.from_numpy(wn[k].astype(np.int32)).to(torch.int16).view(torch.bfloat16).float()
         worst = max(worst, float((a - b).norm() / a.norm()))
     print(f"worst relative weight difference 1 vs {n} GPUs: {worst:.3e}")
-    # rank 0's logged loss is its own shard's mean, so only the weights are comparable
+    # the logged loss is the global token mean on every rank count (HF average_tokens_across_devices)
+    worst_loss = max(abs(a - b) for a, b in zip(l1, ln))
+    print(f"worst |loss difference|: {worst_loss:.3e}")
+    assert len(l1) == len(ln) and worst_loss < 2e-3, (l1, ln)
     assert worst < 2e-3, worst
     print("OK")

@@ -689,8 +689,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __res
   uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sV + 3 * 2 * ATOM64);  // [3]
   uint64_t* bar_s = bar_kv + 3;       // [2] S, dP (j) in TMEM
   uint64_t* bar_dq = bar_s + 2;       //     dQ MMAs of the last block retired
-  uint64_t* bar_p = bar_dq + 1;       //     dS (j) in TMEM (512 arrivals)
-  uint64_t* bar_kvfree = bar_p + 1;   // [3] MMAs that read K/V buffer b retired (for the TMA warp)
+  // [2], one per TMEM stage: dS (j) in TMEM and S/dP (j) drained (512 arrivals). It MUST be per
+  // stage: the lane quarters are coupled only through this barrier, a quarter may run one block
+  // ahead (S/dP (j+1) are issued early), and with a single barrier its arrival for j+1 would
+  // complete phase j before a slower quarter has written dS (j) -- the dQ MMA then reads that
+  // quarter's stale dP bits (found by tools/stress_attn.py: 1.2 % of launches, one quarter of one
+  // CTA wrong, NaN or not). With a barrier per stage a thread reaches the same stage again only
+  // after bar_s (j+2), which the MMA warp commits after it has passed this barrier for j.
+  uint64_t* bar_p = bar_dq + 1;
+  uint64_t* bar_kvfree = bar_p + 2;   // [3] MMAs that read K/V buffer b retired (for the TMA warp)
   uint64_t* bar_qready = bar_kvfree + 3;  // Q, dO rows are in TMEM (512 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qready + 1);
 
@@ -712,7 +719,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __res
     }
     for (int i = 0; i < 2; ++i) mbar_init(&bar_s[i], 1);
     mbar_init(bar_dq, 1);
-    mbar_init(bar_p, BWD_NCOMPUTE);
+    for (int i = 0; i < 2; ++i) mbar_init(&bar_p[i], BWD_NCOMPUTE);
     mbar_init(bar_qready, BWD_NCOMPUTE);
     fence_barrier_init();
   }
@@ -773,7 +780,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __res
           tc_fence_after();
           issue_scores((j + 1) & 1, nkb);
         }
-        mbar_wait(bar_p, j & 1);
+        mbar_wait(&bar_p[j & 1], (j >> 1) & 1);
         tc_fence_after();
         // dQ += dS K : A = dS (bf16 in TMEM, over dP buffer j&1), B = K as MN-major (N = dh, K = kv rows)
         mma_ts_a64_bmn(tmem_dQ, tmem_base + 128 + (j & 1) * 64, k_mn + kb * BUF16, idesc_dq, j != 0);
@@ -843,7 +850,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __res
       tmem_st8(tmem_base + 128 + tb * 64 + lane_base + hc * 8, dsp);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      mbar_arrive(&bar_p[tb]);
     }
 
     mbar_wait(bar_dq, 0);

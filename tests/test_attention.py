@@ -102,3 +102,43 @@ def test_attention_long_sequence_properties(engine):
     qkv3[-1, H * dh:] = 3.0                         # last key and value
     call(engine, "b200w_op_attention_fwd", dev(qkv3), *args)
     assert torch.equal(out.cpu()[:-1], o1[:-1])
+
+
+@pytest.mark.parametrize("B,S,H,Hkv,iters", [(1, 4096, 32, 32, 500), (2, 2048, 8, 2, 300)])
+def test_attention_is_race_free(engine, B, S, H, Hkv, iters):
+    """The kernels have no atomics, so repeated launches on fixed inputs must be BIT-identical.
+    Single-shot parity cannot see an intermittent race: a dQ build whose lane quarters were coupled
+    through one mbarrier shared by two TMEM stages passed every parity test and was wrong (one
+    quarter of one CTA, sometimes NaN) in 1.2 % of launches at this size -- which surfaced only as
+    NaN gradients in a 2-GPU run. 500 launches catch a 1 % race with probability 0.993."""
+    dh = 128
+    g = torch.Generator().manual_seed(11)
+    T, ld = B * S, (H + 2 * Hkv) * dh
+    qkv = dev(torch.randn(T, ld, generator=g).bfloat16())
+    dout = dev(torch.randn(T, H * dh, generator=g).bfloat16())
+    k_off, v_off, scale = H * dh, (H + Hkv) * dh, dh ** -0.5
+    out = torch.empty(T, H * dh, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(H, T, device="cuda", dtype=torch.float32)
+    delta = torch.empty(H, T, device="cuda", dtype=torch.float32)
+    dqkv = torch.zeros(T, ld, device="cuda", dtype=torch.bfloat16)
+
+    def step():
+        out.zero_()
+        dqkv.zero_()
+        call(engine, "b200w_op_attention_fwd", qkv, ld, k_off, v_off, out, H * dh, lse, B, S, H, Hkv, scale)
+        call(engine, "b200w_op_attention_bwd", qkv, ld, k_off, v_off, out, dout, H * dh, lse, delta, dqkv,
+             B, S, H, Hkv, scale)
+
+    step()
+    ref = (out.clone(), lse.clone(), dqkv.clone())
+    assert torch.isfinite(ref[2].float()).all()
+    bad = {"out": 0, "lse": 0, "dq": 0, "dk": 0, "dv": 0}
+    for _ in range(iters):
+        step()
+        bad["out"] += not torch.equal(out, ref[0])
+        bad["lse"] += not torch.equal(lse, ref[1])
+        bad["dq"] += not torch.equal(dqkv[:, :k_off], ref[2][:, :k_off])
+        bad["dk"] += not torch.equal(dqkv[:, k_off:v_off], ref[2][:, k_off:v_off])
+        bad["dv"] += not torch.equal(dqkv[:, v_off:], ref[2][:, v_off:])
+    print(f"attention race check B{B} S{S} H{H} Hkv{Hkv}: {iters} launches, mismatching launches {bad}")
+    assert not any(bad.values()), bad

@@ -55,7 +55,9 @@ def test_gemm_ignores_leftover_state(engine, a_mn, b_mn, bn, f32, acc):
     g = torch.Generator().manual_seed(3)
     A = dev(torch.randn((K, M) if a_mn else (M, K), generator=g).bfloat16())
     B = dev(torch.randn((K, N) if b_mn else (N, K), generator=g).bfloat16())
-    C0 = dev(torch.randn(M, N, generator=g))
+    if bn < 128 and (a_mn or b_mn):
+        pytest.skip("narrow tiles take K-major operands only")
+    C0 = dev(torch.randn(M, N, generator=g), dtype=torch.float32)  # dev() defaults to bf16
     dt = torch.float32 if f32 else torch.bfloat16
 
     def run():
@@ -74,10 +76,11 @@ def test_gemm_llama_shapes_ignore_leftover_state(engine, M, N, K):
     g = torch.Generator().manual_seed(5)
     A = dev(torch.randn(K, M, generator=g).bfloat16())
     B = dev(torch.randn(K, N, generator=g).bfloat16())
-    C0 = dev(torch.randn(M, N, generator=g))
+    C0 = dev(torch.randn(M, N, generator=g), dtype=torch.float32)  # dev() defaults to bf16
 
     def run():
         D = C0.clone()
+        assert D.dtype == torch.float32
         call(engine, "b200w_op_gemm", A, 1, M, B, 1, N, D, D, 1, N, M, N, K, 512)
         torch.cuda.synchronize()
         return (D,)

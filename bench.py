@@ -377,10 +377,33 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     MICRO_BATCH = args.micro_batch
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # A rank that fails must EXIT, at once: its peers are inside a collective that can no longer
+    # complete, and the launcher only tears the job down when a worker process ends. Interpreter
+    # teardown (destructors -> NCCL / CUDA shutdown on a dead context) can block, so skip it.
+    # (profiles/r01_n8_failure.txt: one rank raised, did not exit, and 7 GPUs spun for 10 minutes.)
+    code = 0
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    except SystemExit as ex:
+        code = ex.code if isinstance(ex.code, int) else 1
+        if not isinstance(ex.code, int) and ex.code is not None:
+            sys.stderr.write(str(ex.code) + "\n")
+    except BaseException:  # noqa: BLE001
+        import traceback
+        traceback.print_exc()
+        code = 1
+    finally:
+        for f in (sys.stderr, _REAL_STDOUT, sys.stdout):
+            try:
+                if f:
+                    f.flush()
+            except Exception:  # noqa: BLE001
+                pass
+    if code:
+        os._exit(code)
 
 
 if __name__ == "__main__":

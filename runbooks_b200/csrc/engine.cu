@@ -35,6 +35,7 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Uid, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
+  int (*CommAbort)(void*) = nullptr;  // optional
   const char* (*GetErrorString)(int) = nullptr;
 };
 constexpr int kNcclInt64 = 4, kNcclFloat32 = 7, kNcclSum = 0;
@@ -57,6 +58,7 @@ NcclApi& nccl() {
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.CommAbort = reinterpret_cast<decltype(api.CommAbort)>(dlsym(api.lib, "ncclCommAbort"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
   }
   return api;
@@ -189,6 +191,7 @@ struct b200w_ctx {
   // ---- DP ----
   void* comm = nullptr;
   int rank = 0, nranks = 1;
+  bool poisoned = false;  // a CUDA / NCCL call failed: the context (and any collective) is dead
   cudaEvent_t ev_grad = nullptr, ev_comm = nullptr;
 
   template <typename T>
@@ -230,13 +233,16 @@ int guarded(b200w_ctx* ctx, F&& f) {
     return B200W_OK;
   } catch (const NcclError& e) {
     ctx->err = e.what();
+    ctx->poisoned = true;
     return B200W_ERR_NCCL;
   } catch (const std::bad_alloc&) {
     ctx->err = "device memory exhausted";
     return B200W_ERR_OOM;
   } catch (const Error& e) {
     ctx->err = e.what();
-    return ctx->err.rfind("check failed", 0) == 0 ? B200W_ERR_INVALID : B200W_ERR_CUDA;
+    if (ctx->err.rfind("check failed", 0) == 0) return B200W_ERR_INVALID;
+    ctx->poisoned = true;
+    return B200W_ERR_CUDA;
   } catch (const std::exception& e) {
     ctx->err = e.what();
     return B200W_ERR_INVALID;
@@ -411,18 +417,27 @@ void loss_micro(b200w_ctx* c, const int32_t* labels, int nseq, float inv_n) {
 //   sync               as overlap, but the host drains c->stream before enqueuing each all-reduce
 //   serial             per-layer, but c->stream waits for each all-reduce: never concurrent with compute
 //   end                one all-reduce of the whole gradient after the backward
+//
+// Default policy (round 1, PROVISIONAL): overlap for <= 2 ranks, where it is verified (10 steps
+// bit-identical across ranks, profiles/r01_bench_n2_v10.json); end for > 2 ranks. The only 8-rank
+// run so far died in its first steps with one rank's dK/dV kernel stalled > 2 s on an mbarrier
+// (profiles/r01_n8_failure.txt) and the cause is not established; what separates that run from the
+// passing ones is NCCL activity while the backward is in flight, which `end` removes entirely.
+// Expected cost at 8 ranks: the 27 GB fp32 all-reduce is exposed, ~7-9 % of a step. Not verified on
+// hardware at 4 or 8 ranks in either mode.
 enum class ArMode { Overlap, Sync, Serial, End };
-ArMode ar_mode() {
+ArMode ar_mode(int nranks) {
   const char* m = getenv("B200W_AR_MODE");
   const std::string v = m ? m : "";
   if (v == "end") return ArMode::End;
   if (v == "sync") return ArMode::Sync;
   if (v == "serial") return ArMode::Serial;
-  return ArMode::Overlap;
+  if (v == "overlap") return ArMode::Overlap;
+  return nranks > 2 ? ArMode::End : ArMode::Overlap;
 }
 
 void allreduce_range(b200w_ctx* c, size_t off, size_t count) {
-  const ArMode mode = ar_mode();
+  const ArMode mode = ar_mode(c->nranks);
   if (mode == ArMode::Sync) B200W_CUDA(cudaStreamSynchronize(c->stream));
   B200W_CUDA(cudaEventRecord(c->ev_grad, c->stream));
   B200W_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_grad, 0));
@@ -549,8 +564,6 @@ long global_valid(b200w_ctx* c, long nvalid_local) {
   return static_cast<long>(*host);
 }
 
-bool ar_overlap_enabled() { return ar_mode() != ArMode::End; }
-
 // forward + loss + backward over a batch that is already on the device. nvalid = this rank's count
 // of target tokens; with a communicator the gradients returned are those of the GLOBAL batch
 // (sum over ranks of sum(nll) / n_global), all-reduced, and scal[0] is the global loss.
@@ -563,7 +576,7 @@ void fwd_bwd_device(b200w_ctx* c, const int32_t* ids_dev, const int32_t* labels_
   const long n_global = global_valid(c, nvalid);
   B200W_CHECK(n_global > 0, "batch has no valid target token");
   const float inv_n = 1.f / static_cast<float>(n_global);
-  allow_overlap = allow_overlap && ar_overlap_enabled();
+  allow_overlap = allow_overlap && ar_mode(c->nranks) != ArMode::End;
   B200W_CUDA(cudaMemsetAsync(c->scal, 0, 8 * sizeof(float), c->stream));
   B200W_CUDA(cudaMemsetAsync(c->g, 0, c->n_zero_prefix * sizeof(float), c->stream));
   const int n_micro = n_seqs / mb;
@@ -675,8 +688,16 @@ int b200w_create(int device, b200w_ctx** out) {
 void b200w_destroy(b200w_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaDeviceSynchronize();
-  if (ctx->comm) nccl().CommDestroy(ctx->comm);
+  // After a device fault (e.g. the bounded mbarrier wait trapped) or an NCCL error, waiting for the
+  // device or for a clean communicator shutdown can block for ever: peers are still inside a
+  // collective that will never complete. Abort instead, so that this process can exit and the
+  // launcher can tear the job down (profiles/r01_n8_failure.txt: a rank that failed but did not
+  // exit kept 7 GPUs spinning for 10 minutes).
+  const bool dead = ctx->poisoned || cudaDeviceSynchronize() != cudaSuccess;
+  if (ctx->comm) {
+    if (!dead) nccl().CommDestroy(ctx->comm);
+    else if (nccl().CommAbort) nccl().CommAbort(ctx->comm);
+  }
   if (ctx->infer && ctx->infer_destroy) ctx->infer_destroy(ctx->infer);
   ctx->free_all();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -870,6 +891,28 @@ int b200w_comm_init(b200w_ctx* ctx, int rank, int nranks, const void* id128) {
     }
     ctx->rank = rank;
     ctx->nranks = nranks;
+    // NCCL connects its transports lazily, at the first collective of each kind (for 8 ranks:
+    // P2P rings plus NVLS multicast objects -- seconds of driver work). Do that now, with the
+    // message classes the step uses (large fp32 sum, one int64, one float) and nothing else on the
+    // GPU, instead of in the middle of the first backward. UNVERIFIED mitigation for
+    // profiles/r01_n8_failure.txt.
+    {
+      const size_t n_big = size_t(64) << 20;  // 256 MB: same protocol/algorithm class as a layer's gradients
+      float* scratch = nullptr;
+      B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&scratch), n_big * sizeof(float)));
+      cudaStream_t cs = ctx->comm_stream;
+      try {
+        B200W_CUDA(cudaMemsetAsync(scratch, 0, n_big * sizeof(float), cs));
+        B200W_NCCL(nccl().AllReduce(scratch, scratch, n_big, kNcclFloat32, kNcclSum, ctx->comm, cs));
+        B200W_NCCL(nccl().AllReduce(scratch, scratch, 1, kNcclFloat32, kNcclSum, ctx->comm, cs));
+        B200W_NCCL(nccl().AllReduce(scratch, scratch, 1, kNcclInt64, kNcclSum, ctx->comm, cs));
+        B200W_CUDA(cudaStreamSynchronize(cs));
+      } catch (...) {
+        cudaFree(scratch);
+        throw;
+      }
+      B200W_CUDA(cudaFree(scratch));
+    }
   });
 }
 

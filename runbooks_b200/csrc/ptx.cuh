@@ -24,7 +24,10 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
 // Bounded spin: a wrong descriptor / byte count must become an error, never a hung GPU box.
 #ifndef B200W_WAIT_LIMIT_CYCLES
-#define B200W_WAIT_LIMIT_CYCLES (4000000000ll)  // ~2 s at 1.9 GHz
+#define B200W_WAIT_LIMIT_CYCLES (40000000000ll)  // ~20 s at 1.9 GHz. Was ~2 s until an 8-rank run
+// trapped here (profiles/r01_n8_failure.txt) and it could not be told apart whether the kernel was
+// deadlocked or the GPU merely stalled for seconds under NCCL's transport setup; a real deadlock still
+// ends in a trap, 20 s later.
 #endif
 
 // ------------------------------------------------------------------------------------------

@@ -141,6 +141,11 @@ def _rank_main(rank, world, uid, content, q):
         q.put((rank, 0, ""))
     except BaseException:  # noqa: BLE001 — the exit code is the whole failure protocol
         q.put((rank, 1, traceback.format_exc()))
+        # deliver the report, then leave WITHOUT interpreter teardown: destructors would shut NCCL /
+        # CUDA down on a dead context and can block while the peers sit in a collective
+        q.close()
+        q.join_thread()
+        os._exit(1)
 
 
 def train(content: str) -> int:
@@ -162,18 +167,41 @@ def train(content: str) -> int:
     procs = [ctx.Process(target=_rank_main, args=(r, world, buf.raw, content, q)) for r in range(world)]
     for p in procs:
         p.start()
-    failed = 0
-    for _ in procs:
-        rank, code, tb = q.get()
-        if code:
-            failed += 1
-            sys.stderr.write(f"[rank {rank}] failed:\n{tb}\n")
-            for p in procs:            # one rank down => the collective can never complete
-                if p.is_alive():
-                    p.terminate()
-            break
+    return supervise(procs, q)
+
+
+def supervise(procs, q, poll: float = 0.25, grace: float = 10.0) -> int:
+    """Waits for every rank's (rank, code, traceback) report. One rank down means that the
+    collective can never complete, so the others are terminated at once -- also when a rank died
+    WITHOUT reporting (device fault in a C call, OOM kill): its exit code is the report. Ranks
+    that ignore SIGTERM (blocked in a driver call) are killed after `grace` seconds."""
+    import queue as queue_mod
+
+    reported, failed = set(), 0
+    while len(reported) < len(procs) and not failed:
+        try:
+            rank, code, tb = q.get(timeout=poll)
+            reported.add(rank)
+            if code:
+                failed += 1
+                sys.stderr.write(f"[rank {rank}] failed:\n{tb}\n")
+        except queue_mod.Empty:
+            for r, p in enumerate(procs):
+                if r not in reported and p.exitcode is not None:  # gone without a word
+                    reported.add(r)
+                    if p.exitcode != 0:
+                        failed += 1
+                        sys.stderr.write(f"[rank {r}] died with exit code {p.exitcode} and no report\n")
+    if failed:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+    deadline = time.time() + grace
     for p in procs:
-        p.join()
+        p.join(max(0.0, deadline - time.time()) if failed else None)
+        if p.is_alive():
+            p.kill()
+            p.join()
     return 1 if failed or any(p.exitcode for p in procs) else 0
 
 

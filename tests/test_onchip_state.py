@@ -6,7 +6,7 @@ it never wrote by zero then produces NaN x 0 = NaN, while after one of OUR kerne
 are finite and the bug hides. `b200w_op_poison_onchip` makes that deterministic on one GPU: it
 fills all 227 KB of shared memory and all 512 TMEM columns of every SM with a NaN pattern. Each op
 is run clean, then again after poisoning, and the results must be bit-identical (split-K decode
-GEMM: atomics reorder fp32 sums, so allclose)."""
+GEMM: atomics reorder fp32 sums, so finite + allclose)."""
 import pytest
 import torch
 
@@ -88,8 +88,14 @@ def test_gemm_llama_shapes_ignore_leftover_state(engine, M, N, K):
     _check(*_three_runs(engine, run), f"wgrad gemm M{M} N{N} K{K}")
 
 
-@pytest.mark.parametrize("split_k", [1, 4])
+@pytest.mark.parametrize("split_k", [
+    pytest.param(0, marks=pytest.mark.xfail(strict=False, reason="case written after round 1's GPU budget was spent: "
+                                            "not yet run on hardware (XPASS expected)")),
+    1])
 def test_decode_gemm_ignores_leftover_state(engine, split_k):
+    """split_k is a flag: 0 = one CTA per tile (deterministic, must be bit-identical); 1 = split-K
+    with an automatic split count whose partial sums meet through fp32 atomics, so the summation
+    order -- and the last bf16 bit of small outputs -- depends on timing: finite + allclose."""
     M, N, K = 32, 1024, 2048
     g = torch.Generator().manual_seed(4)
     X = dev(torch.randn(M, K, generator=g).bfloat16())
@@ -102,7 +108,12 @@ def test_decode_gemm_ignores_leftover_state(engine, split_k):
         torch.cuda.synchronize()
         return (D,)
 
-    _check(*_three_runs(engine, run), f"decode gemm split_k={split_k}")
+    a, b, c = _three_runs(engine, run)
+    if split_k:
+        _same(a[0], c[0], "decode gemm split-K (atomics)", exact=False)
+    else:
+        assert torch.equal(a[0], b[0]), "decode gemm without split-K must be deterministic"
+        _same(a[0], c[0], "decode gemm, no split")
 
 
 @pytest.mark.parametrize("B,S,H,Hkv", [(1, 128, 1, 1), (2, 512, 4, 2), (1, 1024, 2, 2), (1, 4096, 2, 1)])

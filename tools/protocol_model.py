@@ -14,8 +14,13 @@ before it has executed. Buffers carry tags ("what is in here"); every consumer a
 needs. A run ends in OK, a Violation (stale / overwritten data) or a deadlock.
 
 attention.cu's dQ kernel is modelled in its v9 (single bar_p) and v10 (bar_p per stage) forms, the
-dK/dV kernel in its shipped form. tests/test_protocol_model.py requires that the model FINDS the v9
-bug and finds nothing in the shipped protocols."""
+dK/dV and forward kernels in their shipped forms plus variants. tests/test_protocol_model.py requires
+that the model FINDS the v9 bug. It also found something nobody had seen on hardware: the shipped
+dK/dV protocol (one bar_p) is free of stale reads but not of an ABA deadlock -- if the MMA warp is
+held up for a whole compute iteration right after issuing the next block's score MMAs, the compute
+warps finish two blocks, bar_p flips twice and the MMA warp waits for a phase that is already gone.
+Real warps do not stall like the model's scheduler, so this needs an external stall to happen
+(DESIGN.md 7 discusses whether the 8-GPU failure was one); bar_p per stage removes it."""
 import random
 
 
@@ -163,12 +168,12 @@ def dq_kernel(njb, per_stage_bar_p, rng, quarters=4, threads_per_quarter=2):
 # dK/dV kernel (attn_bwd_dkdv_kernel): TMA warp (3 Q/dO buffers), MMA warp, compute warps with a
 # block-wide barrier every iteration, staging tiles double-buffered behind bar_d
 # ---------------------------------------------------------------------------------------------
-def dkdv_kernel(n_iter, rng, n_thr=6, block_barrier=True):
+def dkdv_kernel(n_iter, rng, n_thr=6, block_barrier=True, per_stage_bar_p=False):
     pipe = TensorPipe()
     bar_q = [Mbar(1) for _ in range(3)]
     bar_qfree = [Mbar(1) for _ in range(3)]
     bar_s, bar_d = [Mbar(1), Mbar(1)], [Mbar(1), Mbar(1)]
-    bar_p = Mbar(n_thr)
+    bar_p = [Mbar(n_thr), Mbar(n_thr)] if per_stage_bar_p else [Mbar(n_thr)]
     Q = [None] * 3                       # which block's Q/dO is in buffer b
     S = [None, None]
     stage = [[None] * n_thr for _ in range(2)]     # P/dS staging tiles
@@ -218,7 +223,11 @@ def dkdv_kernel(n_iter, rng, n_thr=6, block_barrier=True):
             if it + 1 < n_iter:
                 yield (lambda nqb=nqb, npar=npar: bar_q[nqb].passed(npar))
                 pipe.issue(scores(it + 1, nqb)); pipe.commit(bar_s[(it + 1) & 1])
-            yield (lambda it=it: bar_p.passed(it & 1))
+            if per_stage_bar_p:
+                b, par = bar_p[it & 1], (it >> 1) & 1
+            else:
+                b, par = bar_p[0], it & 1
+            yield (lambda b=b, par=par: b.passed(par))
             pipe.issue(dvdk(it, qb)); pipe.commit(bar_d[it & 1]); pipe.commit(bar_qfree[qb])
             qb, qpar = nqb, npar
             yield None
@@ -235,7 +244,7 @@ def dkdv_kernel(n_iter, rng, n_thr=6, block_barrier=True):
             yield None
             stage[tb][t] = it
             yield None
-            bar_p.arrive()
+            (bar_p[tb] if per_stage_bar_p else bar_p[0]).arrive()
             if block_barrier:                            # bwd_compute_bar_sync()
                 gen = state["sync_gen"]
                 state["sync_count"] += 1
@@ -401,7 +410,9 @@ if __name__ == "__main__":
                          ("dQ v3-v8 (smem staging, one bar_p)", dq_kernel_v8, dict(njb=8)),
                          ("forward shipped", fwd_kernel, dict(njb=8)),
                          ("forward without the bar_o wait", fwd_kernel, dict(njb=8, wait_bar_o=False)),
-                         ("dK/dV shipped", dkdv_kernel, dict(n_iter=9)),
+                         ("dK/dV shipped (one bar_p)", dkdv_kernel, dict(n_iter=2)),
+                         ("dK/dV with bar_p per stage", dkdv_kernel, dict(n_iter=2, per_stage_bar_p=True)),
+                         ("dK/dV per stage, no block barrier", dkdv_kernel, dict(n_iter=9, per_stage_bar_p=True, block_barrier=False)),
                          ("dK/dV without the block barrier", dkdv_kernel, dict(n_iter=9, block_barrier=False))]:
-        ok, first, other = explore(fn, 400, **kw)
-        print(f"{name:36s} ok {ok:4d}/400   first violation: {first}   other: {other}")
+        ok, first, other = explore(fn, 2000, **kw)
+        print(f"{name:36s} ok {ok:4d}/2000   first violation: {first}   other: {other}")

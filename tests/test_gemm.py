@@ -118,3 +118,26 @@ def test_gemm_rejects_bad_arguments(engine):
     D = torch.zeros(128, 128, device="cuda", dtype=torch.float32)
     with pytest.raises(B200WError):
         call(engine, "b200w_op_gemm", A, 0, 60, A, 0, 60, D, None, 1, 128, 128, 128, 60, 0)
+
+
+@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: not yet run on hardware (XPASS expected)")
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,acc", [(4096, 4096, 4096, 0, 0, False), (4096, 4096, 4096, 0, 1, False),
+                                                 (4096, 11008, 4096, 1, 1, True), (1024, 12288, 4096, 0, 0, False)])
+def test_gemm_is_race_free(engine, M, N, K, a_mn, b_mn, acc):
+    """Same idea as test_attention_is_race_free: no atomics in these kernels, so 200 launches on fixed
+    operands must be bit-identical. (The attention dQ kernel passed every parity test while being
+    wrong in 1.2 % of launches; parity tests run each shape once.)"""
+    Ad, Bd, _ = _operands(M, N, K, a_mn, b_mn, seed=21)
+    C0 = torch.randn(M, N, generator=torch.Generator().manual_seed(22)).to("cuda") if acc else None
+
+    def run():
+        D = C0.clone() if acc else torch.empty(M, N, device="cuda", dtype=torch.float32)
+        call(engine, "b200w_op_gemm", Ad, a_mn, Ad.shape[1], Bd, b_mn, Bd.shape[1], D, D if acc else None, 1, N,
+             M, N, K, 0)
+        return D
+
+    ref = run()
+    assert torch.isfinite(ref).all()
+    bad = sum(not torch.equal(run(), ref) for _ in range(200))
+    print(f"gemm race check M{M} N{N} K{K} a_mn{a_mn} b_mn{b_mn} acc{acc}: mismatching launches {bad}/200")
+    assert bad == 0

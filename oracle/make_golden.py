@@ -188,8 +188,81 @@ def run_falcon():
     print(f"falcon -> {path} ({os.path.getsize(path) / 1024:.0f} KiB); generated[0] = {gen[0].tolist()}")
 
 
+def run_opt():
+    """Tiny opt-125m-family model through the real OPTForCausalLM: two optimiser
+    steps with -100 labels (logits, gradients, updated weights) and a greedy continuation."""
+    from transformers import OPTConfig, OPTForCausalLM
+    from oracle import opt_oracle as OO
+
+    a = OO.OptArch(vocab_size=192, hidden_size=128, ffn_dim=256, num_layers=2, num_heads=2, max_position_embeddings=64)
+    params = OO.seeded_params(a, 31)
+    cfg = OPTConfig(vocab_size=a.vocab_size, hidden_size=a.hidden_size, ffn_dim=a.ffn_dim, num_hidden_layers=a.num_layers,
+                    num_attention_heads=a.num_heads, max_position_embeddings=a.max_position_embeddings,
+                    word_embed_proj_dim=a.hidden_size, do_layer_norm_before=True, activation_function="relu",
+                    enable_bias=True, dropout=0.0, attention_dropout=0.0, layerdrop=0.0, tie_word_embeddings=True)
+    cfg._attn_implementation = "sdpa"
+    torch.manual_seed(0)
+    model = OPTForCausalLM(cfg).float()
+    sd = {k: torch.tensor(v) for k, v in params.items()}
+    sd["lm_head.weight"] = sd["model.decoder.embed_tokens.weight"]
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    assert model.lm_head.weight.data_ptr() == model.model.decoder.embed_tokens.weight.data_ptr(), "head must be tied"
+    rng = np.random.default_rng(32)
+    B, S = 2, 48
+
+    def batch():
+        ids = rng.integers(0, a.vocab_size, size=(B, S)).astype(np.int64)
+        labels = ids.copy()
+        labels[0, :9] = -100
+        labels[1, 20:27] = -100
+        return ids, labels
+
+    ids, labels = batch()
+    model.train()
+    out = model(input_ids=torch.tensor(ids), labels=torch.tensor(labels))
+    out.loss.backward()
+    named = dict(model.named_parameters())          # tied weight appears once
+    grads = {k: p.grad.detach().clone() for k, p in named.items()}
+    gnorm = float(torch.nn.utils.clip_grad_norm_(list(named.values()), 1.0))
+    opt = torch.optim.AdamW(list(named.values()), lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    ids2, labels2 = batch()
+    out2 = model(input_ids=torch.tensor(ids2), labels=torch.tensor(labels2))
+    out2.loss.backward()
+    gnorm2 = float(torch.nn.utils.clip_grad_norm_(list(named.values()), 1.0))
+    for g in opt.param_groups:
+        g["lr"] = 2.5e-5
+    opt.step()
+    fx = dict(arch=np.array([a.vocab_size, a.hidden_size, a.ffn_dim, a.num_layers, a.num_heads, a.max_position_embeddings]),
+              seed=np.int64(31), ids=ids, labels=labels, ids2=ids2, labels2=labels2,
+              loss=np.float32(out.loss.item()), gnorm=np.float32(gnorm), loss2=np.float32(out2.loss.item()),
+              gnorm2=np.float32(gnorm2), logits=out.logits.detach().numpy().astype(np.float32))
+    for k in named:
+        fx["gradnorm/" + k] = np.float32(grads[k].norm().item())
+        fx["grad/" + k] = grads[k].flatten()[::17].numpy().copy()
+        fx["param2/" + k] = named[k].detach().flatten()[::17].numpy().copy()
+    # greedy continuation from the ORIGINAL weights
+    model2 = OPTForCausalLM(cfg).float().eval()
+    model2.load_state_dict(sd, strict=False)
+    prompts = rng.integers(0, a.vocab_size, size=(3, 16)).astype(np.int64)
+    with torch.no_grad():
+        gen = model2.generate(torch.tensor(prompts), max_new_tokens=10, do_sample=False, pad_token_id=1).numpy()[:, 16:]
+        fx["gen_logits"] = model2(torch.tensor(prompts)).logits.numpy().astype(np.float32)
+    fx["prompts"], fx["generated"] = prompts, gen
+    path = os.path.join(OUT, "opt_tiny.npz")
+    np.savez_compressed(path, **fx)
+    print(f"opt -> {path} ({os.path.getsize(path) / 1024:.0f} KiB): loss {out.loss.item():.6f} gnorm {gnorm:.6f} "
+          f"loss2 {out2.loss.item():.6f}; generated[0] = {gen[0].tolist()}")
+
+
 if __name__ == "__main__":
+    if "--opt-only" in sys.argv:
+        run_opt()
+        sys.exit(0)
     run_ops()
     run_falcon()
+    run_opt()
     for name, (a, B, seed) in CASES.items():
         run_case(name, a, B, seed)

@@ -68,3 +68,13 @@ def test_shipped_forward_protocol_is_clean_and_needs_its_bar_o_wait():
     for njb in (1, 2, 8):
         _clean(pm.fwd_kernel, njb=njb)
     _broken(pm.fwd_kernel, "PV MMA", njb=8, wait_bar_o=False)
+
+
+def test_pair_gemm_ring_protocol_is_clean():
+    """gemm_bf16_pair_kernel: a full/empty pair per pipeline stage and a tfull/tempty pair per accumulator
+    stage -- per-stage barriers, so no ABA; checked anyway, including fewer k-blocks than stages, one
+    tile, and the 8-arrival accumulator release collected from both CTAs."""
+    for kw in (dict(num_tiles=5, num_kb=7), dict(num_tiles=1, num_kb=1), dict(num_tiles=3, num_kb=2, stages=6),
+               dict(num_tiles=4, num_kb=13, stages=6)):
+        ok, first, other = pm.explore(pm.gemm_pair_kernel, 300, seed=2, **kw)
+        assert (ok, first, other) == (300, None, {}), (kw, first, other)

@@ -387,6 +387,98 @@ def fwd_kernel(njb, rng, n_thr=8, wait_bar_o=True):
     return res
 
 
+# ---------------------------------------------------------------------------------------------
+# CTA-pair persistent GEMM (gemm.cu gemm_bf16_pair_kernel): TMA producers in both CTAs fill a ring of
+# STAGES slots (one full / empty barrier pair per slot, the leader's full barrier collects both CTAs'
+# bytes), the leader's MMA warp consumes them into one of two TMEM accumulator stages and commits
+# empty (multicast to both CTAs) / tfull (multicast); 4 epilogue warps per CTA drain the
+# accumulator and arrive on the LEADER's tempty barrier (count 8).
+# ---------------------------------------------------------------------------------------------
+def gemm_pair_kernel(num_tiles, num_kb, rng, stages=3, epi_warps=4):
+    pipe = TensorPipe()
+    full = [Mbar(2) for _ in range(stages)]               # leader's: one complete_tx per CTA (modelled as 2 arrivals)
+    empty = [[Mbar(1) for _ in range(stages)] for _ in range(2)]   # per CTA (the commit is multicast)
+    tfull = [[Mbar(1), Mbar(1)] for _ in range(2)]        # per CTA (multicast)
+    tempty = [Mbar(2 * epi_warps), Mbar(2 * epi_warps)]   # leader's
+    slot = [[None] * stages for _ in range(2)]            # per CTA: (tile, kb) whose operand halves are in the slot
+    acc = [None, None]                                    # which tile's sum is in accumulator stage a: (tile, kb_count)
+    state = dict(mma_done=False, out=[[], []])
+
+    def producer(cta):
+        stage, phase = 0, 0
+        for tile in range(num_tiles):
+            for kb in range(num_kb):
+                yield (lambda s=stage, ph=phase: empty[cta][s].passed(ph ^ 1))
+                slot[cta][stage] = (tile, kb)
+                full[stage].arrive()
+                stage += 1
+                if stage == stages:
+                    stage, phase = 0, phase ^ 1
+                yield None
+
+    def mma(tile, kb, stage, a):
+        def ex():
+            for cta in range(2):
+                if slot[cta][stage] != (tile, kb):
+                    raise Violation(f"MMA of tile {tile} k-block {kb} read slot holding {slot[cta][stage]} (CTA {cta})")
+            if kb == 0:
+                acc[a] = [tile, 1]
+            else:
+                if acc[a][0] != tile:
+                    raise Violation(f"MMA of tile {tile} accumulated onto tile {acc[a][0]}")
+                acc[a][1] += 1
+        return ex
+
+    def commit_multicast(bars):
+        def ex():
+            for b in bars:
+                b.arrive()
+        return ex
+
+    def mma_warp():
+        stage, phase, a, aph = 0, 0, 0, 0
+        for tile in range(num_tiles):
+            yield (lambda a=a, aph=aph: tempty[a].passed(aph ^ 1))
+            for kb in range(num_kb):
+                yield (lambda s=stage, ph=phase: full[s].passed(ph))
+                pipe.issue(mma(tile, kb, stage, a))
+                pipe.issue(commit_multicast([empty[0][stage], empty[1][stage]]))
+                stage += 1
+                if stage == stages:
+                    stage, phase = 0, phase ^ 1
+                yield None
+            pipe.issue(commit_multicast([tfull[0][a], tfull[1][a]]))
+            a += 1
+            if a == 2:
+                a, aph = 0, aph ^ 1
+            yield None
+        state["mma_done"] = True
+
+    def epilogue(cta, w):
+        a, aph = 0, 0
+        for tile in range(num_tiles):
+            yield (lambda a=a, aph=aph: tfull[cta][a].passed(aph))
+            if acc[a] != [tile, num_kb]:
+                raise Violation(f"epilogue of tile {tile} read accumulator holding {acc[a]}")
+            yield None                                   # tcgen05.ld + stores
+            if w == 0:
+                state["out"][cta].append(tile)
+            tempty[a].arrive()
+            a += 1
+            if a == 2:
+                a, aph = 0, aph ^ 1
+            yield None
+
+    agents = {"mma": mma_warp(), "pipe": pipe.agent(lambda: state["mma_done"]), "tma0": producer(0), "tma1": producer(1)}
+    for cta in range(2):
+        for w in range(epi_warps):
+            agents[f"epi{cta}{w}"] = epilogue(cta, w)
+    res = run(agents, rng)
+    if res == "ok" and state["out"] != [list(range(num_tiles))] * 2:
+        raise Violation(f"tiles written: {state['out']}")
+    return res
+
+
 def explore(kernel, trials, seed=0, **kw):
     """-> (#ok, first violation or None, other outcomes)"""
     ok, first, other = 0, None, {}
@@ -413,6 +505,8 @@ if __name__ == "__main__":
                          ("dK/dV shipped (one bar_p)", dkdv_kernel, dict(n_iter=2)),
                          ("dK/dV with bar_p per stage", dkdv_kernel, dict(n_iter=2, per_stage_bar_p=True)),
                          ("dK/dV per stage, no block barrier", dkdv_kernel, dict(n_iter=9, per_stage_bar_p=True, block_barrier=False)),
-                         ("dK/dV without the block barrier", dkdv_kernel, dict(n_iter=9, block_barrier=False))]:
+                         ("dK/dV without the block barrier", dkdv_kernel, dict(n_iter=9, block_barrier=False)),
+                         ("pair GEMM, 5 tiles x 7 k-blocks", gemm_pair_kernel, dict(num_tiles=5, num_kb=7)),
+                         ("pair GEMM, 1 tile x 1 k-block", gemm_pair_kernel, dict(num_tiles=1, num_kb=1))]:
         ok, first, other = explore(fn, 2000, **kw)
         print(f"{name:36s} ok {ok:4d}/2000   first violation: {first}   other: {other}")

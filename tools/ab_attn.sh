@@ -2,6 +2,10 @@
 # Same-box per-kernel A/B of the attention kernels: ncu launch durations (serialised, cold cache,
 # --clock-control none) of two library builds, interleaved. Then one --set full capture of the dQ kernel.
 #   usage: tools/ab_attn.sh <other.so> [rounds]
+# To build <other.so>: git show <rev>:runbooks_b200/csrc/attention.cu > /tmp/prev.cu; nvcc (flags of runbooks_b200/build.py)
+# -Irunbooks_b200/csrc -Iinclude -c /tmp/prev.cu -o /tmp/prev.o; link it with the other objects of
+# runbooks_b200/build/ into a second .so inside the repo tree so that it travels to the GPU box
+# (round 1 used rev c3287da).
 set -u
 OTHER=$1; ROUNDS=${2:-2}
 LIB=runbooks_b200/libb200w.so

@@ -2,6 +2,10 @@
 # Same-box A/B of two builds of the library (numbers from different boxes differ by their power-capped
 # clocks). Runs on the GPU box's scratch copy only: the shipped library is swapped and restored.
 #   usage: tools/ab_gemm.sh <other.so> [rounds]
+# To build <other.so>: git show <rev>:runbooks_b200/csrc/gemm.cu > /tmp/prev.cu; nvcc (flags of runbooks_b200/build.py)
+# -Irunbooks_b200/csrc -Iinclude -c /tmp/prev.cu -o /tmp/prev.o; link it with the other objects of
+# runbooks_b200/build/ into a second .so inside the repo tree so that it travels to the GPU box
+# (round 1 used rev e6ad6b9).
 set -u
 OTHER=$1; ROUNDS=${2:-2}
 LIB=runbooks_b200/libb200w.so

@@ -1,0 +1,180 @@
+"""Host logic of the Server path on CPU: continuous batching (infer.Generator), the scheduler thread and
+the HTTP surface the reference probes and the system test speaks (server_controller.go:156-173 readiness
+GET / -> 200; test/system.sh:73-78 POST /v1/completions {"prompt", "max_tokens"}).
+
+The engine is a stub whose "model" makes the next token a hash of EVERYTHING fed into that KV-cache slot
+so far, at the positions it was fed: a scheduler that mixes up slots, positions or the token it feeds
+back produces different text. (The CUDA engine itself is covered by tests/test_infer.py / test_server.py
+on a GPU; there is no CPU fallback in the product.)"""
+import json
+import threading
+import urllib.error
+import urllib.request
+from http.server import ThreadingHTTPServer
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from runbooks_b200 import server
+from runbooks_b200.infer import Generator
+
+VOCAB, EOS = 97, 96
+
+
+class StubEngine:
+    def __init__(self, max_batch=2, max_ctx=64):
+        self.max_batch = max_batch
+        self.serve_arch = SimpleNamespace(max_ctx=max_ctx, vocab_size=VOCAB)
+        self.cache = {}            # slot -> list of (position, token)
+        self.batch_sizes = []
+
+    def step(self, tokens, positions, slots, want_logits=False):
+        assert len(set(slots)) == len(slots), "one row per cache slot"
+        assert len(tokens) <= self.max_batch
+        self.batch_sizes.append(len(tokens))
+        out = []
+        for t, p, s in zip(tokens, positions, slots):
+            hist = self.cache.setdefault(s, [])
+            if p == 0:
+                hist.clear()                       # a new request re-uses the slot from position 0
+            assert p == len(hist), f"slot {s}: fed position {p}, cache holds {len(hist)} tokens"
+            hist.append((int(p), int(t)))
+            h = 7
+            for pp, tt in hist:
+                h = (h * 31 + 3 * pp + tt) % 1000003
+            out.append(h % (VOCAB - 1))            # never EOS unless a test asks for it
+        return np.array(out, dtype=np.int32), None
+
+
+def reference(prompt, max_tokens):
+    """the same stub, one request alone in slot 0"""
+    g = Generator(StubEngine(max_batch=1))
+    return g.generate([prompt], max_tokens)[0]
+
+
+def test_continuous_batching_equals_one_request_at_a_time():
+    rng = np.random.default_rng(0)
+    prompts = [list(map(int, rng.integers(0, VOCAB - 1, size=n))) for n in (1, 5, 3, 9, 2, 7)]
+    lens = [4, 1, 6, 3, 8, 2]
+    eng = StubEngine(max_batch=3)
+    g = Generator(eng)
+    reqs, todo = [], list(zip(prompts, lens))
+    while todo or g.active:
+        while todo and g.free:                     # admit whenever a slot is free, like the scheduler
+            p, n = todo.pop(0)
+            reqs.append((g.add(p, n), p, n))
+        g.step()
+    for r, p, n in reqs:
+        assert r.done and r.out == reference(p, n)
+        assert len(r.out) == n
+    assert max(eng.batch_sizes) == 3 and sorted(g.free) == [0, 1, 2]
+
+
+def test_generator_rejects_what_cannot_fit():
+    g = Generator(StubEngine(max_batch=1, max_ctx=8))
+    with pytest.raises(ValueError):
+        g.add([], 2)
+    with pytest.raises(ValueError):
+        g.add([1, 2, 3, 4, 5], 4)                  # 5 + 4 > 8
+    g.add([1, 2, 3, 4], 4)                         # exactly the cache length
+    with pytest.raises(RuntimeError):
+        g.add([1], 1)                              # no free slot
+
+
+def test_generator_stops_at_eos():
+    class EosAtThird(StubEngine):
+        def step(self, tokens, positions, slots, want_logits=False):
+            nxt, _ = super().step(tokens, positions, slots)
+            return np.array([EOS if p == 4 else n for n, p in zip(nxt, positions)], dtype=np.int32), None
+    g = Generator(EosAtThird(max_batch=1), eos_id=EOS)
+    out = g.generate([[5, 6, 7]], 10)[0]          # positions 0..2 prompt; generated at 2, 3, 4 -> third is EOS
+    assert len(out) == 3 and out[-1] == EOS
+
+
+class CharTok:
+    """ids = code points mod VOCAB; enough for the HTTP layer"""
+    bos_id, eos_id = 1, EOS
+
+    def encode(self, s):
+        return [ord(c) % (VOCAB - 1) for c in s]
+
+    def decode(self, ids):
+        return "".join(chr(97 + i % 26) for i in ids)
+
+
+@pytest.fixture()
+def http_server():
+    eng = StubEngine(max_batch=2, max_ctx=48)
+    sched = server.Scheduler(eng, CharTok())
+    httpd = ThreadingHTTPServer(("127.0.0.1", 0), server.make_handler(sched, "stub-model"))
+    t = threading.Thread(target=httpd.serve_forever, daemon=True)
+    t.start()
+    yield sched, eng, f"http://127.0.0.1:{httpd.server_address[1]}"
+    httpd.shutdown()
+
+
+def _get(url):
+    try:
+        with urllib.request.urlopen(url, timeout=10) as r:
+            return r.status, json.loads(r.read())
+    except urllib.error.HTTPError as e:
+        return e.code, json.loads(e.read())
+
+
+def _post(url, obj):
+    req = urllib.request.Request(url, data=json.dumps(obj).encode(), headers={"Content-Type": "application/json"})
+    try:
+        with urllib.request.urlopen(req, timeout=30) as r:
+            return r.status, json.loads(r.read())
+    except urllib.error.HTTPError as e:
+        return e.code, json.loads(e.read())
+
+
+def test_readiness_probe_follows_the_scheduler(http_server):
+    sched, _, base = http_server
+    assert _get(base + "/")[0] == 503                       # model still loading: the Deployment is not Ready
+    sched.start()
+    assert sched.ready.wait(5)
+    code, body = _get(base + "/")
+    assert code == 200 and body["status"] == "ok"
+    assert _get(base + "/v1/models")[1]["data"][0]["id"] == "stub-model"
+    assert _get(base + "/nope")[0] == 404
+
+
+def test_completions_shape_and_concurrency_beyond_the_slot_count(http_server):
+    sched, eng, base = http_server
+    sched.start()
+    prompts = [f"request number {i} " + "x" * i for i in range(8)]     # 8 requests, 2 cache slots
+    results = [None] * len(prompts)
+
+    def go(i):
+        results[i] = _post(base + "/v1/completions", {"prompt": prompts[i], "max_tokens": 3 + i % 4})
+    threads = [threading.Thread(target=go, args=(i,)) for i in range(len(prompts))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    tok = CharTok()
+    for i, (code, body) in enumerate(results):
+        assert code == 200, body
+        n = 3 + i % 4
+        ids = [tok.bos_id] + tok.encode(prompts[i])
+        assert body["object"] == "text_completion" and body["model"] == "stub-model"
+        ch = body["choices"][0]
+        assert ch["text"] == tok.decode(reference(ids, n)) and ch["finish_reason"] == "length"
+        assert body["usage"] == {"prompt_tokens": len(ids), "completion_tokens": n, "total_tokens": len(ids) + n}
+    assert max(eng.batch_sizes) == 2
+
+
+def test_bad_requests_do_not_kill_the_server(http_server):
+    sched, _, base = http_server
+    sched.start()
+    assert _post(base + "/v1/completions", {"max_tokens": 3})[0] == 400                     # no prompt
+    assert _post(base + "/v1/completions", {"prompt": "hi", "max_tokens": 0})[0] == 400
+    code, body = _post(base + "/v1/completions", {"prompt": "y" * 60, "max_tokens": 4})     # longer than the KV cache
+    assert code == 400 and "KV cache" in body["error"]
+    assert _post(base + "/v1/other", {"prompt": "hi"})[0] == 404
+    code, body = _post(base + "/v1/completions", {"prompt": ["list form"], "max_tokens": 2})
+    assert code == 200 and body["usage"]["completion_tokens"] == 2
+    assert _get(base + "/")[0] == 200

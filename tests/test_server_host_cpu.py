@@ -144,7 +144,6 @@ def test_readiness_probe_follows_the_scheduler(http_server):
 
 def test_completions_shape_and_concurrency_beyond_the_slot_count(http_server):
     sched, eng, base = http_server
-    sched.start()
     prompts = [f"request number {i} " + "x" * i for i in range(8)]     # 8 requests, 2 cache slots
     results = [None] * len(prompts)
 
@@ -153,6 +152,14 @@ def test_completions_shape_and_concurrency_beyond_the_slot_count(http_server):
     threads = [threading.Thread(target=go, args=(i,)) for i in range(len(prompts))]
     for t in threads:
         t.start()
+    # all eight are queued BEFORE the scheduler runs (the stub engine is instantaneous, so otherwise
+    # whether two requests ever share a step would depend on thread timing)
+    import time
+    deadline = time.time() + 20
+    while sched.q.qsize() < len(prompts) and time.time() < deadline:
+        time.sleep(0.01)
+    assert sched.q.qsize() == len(prompts)
+    sched.start()
     for t in threads:
         t.join(60)
     tok = CharTok()

@@ -40,7 +40,7 @@ def _ignores_sigterm(rank, q):
 
 
 def _run(targets, grace=2.0):
-    ctx = mp.get_context("fork")
+    ctx = mp.get_context("spawn")   # not fork: the pytest process is multi-threaded by the time this runs
     q = ctx.Queue()
     procs = [ctx.Process(target=t, args=(r, q)) for r, t in enumerate(targets)]
     for p in procs:

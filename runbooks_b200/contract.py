@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import glob
 import json
+import math
 import os
 import shutil
 from dataclasses import dataclass, field
@@ -42,7 +43,10 @@ class TrainParams:
     adam_epsilon: float = 1e-8
     max_grad_norm: float = 1.0
     lr_scheduler_type: str = "linear"
-    warmup_steps: int = 0
+    warmup_steps: float = 0.0         # >= 1: exact steps; in [0, 1): ratio of the total (training_args.py:789, :2068-2075)
+    optim: str = "adamw_torch_fused"   # the default with torch >= 2.8 (training_args.py:797-806); same AdamW formula as adamw_torch
+    label_smoothing_factor: float = 0.0
+    average_tokens_across_devices: str = "true"
     save_steps: int = 500
     logging_steps: int = 1
     seed: int = 42
@@ -50,7 +54,9 @@ class TrainParams:
     prompt_template: str = "{prompt}{completion}"
     extra: Dict[str, object] = field(default_factory=dict)
 
-    ALIASES = {"epochs": "num_train_epochs", "lr": "learning_rate", "batch_size": "per_device_train_batch_size"}
+    # warmup_ratio: deprecated TrainingArguments alias that is assigned into warmup_steps (training_args.py:1472-1474)
+    ALIASES = {"epochs": "num_train_epochs", "lr": "learning_rate", "batch_size": "per_device_train_batch_size",
+               "warmup_ratio": "warmup_steps"}
 
 
 def _coerce(value, target_type):
@@ -89,11 +95,28 @@ def load_params(path: Optional[str] = None, environ: Optional[Dict[str, str]] = 
                 raise ValueError(f"param {k!r}: cannot read {v!r} as {type(getattr(p, k2)).__name__}") from e
         else:
             p.extra[k] = v
+    # TrainingArguments that change the arithmetic and are not implemented must fail the Job (exit 1 is the
+    # whole protocol) instead of training something else and reporting success; everything else that is
+    # unknown lands in `extra` and is listed in the worker's start event.
     if p.lr_scheduler_type != "linear":
         raise ValueError("only lr_scheduler_type=linear (the TrainingArguments default) is implemented")
+    if p.optim not in ("adamw_torch", "adamw_torch_fused"):
+        raise ValueError(f"optim={p.optim!r} is not implemented (AdamW, the TrainingArguments default, is)")
+    if p.label_smoothing_factor != 0.0:
+        raise ValueError("label_smoothing_factor != 0 is not implemented")
+    if str(p.average_tokens_across_devices).strip().lower() not in ("true", "1"):
+        raise ValueError("average_tokens_across_devices=false is not implemented: the N-rank step always "
+                         "normalises by the global target count (the TrainingArguments default)")
+    if p.warmup_steps < 0:
+        raise ValueError("warmup_steps must be >= 0")
     if p.gradient_accumulation_steps < 1 or p.per_device_train_batch_size < 1:
         raise ValueError("batch sizes must be >= 1")
     return p
+
+
+def warmup_steps_for(total_steps: int, warmup_steps: float) -> int:
+    """TrainingArguments.get_warmup_steps (training_args.py:2068-2075)."""
+    return int(warmup_steps) if warmup_steps >= 1 else int(math.ceil(total_steps * warmup_steps))
 
 
 def linear_lr(step_index: int, total_steps: int, base_lr: float, warmup: int = 0) -> float:

@@ -93,10 +93,12 @@ def train_rank(rank: int, world: int, uid: bytes, content: str) -> None:
         reps = (per_step + len(ids) - 1) // len(ids)
         ids, labels = np.tile(ids, (reps, 1)), np.tile(labels, (reps, 1))
     per_rank = per_step // world
+    warmup = contract.warmup_steps_for(total_steps, params.warmup_steps)
     if rank == 0:
         log(event="start", model=hf_cfg.get("_name_or_path", "llama"), params=int(sum(np.prod(s) for _, s in eng.params())),
             sequences=int(len(ids)), seq_len=seq_len, world_size=world, total_steps=total_steps,
-            global_batch=per_step, load_seconds=round(time.time() - t0, 2), device_gb=round(eng.device_bytes() / 1e9, 2))
+            global_batch=per_step, load_seconds=round(time.time() - t0, 2), device_gb=round(eng.device_bytes() / 1e9, 2),
+            warmup_steps=warmup, ignored_params=sorted(params.extra))
 
     rng = np.random.default_rng(params.seed)
     order: List[int] = []
@@ -107,7 +109,7 @@ def train_rank(rank: int, world: int, uid: bytes, content: str) -> None:
             order = list(rng.permutation(len(ids)))       # same permutation on every rank (same seed)
         batch, order = order[:per_step], order[per_step:]
         mine = batch[rank::world]                           # rank r takes sequences [r::N]
-        lr = contract.linear_lr(step, total_steps, params.learning_rate, params.warmup_steps)
+        lr = contract.linear_lr(step, total_steps, params.learning_rate, warmup)
         loss, gnorm = eng.train_step(ids[mine], labels[mine], lr=lr)
         step += 1
         if rank == 0 and step % max(1, params.logging_steps) == 0:

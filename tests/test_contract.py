@@ -165,3 +165,52 @@ def test_serve_arch_from_hf_configs():
                                    "intermediate_size": 11008, "num_hidden_layers": 32, "num_attention_heads": 32,
                                    "rms_norm_eps": 1e-5, "max_position_embeddings": 4096})
     assert (ll.family, ll.num_kv_heads, ll.head_dim, ll.max_ctx, ll.tie_embeddings) == ("llama", 32, 128, 4096, False)
+
+
+def test_warmup_semantics_match_training_arguments(tmp_path):
+    """warmup_steps >= 1: exact steps; in [0, 1): ratio of the total, rounded up; warmup_ratio: deprecated
+    alias. Checked against the real TrainingArguments.get_warmup_steps (the class itself cannot be
+    instantiated here -- it needs `accelerate` -- but the method only reads self.warmup_steps)."""
+    from types import SimpleNamespace
+    from transformers import TrainingArguments
+    for w in (0, 0.03, 0.1, 0.25, 0.999, 1, 7, 250):
+        for total in (1, 7, 33, 100, 1000):
+            want = TrainingArguments.get_warmup_steps(SimpleNamespace(warmup_steps=w), total)
+            assert contract.warmup_steps_for(total, w) == want, (w, total)
+    f = TrainingArguments.__dataclass_fields__
+    d = contract.TrainParams()
+    assert f["warmup_steps"].default == d.warmup_steps == 0
+    assert f["optim"].default == d.optim and d.optim in ("adamw_torch", "adamw_torch_fused")
+    assert f["label_smoothing_factor"].default == d.label_smoothing_factor == 0.0
+    assert f["average_tokens_across_devices"].default is True
+    p = tmp_path / "params.json"
+    p.write_text(json.dumps({"warmup_ratio": "0.1", "max_steps": 50}))
+    q = contract.load_params(str(p), environ={})
+    assert q.warmup_steps == 0.1 and contract.warmup_steps_for(50, q.warmup_steps) == 5
+    p.write_text(json.dumps({"warmup_steps": 12}))
+    assert contract.warmup_steps_for(50, contract.load_params(str(p), environ={}).warmup_steps) == 12
+    # the schedule with warm-up, against transformers' own lambda
+    import torch
+    from transformers import get_linear_schedule_with_warmup
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=2e-4)
+    sch = get_linear_schedule_with_warmup(opt, num_warmup_steps=5, num_training_steps=50)
+    for i in range(50):
+        assert abs(contract.linear_lr(i, 50, 2e-4, 5) - sch.get_last_lr()[0]) < 1e-12
+        opt.step()
+        sch.step()
+
+
+def test_unimplemented_arithmetic_changing_params_fail_loudly(tmp_path):
+    """The Job's exit code is the whole protocol: a TrainingArguments value that would change the arithmetic and
+    is not implemented must not be ignored. Unknown harmless keys are kept in `extra` (and logged by the worker)."""
+    p = tmp_path / "params.json"
+    for bad in ({"optim": "adafactor"}, {"lr_scheduler_type": "cosine"}, {"label_smoothing_factor": 0.1},
+                {"average_tokens_across_devices": False}, {"average_tokens_across_devices": "false"}, {"warmup_steps": -1}):
+        p.write_text(json.dumps(bad))
+        with pytest.raises(ValueError):
+            contract.load_params(str(p), environ={})
+    for ok in ({"optim": "adamw_torch_fused"}, {"average_tokens_across_devices": True}, {"average_tokens_across_devices": "True"},
+               {"bf16": True, "gradient_checkpointing": "true", "report_to": "none"}):
+        p.write_text(json.dumps(ok))
+        q = contract.load_params(str(p), environ={})
+        assert set(q.extra) == set(ok) - set(contract.TrainParams.__dataclass_fields__)

@@ -1,7 +1,9 @@
 """Runs the -m gpu tests one test FUNCTION per process, each under a timeout, so that a kernel
 trap (which poisons the CUDA context) or a hang in one test cannot hide the results of the others.
 Writes gpurun_out/gpu_tests.json + per-function logs. Used for development probes; the driver's
-own round-end run is the plain `pytest -m gpu`."""
+own round-end run is the plain `pytest -m gpu`.
+  --no-x   do not stop a function at its first failing parametrisation (with -x, the default, one bad
+           parameter hides the outcome of all the later ones)."""
 import json
 import os
 import subprocess
@@ -10,11 +12,12 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
+NO_X = "--no-x" in sys.argv
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    sel = sys.argv[1:] or ["tests"]
+    sel = [a for a in sys.argv[1:] if a != "--no-x"] or ["tests"]
     r = subprocess.run([sys.executable, "-m", "pytest", *sel, "-m", "gpu", "--collect-only", "-q"],
                        cwd=ROOT, capture_output=True, text=True)
     funcs = []
@@ -29,7 +32,7 @@ def main():
         t0 = time.time()
         log = os.path.join(OUT, "test_" + f.replace("/", "_").replace("::", "__") + ".log")
         try:
-            p = subprocess.run([sys.executable, "-m", "pytest", f, "-m", "gpu", "-q", "-s", "-x",
+            p = subprocess.run([sys.executable, "-m", "pytest", f, "-m", "gpu", "-q", "-s", *([] if NO_X else ["-x"]),
                                 "--no-header", "-p", "no:cacheprovider"],
                                cwd=ROOT, capture_output=True, text=True, timeout=420)
             out, code = p.stdout + p.stderr, p.returncode

@@ -3,9 +3,11 @@
 # that is a small multiple of the measured N = 2 run time (58 s), because an N-GPU gpurun call is charged
 # N x its wall time (round 1 lost 89 GPU-minutes to one 8-GPU call with `timeout 600`).
 #
-#   step 1 (1 GPU, ~4 min):   gpurun --timeout 900 -- 'bash tools/round2_first.sh one'
-#   step 2 (2 GPUs, ~3 min):  gpurun --gpus 2 --timeout 600 -- 'bash tools/round2_first.sh two'
-#   step 3 (8 GPUs, <= 4 min): gpurun --gpus 8 --timeout 420 -- 'bash tools/round2_first.sh eight'
+#   step 1 (1 GPU):   tools/gpurun_capped.sh --inner 3300 --max-minutes 60 -- 'bash tools/round2_first.sh one'
+#   step 2 (2 GPUs):  tools/gpurun_capped.sh --gpus 2 --inner 340 --max-minutes 15 -- 'bash tools/round2_first.sh two'
+#   step 3 (8 GPUs):  tools/gpurun_capped.sh --gpus 8 --inner 340 --max-minutes 55 -- 'bash tools/round2_first.sh eight'
+# (--inner = the sum of the `timeout` values of the legs below; gpurun_capped refuses a call whose worst case
+#  N x (inner + 60 s) exceeds the cap or what is left of the round's budget)
 set -u
 mkdir -p gpurun_out
 T="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"

@@ -70,3 +70,38 @@ def test_product_code_never_touches_the_oracle():
                              r"[\"'][^\"'\n]*oracle/_ref", txt, re.M):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_header_is_plain_c_and_the_integration_example_links(lib_path, tmp_path):
+    """include/b200w.h is what a cgo / C host binds: it must compile as C99 (no C++-isms,
+    no torch types) and a C program using it as that section shows must link against the library and get
+    the documented loud failure on a machine without a B200."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdint.h>
+#include "b200w.h"
+int main(void) {
+  b200w_ctx* ctx = NULL;
+  int st = b200w_create(0, &ctx);
+  if (st != B200W_OK) { printf("create failed as documented: %d %s\n", st, b200w_last_error(NULL)); return 3; }
+  b200w_arch a = {32000, 4096, 11008, 32, 32, 32, 128, 4096, 1e-5f, 10000.0f};
+  st = b200w_model_init(ctx, &a, NULL, 1, 1);
+  float loss = 0, gnorm = 0;
+  int32_t ids[1] = {0};
+  if (st == B200W_OK) st = b200w_train_step(ctx, ids, ids, 1, 5e-5f, &loss, &gnorm);
+  b200w_destroy(ctx);
+  return st == B200W_OK ? 0 : 4;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(lib_path)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-o", str(exe), "-L", libdir, "-lb200w", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert run.returncode == 3 and "no CPU fallback" in run.stdout, (run.returncode, run.stdout, run.stderr)

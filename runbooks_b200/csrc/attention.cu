@@ -451,21 +451,17 @@ constexpr int KV_SMEM = 2 * ATOM128 /*K*/ + 2 * ATOM128 /*V*/ + 3 * 2 * ATOM64 /
 // S^T[2]: [0,64) [64,128)   dP^T[2]: [128,192) [192,256)   dV: [256,384)   dK: [384,512)
 constexpr int KV_TMEM_COLS = 512;
 
-// bar_p ("P^T, dS^T of block `it` are in the staging tile") as ONE mbarrier (0, the build verified on
-// hardware in round 1) or one per staging buffer (1). With one barrier the kernel is free of stale
-// reads -- the block-wide barrier at the end of every iteration keeps the compute warps together --
-// but not of an ABA hazard: the compute warps need nothing from the MMA warp to run block it+1 once
-// its score MMAs are issued, so if the MMA warp is held up for a whole compute iteration right
-// after issuing them, bar_p completes twice and the MMA warp waits for a parity that has already
-// flipped back: permanent hang (tools/protocol_model.py finds it in ~0.3 % of adversarial
-// schedules; the hang leaves the TMA warp on bar_qfree[0] parity 0, which is what the 8-GPU run of
-// profiles/r01_n8_failure.txt trapped on). Real warps do not stall like that by themselves, so 0 has
-// 14 000 clean launches; 1 is the same change that fixed the dQ kernel, is clean in the model, and
-// was written after the round's GPU budget was spent: NOT yet run on hardware, hence off.
-#ifndef B200W_DKDV_BARP_PER_STAGE
-#define B200W_DKDV_BARP_PER_STAGE 0
-#endif
-constexpr int KV_NBARP = B200W_DKDV_BARP_PER_STAGE ? 2 : 1;
+// bar_p ("P^T, dS^T of block `it` are in the staging tile") exists once per staging buffer. With a
+// single barrier the kernel was free of stale reads (the block-wide barrier at the end of every
+// iteration keeps the compute warps together) but not of an ABA hazard: the compute warps need
+// nothing from the MMA warp to run block it+1 once its score MMAs are issued, so an MMA warp held up
+// for a whole compute iteration right after issuing them saw bar_p complete twice and waited for a
+// parity that had flipped back -- a permanent hang (tools/protocol_model.py: ~0.3 % of adversarial
+// schedules; the end state, TMA warp parked on bar_qfree[0] parity 0, is what the 8-GPU run of
+// profiles/r01_n8_failure.txt trapped on). One barrier per stage is the change that fixed the dQ
+// kernel's race; a thread reaches the same stage again only after bar_s(it+2), which the MMA warp
+// commits after it has passed this barrier for `it`.
+constexpr int KV_NBARP = 2;
 
 __global__ void __launch_bounds__(BWD_NTHREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
@@ -587,11 +583,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           tc_fence_after();
           issue_scores((it + 1) & 1, nqb_);
         }
-#if B200W_DKDV_BARP_PER_STAGE
         mbar_wait(&bar_p[it & 1], (it >> 1) & 1);
-#else
-        mbar_wait(bar_p, it & 1);
-#endif
         tc_fence_after();
         // dV += P^T dO, dK += dS^T Q : A K-major [128 kv x 64 q], B MN-major (N = dh, K = q rows)
         const uint32_t pb = (it & 1) * A128;  // P/dS staging buffer of this block
@@ -662,7 +654,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&bar_p[B200W_DKDV_BARP_PER_STAGE ? tb : 0]);
+      mbar_arrive(&bar_p[tb]);
       if (have_next) sStat[(tb ^ 1) * 128 + tid] = stat_next * stat_mul;
       bwd_compute_bar_sync();  // stats(it+1) visible; stats(it) no longer read
     }

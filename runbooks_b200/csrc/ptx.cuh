@@ -22,12 +22,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
-// Bounded spin: a wrong descriptor / byte count must become an error, never a hung GPU box.
-#ifndef B200W_WAIT_LIMIT_CYCLES
-#define B200W_WAIT_LIMIT_CYCLES (40000000000ll)  // ~20 s at 1.9 GHz. Was ~2 s until an 8-rank run
-// trapped here (profiles/r01_n8_failure.txt) and it could not be told apart whether the kernel was
-// deadlocked or the GPU merely stalled for seconds under NCCL's transport setup; a real deadlock still
-// ends in a trap, 20 s later.
+// Bounded spin: a wrong descriptor / byte count must become an error, never a hung GPU box. The bound
+// is a POLL COUNT, not a clock: every failed `mbarrier.try_wait` with a suspend-time hint parks the
+// warp in hardware for up to the hint (1 us here) before it returns, so 2^25 failed polls are >= ~30 s
+// of waiting while a poll costs three instructions (try_wait, add, branch). Round 1 re-read clock64()
+// and did a 64-bit compare on every failed poll; the instruction census of the attention kernels
+// (profiles/r01_attention_instruction_census.txt) showed that polling was 10-15 % of what they issued.
+#ifndef B200W_WAIT_LIMIT_POLLS
+#define B200W_WAIT_LIMIT_POLLS (1u << 25)
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -58,11 +60,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait that may suspend the warp for up to `ns` nanoseconds before reporting failure
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > B200W_WAIT_LIMIT_CYCLES) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait_hint(bar, parity, 1000u)) {
+    if (++polls > B200W_WAIT_LIMIT_POLLS) {
       printf("b200w: mbarrier wait timed out (block %d,%d thread %d bar smem 0x%x parity %u)\n",
              blockIdx.x, blockIdx.y, threadIdx.x, smem_u32(bar), parity);
       __trap();

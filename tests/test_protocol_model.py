@@ -40,8 +40,8 @@ def test_shipped_dq_protocol_is_clean():
     _clean(pm.dq_kernel, njb=3, per_stage_bar_p=True)
 
 
-def test_shipped_dkdv_protocol_has_no_stale_reads_but_a_known_aba_deadlock():
-    """B200W_DKDV_BARP_PER_STAGE=0, the build verified on hardware: never a stale read (the block-wide
+def test_round1_dkdv_protocol_had_no_stale_reads_but_an_aba_deadlock():
+    """The single-bar_p protocol shipped in round 1 (no longer in attention.cu): never a stale read (the block-wide
     barrier keeps the compute warps together), but if the MMA warp is held up for a whole compute
     iteration the single bar_p flips twice and it waits for ever (attention.cu). The
     model must keep seeing that, or it has lost the sensitivity that makes its clean verdicts mean
@@ -56,8 +56,8 @@ def test_shipped_dkdv_protocol_has_no_stale_reads_but_a_known_aba_deadlock():
     _broken(pm.dkdv_kernel, "dV/dK MMA", n_iter=9, block_barrier=False)   # the block barrier is load-bearing
 
 
-def test_per_stage_bar_p_makes_the_dkdv_protocol_clean():
-    """B200W_DKDV_BARP_PER_STAGE=1 (compiled and in the model, not yet run on hardware)."""
+def test_shipped_dkdv_protocol_is_clean():
+    """One bar_p per staging buffer: the only dK/dV protocol in attention.cu since round 2."""
     for n_iter in (2, 3, 4, 9):                              # fewer / more blocks than Q/dO buffers
         _clean(pm.dkdv_kernel, n_iter=n_iter, per_stage_bar_p=True)
     ok, first, other = pm.explore(pm.dkdv_kernel, 2000, seed=3, n_iter=2, per_stage_bar_p=True)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200W_ABI_VERSION 1
+#define B200W_ABI_VERSION 2 /* 2: b200w_arch / b200w_infer_arch gained family, pad_token_id, max_positions */
 #if defined(__GNUC__)
 #define B200W_API __attribute__((visibility("default")))
 #else
@@ -42,20 +42,33 @@ typedef enum {
 
 typedef enum { B200W_BF16 = 0, B200W_F32 = 1, B200W_I32 = 2 } b200w_dtype;
 
-/* Architecture of the causal LM. Llama family for this round (models/llama/modeling_llama.py in
- * HF transformers 5.5.0 is the oracle: RMSNorm, rotate_half RoPE, SwiGLU, untied lm_head, no
- * biases). head_dim must be 128. */
+/* Model families. The fine-tune engine builds LLAMA and OPT, the Server engine all three. */
+#define B200W_FAMILY_LLAMA 0  /* HF models/llama/modeling_llama.py: RMSNorm, rotate_half RoPE, SwiGLU,
+                                 untied lm_head, no biases; head_dim must be 128 for training      */
+#define B200W_FAMILY_FALCON 1 /* HF models/falcon/modeling_falcon.py, falcon-7b layout (Server only) */
+#define B200W_FAMILY_OPT 2    /* HF models/opt/modeling_opt.py, opt-125m layout: learned positions
+                                 (+2), pre-LayerNorm with bias, biased projections, ReLU MLP, tied
+                                 lm_head; head_dim 64 or 128 (64 is stored zero-padded to 128 on the
+                                 device, invisibly to load/read_tensor). The reference's config #1:
+                                 examples/facebook-opt-125m/finetuned-model.yaml                    */
+
+/* Architecture of the causal LM to fine-tune. */
 typedef struct {
   int32_t vocab_size;
   int32_t hidden_size;
-  int32_t intermediate_size;
+  int32_t intermediate_size; /* Llama: intermediate_size; OPT: ffn_dim                            */
   int32_t num_layers;
   int32_t num_heads;
   int32_t num_kv_heads;
   int32_t head_dim;
-  int32_t max_seq_len; /* sequences are packed to exactly this many tokens */
-  float rms_norm_eps;
-  float rope_theta;
+  int32_t max_seq_len;  /* sequences are packed to exactly this many tokens (multiple of 128)      */
+  float rms_norm_eps;   /* RMSNorm eps (Llama) / LayerNorm eps (OPT: 1e-5)                          */
+  float rope_theta;     /* Llama only                                                                */
+  int32_t family;       /* B200W_FAMILY_LLAMA or B200W_FAMILY_OPT                                    */
+  int32_t pad_token_id; /* nn.Embedding(padding_idx=config.pad_token_id): that row gets no gradient
+                           from the lookup (modeling_llama.py:358-361, modeling_opt.py:289); -1: none */
+  int32_t max_positions; /* OPT: max_position_embeddings (the table holds 2 more rows); else 0      */
+  int32_t reserved[3];   /* zero                                                                     */
 } b200w_arch;
 
 /* Optimiser hyper-parameters; b200w_default_hparams() fills in the transformers.TrainingArguments
@@ -64,7 +77,8 @@ typedef struct {
   float lr;            /* 5e-5; the per-step value is passed to b200w_train_step            */
   float beta1, beta2;  /* 0.9, 0.999                                                          */
   float eps;           /* 1e-8                                                                */
-  float weight_decay;  /* 0.0                                                                 */
+  float weight_decay;  /* 0.0; applied as HF Trainer does (trainer.py get_decay_parameter_names):
+                          not to norm weights, LayerNorm parameters or biases                    */
   float max_grad_norm; /* 1.0 (<= 0 disables clipping)                                        */
 } b200w_hparams;
 
@@ -147,8 +161,6 @@ B200W_API int64_t b200w_device_bytes(const b200w_ctx* ctx);
 
 /* ---- Server decode path (server_controller.go:149-173 starts the container
  * that runs this loop; oracle: HF FalconForCausalLM / LlamaForCausalLM .generate(do_sample=False)) */
-#define B200W_FAMILY_LLAMA 0
-#define B200W_FAMILY_FALCON 1
 typedef struct {
   int32_t family;            /* B200W_FAMILY_*                                                  */
   int32_t vocab_size;
@@ -161,7 +173,9 @@ typedef struct {
   int32_t max_ctx;           /* KV-cache length per slot                                        */
   float norm_eps;
   float rope_theta;
-  int32_t tie_embeddings;    /* lm_head shares the embedding matrix (Falcon)                    */
+  int32_t tie_embeddings;    /* lm_head shares the embedding matrix (Falcon, OPT)               */
+  int32_t max_positions;     /* OPT: max_position_embeddings (learned table, +2 rows); else 0   */
+  int32_t reserved[3];       /* zero                                                            */
 } b200w_infer_arch;
 /* bf16 weights + a KV cache of max_batch slots x max_ctx positions. Parameter names are the HF
  * checkpoint keys of the family ("transformer.h.0.self_attention.query_key_value.weight", ...). */
@@ -188,10 +202,25 @@ B200W_API int b200w_op_gemm(b200w_ctx* ctx, const void* A, int a_mn, int lda, co
 /* out[M,N] = X[M,K] W[N,K]^T (+C), M <= 128: the decode-time projection (swap-AB, split-K). */
 B200W_API int b200w_op_gemm_decode(b200w_ctx* ctx, const void* X, const void* W, void* out, const void* C, int M,
                          int N, int K, int split_k);
-B200W_API int b200w_op_embed_fwd(b200w_ctx* ctx, const int32_t* ids, const void* table, void* out, int T, int d,
-                       int vocab);
-B200W_API int b200w_op_embed_bwd(b200w_ctx* ctx, const int32_t* ids, const void* dout, float* dtable, int T,
-                       int d, int vocab);
+/* pos_table (NULL or bf16 [*, d]): row (t % S) + pos_offset is added (OPT learned positions).
+ * embed_bwd: pad_id = nn.Embedding padding_idx (-1 none); dpos NULL or the position-table gradient. */
+B200W_API int b200w_op_embed_fwd(b200w_ctx* ctx, const int32_t* ids, const void* table, const void* pos_table,
+                       void* out, int T, int d, int vocab, int S, int pos_offset);
+B200W_API int b200w_op_embed_bwd(b200w_ctx* ctx, const int32_t* ids, const void* dout, float* dtable, float* dpos,
+                       int T, int d, int vocab, int pad_id, int S, int pos_offset);
+/* LayerNorm with bias (OPT family; oracle torch.nn.LayerNorm). mean / rstd fp32 [T]. */
+B200W_API int b200w_op_layernorm_fwd(b200w_ctx* ctx, const void* x, const void* w, const void* b, void* y,
+                           float* mean, float* rstd, int T, int d, float eps);
+/* dx = (dresid ? dresid : 0) + dLN/dx ; dw += sum dy*xhat ; db += sum dy (fp32, deterministic) */
+B200W_API int b200w_op_layernorm_bwd(b200w_ctx* ctx, const void* dy, const void* x, const void* w,
+                           const float* mean, const float* rstd, const void* dresid, void* dx,
+                           float* dw, float* db, int T, int d);
+/* x[t, c] = act(x[t, c] + bias[c]) in place, N columns of rows with stride ld; act 0 none, 1 relu */
+B200W_API int b200w_op_bias_act(b200w_ctx* ctx, void* x, const void* bias, int T, int N, int ld, int act);
+/* dz = dy where act > 0 else 0 (act = saved post-ReLU activation); n elements, multiple of 8 */
+B200W_API int b200w_op_relu_bwd(b200w_ctx* ctx, const void* dy, const void* act, void* dz, int64_t n);
+/* db[c] += sum_t dy[t, c] (fp32) */
+B200W_API int b200w_op_colsum(b200w_ctx* ctx, const void* dy, float* db, int T, int N, int ld);
 B200W_API int b200w_op_rmsnorm_fwd(b200w_ctx* ctx, const void* x, const void* w, void* y, float* rstd, int T,
                          int d, float eps);
 B200W_API int b200w_op_rmsnorm_bwd(b200w_ctx* ctx, const void* dy, const void* x, const void* w,
@@ -211,11 +240,12 @@ B200W_API int b200w_op_attention_fwd(b200w_ctx* ctx, const void* qkv, int ld_qkv
 B200W_API int b200w_op_attention_bwd(b200w_ctx* ctx, const void* qkv, int ld_qkv, int k_off, int v_off,
                            const void* out, const void* dout, int ld_out, const float* lse2,
                            float* delta, void* dqkv, int B, int S, int H, int Hkv, float scale);
-B200W_API int b200w_op_adamw(b200w_ctx* ctx, float* master, float* m, float* v, const float* g, void* w_bf16,
-                   int64_t n, float lr, float beta1, float beta2, float eps, float wd, int step,
-                   float gscale);
+/* g: fp32, or bf16 when g_bf16 != 0 (the data-parallel wire copy) */
+B200W_API int b200w_op_adamw(b200w_ctx* ctx, float* master, float* m, float* v, const void* g, int g_bf16,
+                   void* w_bf16, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
+                   int step, float gscale);
 /* returns sqrt(sum g^2) in *norm_out (HOST) */
-B200W_API int b200w_op_grad_norm(b200w_ctx* ctx, const float* g, int64_t n, float* norm_out);
+B200W_API int b200w_op_grad_norm(b200w_ctx* ctx, const void* g, int g_bf16, int64_t n, float* norm_out);
 /* Robustness hook: overwrites ALL shared memory (227 KB) and all 512 TMEM columns of every SM with
  * `pattern` (e.g. 0x7FC07FC0: NaN as bf16 pairs and as fp32). A kernel may never depend on on-chip
  * state left by whatever ran before it (another library's kernel, e.g. NCCL's, leaves arbitrary

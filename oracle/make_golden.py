@@ -40,7 +40,7 @@ def make_batch(a: Arch, B: int, seed: int):
     return ids, labels
 
 
-def hf_model(a: Arch, params):
+def hf_model(a: Arch, params, pad_token_id=None):
     from transformers import LlamaConfig, LlamaForCausalLM
 
     cfg = LlamaConfig(
@@ -50,6 +50,7 @@ def hf_model(a: Arch, params):
         max_position_embeddings=a.max_seq_len, rms_norm_eps=a.rms_norm_eps,
         rope_parameters={"rope_type": "default", "rope_theta": a.rope_theta},
         tie_word_embeddings=False, attention_bias=False, mlp_bias=False, attention_dropout=0.0,
+        pad_token_id=pad_token_id,
     )
     cfg._attn_implementation = "sdpa"
     model = LlamaForCausalLM(cfg).float()
@@ -103,6 +104,122 @@ def run_case(name, a: Arch, B: int, seed: int):
     np.savez_compressed(path, **fx)
     print(f"{name}: loss {loss.item():.6f} gnorm {gnorm:.6f} loss2 {out2.loss.item():.6f} -> {path} "
           f"({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+def run_trainer_case():
+    """The three places where round 1 deviated from the Trainer step, pinned by the real HF objects:
+    (1) num_items_in_batch counted on the UNSHIFTED labels (trainer.py:2136) and passed to the model,
+    (2) config.pad_token_id -> nn.Embedding(padding_idx) (the pad row gets no lookup gradient),
+    (3) weight_decay = 0.01 with Trainer's decay / no-decay groups (trainer.py:1280-1290,
+        trainer_pt_utils.get_parameter_names)."""
+    from transformers.trainer_pt_utils import get_parameter_names
+
+    a = Arch(256, 256, 384, 2, 2, 2, 128, 128, 1e-5, 10000.0, pad_token_id=3)
+    B, seed, wd = 2, 41, 0.5   # lr 1e-3 x wd 0.5: the decay is 5e-4 per step, well above the bf16 noise floor
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    params = seeded_params(a, seed)
+    rng = np.random.default_rng(seed + 1000)
+
+    def batch():
+        ids = rng.integers(0, a.vocab_size, size=(B, a.max_seq_len), dtype=np.int64)
+        ids[:, 5] = a.pad_token_id
+        ids[0, 77] = a.pad_token_id
+        labels = ids.copy()                    # packed plain text: every label counts, incl. position 0
+        labels[1, 30:41] = -100
+        return ids, labels
+
+    model = hf_model(a, params, pad_token_id=a.pad_token_id)
+    assert model.model.embed_tokens.padding_idx == a.pad_token_id
+    model.train()
+    named = dict(model.named_parameters())
+    forbidden = [r"bias", r"layernorm", r"rmsnorm", r"(?:^|\.)norm(?:$|\.)", r"_norm(?:$|\.)"]
+    decay_names = set(get_parameter_names(model, [torch.nn.LayerNorm], forbidden))
+    opt = torch.optim.AdamW([
+        {"params": [p for n, p in named.items() if n in decay_names], "weight_decay": wd},
+        {"params": [p for n, p in named.items() if n not in decay_names], "weight_decay": 0.0},
+    ], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    fx = dict(arch=np.array([a.vocab_size, a.hidden_size, a.intermediate_size, a.num_layers, a.num_heads,
+                             a.num_kv_heads, a.head_dim, a.max_seq_len], dtype=np.int64), lrs=np.array([1e-3, 5e-4]),
+              arch_f=np.array([a.rms_norm_eps, a.rope_theta], dtype=np.float64),
+              batch=np.array([B, seed], dtype=np.int64), pad_token_id=np.int64(a.pad_token_id),
+              weight_decay=np.float64(wd), no_decay=np.array(sorted(set(named) - decay_names)))
+    for step, lr in ((1, 1e-3), (2, 5e-4)):
+        ids, labels = batch()
+        n = torch.tensor(int((labels != -100).sum()))
+        out = model(input_ids=torch.tensor(ids), labels=torch.tensor(labels), num_items_in_batch=n)
+        out.loss.backward()
+        if step == 1:
+            grads = {k: p.grad.detach().clone() for k, p in named.items()}
+            fx["logits"] = out.logits.detach().numpy().astype(np.float32)
+        gnorm = float(torch.nn.utils.clip_grad_norm_(list(named.values()), 1.0))
+        for g in opt.param_groups:
+            g["lr"] = lr
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        sfx = "" if step == 1 else "2"
+        fx["ids" + sfx], fx["labels" + sfx] = ids, labels
+        fx["loss" + sfx], fx["gnorm" + sfx] = np.float32(out.loss.item()), np.float32(gnorm)
+        fx["num_items" + sfx] = np.int64(int(n))
+    for k in named:
+        fx["gradnorm/" + k] = np.float32(grads[k].norm().item())
+        fx["grad/" + k] = grads[k].flatten()[::SAMPLE_STRIDE].numpy().copy()
+        fx["param2/" + k] = named[k].detach().flatten()[::SAMPLE_STRIDE].numpy().copy()
+    fx["pad_row_grad"] = grads["model.embed_tokens.weight"][a.pad_token_id].numpy().copy()
+    path = os.path.join(OUT, "llama_tiny_trainer.npz")
+    np.savez_compressed(path, **fx)
+    print(f"llama_tiny_trainer: loss {float(fx['loss']):.6f} gnorm {float(fx['gnorm']):.6f} num_items {int(fx['num_items'])} "
+          f"no_decay {len(fx['no_decay'])} tensors -> {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+def run_falcon_7b_width():
+    """Config #4 at the TRUE Falcon-7B layer width (d 4544, 71 query heads + 1 kv head of 64, ffn 18176,
+    V 65024), 2 layers: the shapes the toy golden cannot reach -- 71 is not a multiple of the decode
+    attention's 8-head group, 4544 is not a multiple of 128, split-K runs at K = 18176. Prompt logits
+    (strided sample), greedy continuation and the fp32 top-2 margin of every generated step, from the
+    real FalconForCausalLM. Parameters are re-created from the seed by the test (710 M values)."""
+    from transformers import FalconConfig, FalconForCausalLM
+    from oracle import falcon_oracle as FO
+
+    a = FO.FalconArch(vocab_size=65024, hidden_size=4544, num_layers=2, num_heads=71, head_dim=64)
+    # one layer's std 0.12 random matrices at this width would saturate everything: scale as 1/sqrt(fan_in)
+    params = FO.seeded_params(a, 23, std=0.015)
+    cfg = FalconConfig(vocab_size=a.vocab_size, hidden_size=a.hidden_size, num_hidden_layers=a.num_layers,
+                       num_attention_heads=a.num_heads, multi_query=True, parallel_attn=True, bias=False,
+                       new_decoder_architecture=False, alibi=False, layer_norm_epsilon=1e-5,
+                       max_position_embeddings=2048, tie_word_embeddings=True, hidden_dropout=0.0,
+                       attention_dropout=0.0)
+    cfg._attn_implementation = "sdpa"
+    torch.set_num_threads(8)
+    model = FalconForCausalLM(cfg).float().eval()
+    sd = {k: torch.tensor(v) for k, v in params.items()}
+    sd["lm_head.weight"] = sd["transformer.word_embeddings.weight"]
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("rotary" in m or "inv_freq" in m for m in missing), (missing, unexpected)
+    rng = np.random.default_rng(78)
+    prompts = rng.integers(0, a.vocab_size, size=(3, 20), dtype=np.int64)
+    n_new = 8
+    with torch.no_grad():
+        logits = model(torch.tensor(prompts)).logits.numpy()
+        ids = torch.tensor(prompts)
+        gen, margins = [], []
+        for _ in range(n_new):
+            lg = model(ids).logits[:, -1]
+            top2 = torch.topk(lg, 2, dim=-1).values
+            margins.append((top2[:, 0] - top2[:, 1]).numpy())
+            nxt = lg.argmax(-1, keepdim=True)
+            gen.append(nxt.numpy())
+            ids = torch.cat([ids, nxt], dim=1)
+    gen = np.concatenate(gen, axis=1)
+    path = os.path.join(OUT, "falcon_7b_width.npz")
+    np.savez_compressed(path, arch=np.array([a.vocab_size, a.hidden_size, a.num_layers, a.num_heads, a.head_dim]),
+                        seed=np.int64(23), std=np.float64(0.015), prompts=prompts,
+                        logits_last=logits[:, -1, ::8].astype(np.float32), logits_stride=np.int64(8),
+                        logits_last_absmax=np.abs(logits[:, -1]).max(-1).astype(np.float32),
+                        logits_norm=np.linalg.norm(logits[:, -1].astype(np.float64), axis=-1),
+                        generated=gen, margins=np.stack(margins, 1).astype(np.float32))
+    print(f"falcon_7b_width -> {path} ({os.path.getsize(path) / 1024:.0f} KiB); generated[0] = {gen[0].tolist()} "
+          f"margins[0] = {np.stack(margins, 1)[0].round(3).tolist()}")
 
 
 def run_ops():
@@ -194,7 +311,7 @@ def run_opt():
     from transformers import OPTConfig, OPTForCausalLM
     from oracle import opt_oracle as OO
 
-    a = OO.OptArch(vocab_size=192, hidden_size=128, ffn_dim=256, num_layers=2, num_heads=2, max_position_embeddings=64)
+    a = OO.OptArch(vocab_size=192, hidden_size=128, ffn_dim=256, num_layers=2, num_heads=2, max_position_embeddings=128)
     params = OO.seeded_params(a, 31)
     cfg = OPTConfig(vocab_size=a.vocab_size, hidden_size=a.hidden_size, ffn_dim=a.ffn_dim, num_hidden_layers=a.num_layers,
                     num_attention_heads=a.num_heads, max_position_embeddings=a.max_position_embeddings,
@@ -209,18 +326,23 @@ def run_opt():
     assert not unexpected and not missing, (missing, unexpected)
     assert model.lm_head.weight.data_ptr() == model.model.decoder.embed_tokens.weight.data_ptr(), "head must be tied"
     rng = np.random.default_rng(32)
-    B, S = 2, 48
+    B, S = 2, 128   # the CUDA attention kernels take sequence lengths that are multiples of 128
 
     def batch():
         ids = rng.integers(0, a.vocab_size, size=(B, S)).astype(np.int64)
+        ids[0, 40] = ids[1, 7] = a.pad_token_id      # the pad row must get no lookup gradient
         labels = ids.copy()
         labels[0, :9] = -100
-        labels[1, 20:27] = -100
+        labels[1, 20:27] = -100                      # row 1 keeps its FIRST label: Trainer counts it
         return ids, labels
+
+    def n_items(lab):
+        """HF Trainer's num_items_in_batch (trainer.py:2136): non-ignored UNSHIFTED labels."""
+        return torch.tensor(int((lab != -100).sum()))
 
     ids, labels = batch()
     model.train()
-    out = model(input_ids=torch.tensor(ids), labels=torch.tensor(labels))
+    out = model(input_ids=torch.tensor(ids), labels=torch.tensor(labels), num_items_in_batch=n_items(labels))
     out.loss.backward()
     named = dict(model.named_parameters())          # tied weight appears once
     grads = {k: p.grad.detach().clone() for k, p in named.items()}
@@ -229,7 +351,7 @@ def run_opt():
     opt.step()
     opt.zero_grad(set_to_none=True)
     ids2, labels2 = batch()
-    out2 = model(input_ids=torch.tensor(ids2), labels=torch.tensor(labels2))
+    out2 = model(input_ids=torch.tensor(ids2), labels=torch.tensor(labels2), num_items_in_batch=n_items(labels2))
     out2.loss.backward()
     gnorm2 = float(torch.nn.utils.clip_grad_norm_(list(named.values()), 1.0))
     for g in opt.param_groups:
@@ -261,8 +383,15 @@ if __name__ == "__main__":
     if "--opt-only" in sys.argv:
         run_opt()
         sys.exit(0)
+    if "--round2" in sys.argv:     # the fixtures added in round 2 (the others are unchanged)
+        run_opt()
+        run_trainer_case()
+        run_falcon_7b_width()
+        sys.exit(0)
     run_ops()
     run_falcon()
     run_opt()
+    run_trainer_case()
+    run_falcon_7b_width()
     for name, (a, B, seed) in CASES.items():
         run_case(name, a, B, seed)

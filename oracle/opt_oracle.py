@@ -29,7 +29,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .llama_oracle import adamw_update, bf16_round, causal_lm_loss, clip_grad_norm
+from .llama_oracle import adamw_update, bf16_round, causal_lm_loss, clip_grad_norm, decays, trainer_num_items
 
 POS_OFFSET = 2  # modeling_opt.py:53
 
@@ -133,12 +133,14 @@ def forward(P: Dict[str, torch.Tensor], ids: torch.Tensor, a: OptArch) -> torch.
     return F.linear(h, P["model.decoder.embed_tokens.weight"])                          # tied head, no bias
 
 
-def train_step(params_np, ids, labels, a: OptArch, lr=5e-5, max_grad_norm=1.0, state=None, step=1):
+def train_step(params_np, ids, labels, a: OptArch, lr=5e-5, max_grad_norm=1.0, state=None, step=1,
+               weight_decay=0.0):
     """fwd, HF causal-LM loss, bwd (the tied table receives embedding + head gradients through
     autograd), global-norm clip, AdamW. Same return layout as llama_oracle.train_step."""
     P = {k: torch.tensor(v, dtype=torch.float32, requires_grad=True) for k, v in params_np.items()}
     logits = forward(P, torch.as_tensor(ids, dtype=torch.int64), a)
-    loss, nll = causal_lm_loss(logits, torch.as_tensor(labels, dtype=torch.int64))
+    lab = torch.as_tensor(labels, dtype=torch.int64)
+    loss, nll = causal_lm_loss(logits, lab, trainer_num_items(lab))   # HF Trainer's normaliser
     loss.backward()
     grads = {k: p.grad.detach() for k, p in P.items()}
     gnorm, coef = clip_grad_norm(grads, max_grad_norm)
@@ -146,7 +148,8 @@ def train_step(params_np, ids, labels, a: OptArch, lr=5e-5, max_grad_norm=1.0, s
     for k, p in P.items():
         m0 = torch.zeros_like(p) if state is None else torch.as_tensor(state["m"][k])
         v0 = torch.zeros_like(p) if state is None else torch.as_tensor(state["v"][k])
-        pn, mn, vn = adamw_update(p.detach(), grads[k] * coef, m0, v0, step, lr)
+        pn, mn, vn = adamw_update(p.detach(), grads[k] * coef, m0, v0, step, lr,
+                                  wd=weight_decay if decays(k) else 0.0)
         new_p[k], new_m[k], new_v[k] = pn.numpy(), mn.numpy(), vn.numpy()
     return dict(loss=float(loss.detach()), gnorm=gnorm, logits=logits.detach().numpy(), nll=nll.detach().numpy(),
                 grads={k: g.numpy() for k, g in grads.items()}, params=new_p, m=new_m, v=new_v)

@@ -19,6 +19,7 @@ i64p = C.POINTER(C.c_int64)
 vp = C.c_void_p
 
 BF16, F32, I32 = 0, 1, 2
+ABI_VERSION = 2  # include/b200w.h B200W_ABI_VERSION
 
 
 class Arch(C.Structure):
@@ -26,7 +27,8 @@ class Arch(C.Structure):
         ("vocab_size", C.c_int32), ("hidden_size", C.c_int32), ("intermediate_size", C.c_int32),
         ("num_layers", C.c_int32), ("num_heads", C.c_int32), ("num_kv_heads", C.c_int32),
         ("head_dim", C.c_int32), ("max_seq_len", C.c_int32), ("rms_norm_eps", C.c_float),
-        ("rope_theta", C.c_float),
+        ("rope_theta", C.c_float), ("family", C.c_int32), ("pad_token_id", C.c_int32),
+        ("max_positions", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -36,6 +38,7 @@ class InferArch(C.Structure):
         ("intermediate_size", C.c_int32), ("num_layers", C.c_int32), ("num_heads", C.c_int32),
         ("num_kv_heads", C.c_int32), ("head_dim", C.c_int32), ("max_ctx", C.c_int32),
         ("norm_eps", C.c_float), ("rope_theta", C.c_float), ("tie_embeddings", C.c_int32),
+        ("max_positions", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -82,8 +85,14 @@ PROTOTYPES = {
     "b200w_op_gemm": (C.c_int, [c_ctx, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "b200w_op_gemm_decode": (C.c_int, [c_ctx, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]),
-    "b200w_op_embed_fwd": (C.c_int, [c_ctx, vp, vp, vp, C.c_int, C.c_int, C.c_int]),
-    "b200w_op_embed_bwd": (C.c_int, [c_ctx, vp, vp, vp, C.c_int, C.c_int, C.c_int]),
+    "b200w_op_embed_fwd": (C.c_int, [c_ctx, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "b200w_op_embed_bwd": (C.c_int, [c_ctx, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int]),
+    "b200w_op_layernorm_fwd": (C.c_int, [c_ctx, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_float]),
+    "b200w_op_layernorm_bwd": (C.c_int, [c_ctx, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]),
+    "b200w_op_bias_act": (C.c_int, [c_ctx, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "b200w_op_relu_bwd": (C.c_int, [c_ctx, vp, vp, vp, C.c_int64]),
+    "b200w_op_colsum": (C.c_int, [c_ctx, vp, vp, C.c_int, C.c_int, C.c_int]),
     "b200w_op_rmsnorm_fwd": (C.c_int, [c_ctx, vp, vp, vp, vp, C.c_int, C.c_int, C.c_float]),
     "b200w_op_rmsnorm_bwd": (C.c_int, [c_ctx, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]),
     "b200w_op_rope": (C.c_int, [c_ctx, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
@@ -95,9 +104,9 @@ PROTOTYPES = {
                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
     "b200w_op_attention_bwd": (C.c_int, [c_ctx, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp,
                                          vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
-    "b200w_op_adamw": (C.c_int, [c_ctx, vp, vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float,
+    "b200w_op_adamw": (C.c_int, [c_ctx, vp, vp, vp, vp, C.c_int, vp, C.c_int64, C.c_float, C.c_float,
                                  C.c_float, C.c_float, C.c_float, C.c_int, C.c_float]),
-    "b200w_op_grad_norm": (C.c_int, [c_ctx, vp, C.c_int64, f32p]),
+    "b200w_op_grad_norm": (C.c_int, [c_ctx, vp, C.c_int, C.c_int64, f32p]),
     "b200w_op_poison_onchip": (C.c_int, [c_ctx, C.c_uint32]),
 }
 
@@ -124,7 +133,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.b200w_abi_version() != 1:
+    if lib.b200w_abi_version() != ABI_VERSION:
         raise ImportError("libb200w.so ABI version mismatch")
     _lib = lib
     return lib

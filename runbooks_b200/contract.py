@@ -246,44 +246,75 @@ def iter_safetensors(model_dir: str) -> Iterator[Tuple[str, np.ndarray]]:
                     yield name, t.float().contiguous().numpy()
 
 
+def canonical_tensor_name(name: str, hf_config: dict) -> str:
+    """Checkpoint key -> the key of the *ForCausalLM state dict. OPT checkpoints saved from the bare
+    OPTModel (and the original metaseq conversions) lack the leading "model."."""
+    if hf_config.get("model_type") == "opt" and name.startswith("decoder."):
+        return "model." + name
+    return name
+
+
+def is_ignorable_tensor(name: str, hf_config: dict) -> bool:
+    """Tensors a checkpoint may hold that carry no trainable arithmetic: rotary inv_freq buffers, and
+    the duplicate lm_head.weight of a tied model."""
+    if name.endswith("rotary_emb.inv_freq"):
+        return True
+    tied = hf_config.get("tie_word_embeddings", hf_config.get("model_type") in ("opt", "falcon"))
+    return bool(tied) and name == "lm_head.weight"
+
+
 MAX_SHARD_BYTES = 5 * 1000 ** 3  # save_pretrained's default max_shard_size="5GB"
 
 
+def plan_shards(sizes: Dict[str, int]) -> List[List[str]]:
+    """save_pretrained's greedy sharding over the tensors in order: a new shard starts when the next
+    tensor would take the current one past MAX_SHARD_BYTES."""
+    shards: List[List[str]] = [[]]
+    cur = 0
+    for name, nbytes in sizes.items():
+        if cur and cur + nbytes > MAX_SHARD_BYTES:
+            shards.append([])
+            cur = 0
+        shards[-1].append(name)
+        cur += nbytes
+    return shards
+
+
 def save_hf_checkpoint(out_dir: str, hf_config: dict, tensors: Iterable[Tuple[str, np.ndarray]],
-                       copy_from: Optional[str] = None) -> List[str]:
+                       copy_from: Optional[str] = None, sizes: Optional[Dict[str, int]] = None) -> List[str]:
     """Writes config.json + bf16 safetensors shards (+ model.safetensors.index.json when there is
     more than one) in the layout `save_pretrained` produces, so that the Server the controller
     later points at this directory (server_controller.go:184-193) — or AutoModelForCausalLM —
-    can load it. `tensors` yields (name, uint16 bf16-bit array). Tokenizer files are copied
-    through from the base model directory."""
+    can load it. `tensors` yields (name, uint16 bf16-bit array) in the order of `sizes` (name ->
+    bytes); with `sizes` every shard is written as soon as its last tensor has arrived, so at most
+    one 5 GB shard is resident on the host. Tokenizer files are copied through from the base
+    model directory."""
     import torch
     from safetensors.torch import save_file
 
     os.makedirs(out_dir, exist_ok=True)
-    shards: List[Dict[str, "torch.Tensor"]] = [{}]
-    sizes = [0]
-    for name, arr in tensors:
-        assert arr.dtype == np.uint16, "checkpoints are written in bf16"
-        t = torch.from_numpy(np.ascontiguousarray(arr)).view(torch.bfloat16)
-        nbytes = t.numel() * 2
-        if sizes[-1] and sizes[-1] + nbytes > MAX_SHARD_BYTES:
-            shards.append({})
-            sizes.append(0)
-        shards[-1][name] = t
-        sizes[-1] += nbytes
-    written = []
-    if len(shards) == 1:
-        save_file(shards[0], os.path.join(out_dir, "model.safetensors"), metadata={"format": "pt"})
-        written.append("model.safetensors")
-    else:
-        weight_map = {}
-        for i, sh in enumerate(shards):
-            fn = f"model-{i + 1:05d}-of-{len(shards):05d}.safetensors"
-            save_file(sh, os.path.join(out_dir, fn), metadata={"format": "pt"})
-            written.append(fn)
-            weight_map.update({k: fn for k in sh})
+    if sizes is None:
+        tensors = list(tensors)
+        sizes = {n: a.size * 2 for n, a in tensors}
+    plan = plan_shards(sizes)
+    written: List[str] = []
+    weight_map: Dict[str, str] = {}
+    it = iter(tensors)
+    for i, names in enumerate(plan):
+        shard: Dict[str, "torch.Tensor"] = {}
+        for want in names:
+            name, arr = next(it)
+            assert name == want, f"tensor order differs from the shard plan: {name} != {want}"
+            assert arr.dtype == np.uint16, "checkpoints are written in bf16"
+            shard[name] = torch.from_numpy(np.ascontiguousarray(arr)).view(torch.bfloat16)
+        fn = "model.safetensors" if len(plan) == 1 else f"model-{i + 1:05d}-of-{len(plan):05d}.safetensors"
+        save_file(shard, os.path.join(out_dir, fn), metadata={"format": "pt"})
+        written.append(fn)
+        weight_map.update({k: fn for k in shard})
+        del shard
+    if len(plan) > 1:
         with open(os.path.join(out_dir, "model.safetensors.index.json"), "w") as f:
-            json.dump({"metadata": {"total_size": int(sum(sizes))}, "weight_map": weight_map}, f, indent=2)
+            json.dump({"metadata": {"total_size": int(sum(sizes.values()))}, "weight_map": weight_map}, f, indent=2)
     cfg = dict(hf_config)
     cfg["torch_dtype"] = "bfloat16"
     with open(os.path.join(out_dir, "config.json"), "w") as f:

@@ -893,11 +893,8 @@ void attention_fwd(const void* qkv, int ld_qkv, int k_off, int v_off, void* out,
   B200W_CHECK(H % Hkv == 0 && ld_out % 8 == 0, "bad head configuration");
   const size_t T = static_cast<size_t>(B) * S;
   CUtensorMap tm = make_tmap_bf16_2d(qkv, T, ld_qkv, ld_qkv, 64, 64);
-  static bool attr = false;
-  if (!attr) {
-    set_smem(attn_fwd_kernel, FWD_SMEM);
-    attr = true;
-  }
+  static PerDeviceOnce once;
+  once.run([&] { set_smem(attn_fwd_kernel, FWD_SMEM); });
   const int grid = (S / FWD_BQ) * B * H;
   const float scale_log2 = scale * 1.4426950408889634f;
   attn_fwd_kernel<<<grid, NTHREADS, FWD_SMEM, s>>>(tm, static_cast<bf16*>(out), ld_out, lse2, k_off,
@@ -915,12 +912,11 @@ void attention_bwd(const void* qkv, int ld_qkv, int k_off, int v_off, const void
   attn_bwd_delta(out, dout, ld_out, delta, static_cast<int>(T), H, s);
   CUtensorMap tm_qkv = make_tmap_bf16_2d(qkv, T, ld_qkv, ld_qkv, 64, 64);
   CUtensorMap tm_do = make_tmap_bf16_2d(dout, T, ld_out, ld_out, 64, 64);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce once;
+  once.run([&] {
     set_smem(attn_bwd_dkdv_kernel, KV_SMEM);
     set_smem(attn_bwd_dq_kernel, DQ_SMEM);
-    attr = true;
-  }
+  });
   const float scale_log2 = scale * 1.4426950408889634f;
   attn_bwd_dkdv_kernel<<<(S / BWD_BKV) * B * Hkv, BWD_NTHREADS, KV_SMEM, s>>>(
       tm_qkv, tm_do, lse2, delta, static_cast<bf16*>(dqkv), ld_qkv, k_off, v_off, B, S, H, Hkv, scale,

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -38,7 +39,7 @@ struct NcclApi {
   int (*CommAbort)(void*) = nullptr;  // optional
   const char* (*GetErrorString)(int) = nullptr;
 };
-constexpr int kNcclInt64 = 4, kNcclFloat32 = 7, kNcclSum = 0;
+constexpr int kNcclInt64 = 4, kNcclFloat32 = 7, kNcclBfloat16 = 9, kNcclSum = 0;
 
 NcclApi& nccl() {
   static NcclApi api;
@@ -74,10 +75,63 @@ std::string g_create_error;
 
 struct Param {
   std::string name;
-  int64_t rows, cols;
-  size_t off;  // element offset into the flat parameter space
-  bool is_norm;
+  int64_t rows, cols;    // shape of the HF tensor (what load_tensor / read_tensor exchange)
+  int64_t irows, icols;  // shape on the device: equal, or with every head padded from dh to dhp
+  size_t off;            // element offset into the flat parameter space
+  bool is_norm;          // 1-D "ones" parameter (norm weight)
+  bool is_zero_init;     // 1-D parameter HF initialises to zero (biases)
+  bool decay;            // HF Trainer applies weight decay (trainer.py get_decay_parameter_names)
+  int pad;               // 0 dense; 1 rows are heads of `dh` padded to `dhp`; 2 columns are
+  size_t isize() const { return static_cast<size_t>(irows) * icols; }
 };
+
+// dst (internal, padded) <-> src (dense HF layout). Heads of dh elements sit at stride dhp along
+// rows (pad == 1) or columns (pad == 2); the padding itself is never written here (it is zero from
+// the memset at allocation and stays zero: every gradient that reaches it is exactly zero, see
+// DESIGN.md 3.6).
+__global__ void pad_scatter_kernel(const float* __restrict__ src, float* master, bf16* w, int64_t rows,
+                                   int64_t cols, int64_t icols, int pad, int dh, int dhp) {
+  const int64_t n = rows * cols;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols, c = i % cols;
+    const int64_t ir = pad == 1 ? (r / dh) * dhp + r % dh : r;
+    const int64_t ic = pad == 2 ? (c / dh) * dhp + c % dh : c;
+    const float v = src[i];
+    if (master) master[ir * icols + ic] = v;
+    w[ir * icols + ic] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void pad_gather_kernel(const float* srcf, const bf16* srcb, float* __restrict__ dst,
+                                  int64_t rows, int64_t cols, int64_t icols, int pad, int dh, int dhp) {
+  const int64_t n = rows * cols;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols, c = i % cols;
+    const int64_t ir = pad == 1 ? (r / dh) * dhp + r % dh : r;
+    const int64_t ic = pad == 2 ? (c / dh) * dhp + c % dh : c;
+    dst[i] = srcf ? srcf[ir * icols + ic] : __bfloat162float(srcb[ir * icols + ic]);
+  }
+}
+// zero everything outside the real head dimensions of a padded parameter (after a random init)
+__global__ void pad_zero_kernel(float* master, bf16* w, int64_t irows, int64_t icols, int pad, int dh,
+                                int dhp) {
+  const int64_t n = irows * icols;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / icols, c = i % icols;
+    const bool is_pad = pad == 1 ? (r % dhp) >= dh : (c % dhp) >= dh;
+    if (is_pad) {
+      if (master) master[i] = 0.f;
+      w[i] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+// inv_n[0] = 1 / count (0 when the count is 0): the loss normaliser, kept on the device
+__global__ void set_count_kernel(long long* cnt, long long v) { cnt[0] = v; }
+__global__ void inv_count_kernel(const long long* cnt, float* inv_n) {
+  inv_n[0] = cnt[0] > 0 ? 1.f / static_cast<float>(cnt[0]) : 0.f;
+}
 
 __global__ void init_normal_kernel(float* master, bf16* w, size_t n, uint64_t seed, float std) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -144,26 +198,30 @@ struct b200w_ctx {
   b200w_hparams hp{};
   int micro_batch = 0;
   int step = 0;
+  int dhp = 128;   // head dimension on the device (head_dim 64 is stored zero-padded to 128)
   std::vector<Param> params;
   std::unordered_map<std::string, int> index;
   size_t n_elems = 0;       // all parameters
-  size_t n_zero_prefix = 0; // embed + norm weights: gradients accumulated with atomics
+  size_t n_zero_prefix = 0; // embeddings + 1-D parameters: gradients accumulated, cleared per step
+  struct Seg { size_t off, n; bool decay; };
+  std::vector<Seg> segs;    // contiguous ranges of equal weight-decay policy, in offset order
   bf16* w = nullptr;
   float *master = nullptr, *m = nullptr, *v = nullptr, *g = nullptr;
+  bf16* gw = nullptr;       // bf16 wire copy of the gradients (data parallel only)
   float2* rope_tab = nullptr;
 
-  struct LayerP { size_t ln1, ln2, wqkv, wo, wgu, wd; };
+  struct LayerP { size_t ln1, ln1b, ln2, ln2b, wqkv, bqkv, wo, bo, wgu, b1, wd, b2; };
   std::vector<LayerP> lp;
-  size_t p_embed = 0, p_norm = 0, p_lm = 0;
+  size_t p_embed = 0, p_pos = 0, p_norm = 0, p_normb = 0, p_lm = 0;
 
   // ---- activations for one micro-batch ----
   struct LayerA {
     bf16 *h_in, *n1, *qkv, *attn, *h_mid, *n2, *gu, *act;
-    float *rstd1, *rstd2, *lse;
+    float *rstd1, *rstd2, *mean1, *mean2, *lse;
   };
   std::vector<LayerA> la;
   bf16 *h_final = nullptr, *nf = nullptr, *logits = nullptr;
-  float *rstdf = nullptr, *nll = nullptr;
+  float *rstdf = nullptr, *meanf = nullptr, *nll = nullptr;
   int32_t *ids_dev = nullptr, *labels_dev = nullptr, *targets = nullptr;
   size_t ids_cap = 0;
   int32_t* pinned = nullptr;
@@ -172,9 +230,10 @@ struct b200w_ctx {
        *dattn = nullptr, *dqkv = nullptr;
   float *delta = nullptr, *dw_partial = nullptr;
   float* scal = nullptr;    // [0] loss, [1] gscale, [2] gnorm
-  long long* cnt_dev = nullptr;  // valid-target count, summed over the ranks (HF num_items_in_batch)
+  float* inv_n = nullptr;   // 1 / (global) target count of the running step
+  long long* cnt_dev = nullptr;  // target count, summed over the ranks (HF num_items_in_batch)
   double* sumsq = nullptr;
-  float* host_scal = nullptr;  // pinned [4]
+  float* host_scal = nullptr;  // pinned [8]
   float* hook_scal = nullptr;
 
   // ---- timing / profiling (bench.py) ----
@@ -191,6 +250,7 @@ struct b200w_ctx {
   // ---- DP ----
   void* comm = nullptr;
   int rank = 0, nranks = 1;
+  int ar_sm_reserve = 0;  // SMs the GEMMs leave to NCCL while the all-reduce overlaps the backward
   bool poisoned = false;  // a CUDA / NCCL call failed: the context (and any collective) is dead
   cudaEvent_t ev_grad = nullptr, ev_comm = nullptr;
 
@@ -207,6 +267,14 @@ struct b200w_ctx {
     dev_bytes += static_cast<int64_t>(bytes);
     return static_cast<T*>(p);
   }
+  void release(void* p) {
+    for (size_t i = 0; i < allocs.size(); ++i)
+      if (allocs[i] == p) {
+        cudaFree(p);
+        allocs.erase(allocs.begin() + i);
+        return;
+      }
+  }
   void free_all() {
     for (void* p : allocs) cudaFree(p);
     allocs.clear();
@@ -216,7 +284,11 @@ struct b200w_ctx {
 
 namespace {
 
-int qkv_dim(const b200w_arch& a) { return (a.num_heads + 2 * a.num_kv_heads) * a.head_dim; }
+bool is_opt(const b200w_arch& a) { return a.family == B200W_FAMILY_OPT; }
+int qd_of(const b200w_ctx* c) { return c->arch.num_heads * c->dhp; }
+int kd_of(const b200w_ctx* c) { return c->arch.num_kv_heads * c->dhp; }
+int qkv_dim(const b200w_ctx* c) { return qd_of(c) + 2 * kd_of(c); }
+constexpr int OPT_POS_OFFSET = 2;  // HF models/opt/modeling_opt.py:53
 
 // device scalar scratch for the per-kernel hooks (exists without a model)
 float* ctx_scal(b200w_ctx* c) {
@@ -249,50 +321,117 @@ int guarded(b200w_ctx* ctx, F&& f) {
   }
 }
 
-void add_param(b200w_ctx* c, const std::string& name, int64_t rows, int64_t cols, bool is_norm,
-               size_t* off_out) {
-  Param p{name, rows, cols, c->n_elems, is_norm};
+// kind: 'm' matrix (decayed), 'n' norm weight (ones, no decay), 'b' bias / LayerNorm bias (zeros, no
+// decay). pad: see Param. HF Trainer's decay rule (trainer.py:1280-1290): everything except
+// nn.LayerNorm parameters and names matching bias / layernorm / rmsnorm / norm.
+void add_param(b200w_ctx* c, const std::string& name, int64_t rows, int64_t cols, char kind, size_t* off_out,
+               int pad = 0) {
+  const int dh = c->arch.head_dim, dhp = c->dhp;
+  Param p{};
+  p.name = name;
+  p.rows = rows;
+  p.cols = cols;
+  p.irows = pad == 1 ? rows / dh * dhp : rows;
+  p.icols = pad == 2 ? cols / dh * dhp : cols;
+  p.off = c->n_elems;
+  p.is_norm = kind == 'n';
+  p.is_zero_init = kind == 'b';
+  p.decay = kind == 'm';
+  p.pad = dhp == dh ? 0 : pad;
   *off_out = c->n_elems;
   c->index[name] = static_cast<int>(c->params.size());
   c->params.push_back(p);
-  c->n_elems += static_cast<size_t>(rows) * cols;
+  c->n_elems += p.isize();
 }
 
-void build_params(b200w_ctx* c) {
+void build_segments(b200w_ctx* c) {
+  c->segs.clear();
+  for (const Param& p : c->params) {
+    if (!c->segs.empty() && c->segs.back().decay == p.decay && c->segs.back().off + c->segs.back().n == p.off)
+      c->segs.back().n += p.isize();
+    else
+      c->segs.push_back({p.off, p.isize(), p.decay});
+  }
+}
+
+void build_params_llama(b200w_ctx* c) {
   const b200w_arch& a = c->arch;
   const int d = a.hidden_size, f = a.intermediate_size, L = a.num_layers;
   const int qd = a.num_heads * a.head_dim, kd = a.num_kv_heads * a.head_dim;
-  c->lp.resize(L);
+  c->lp.assign(L, {});
   // atomically-accumulated gradients first, so one memset clears them
-  add_param(c, "model.embed_tokens.weight", a.vocab_size, d, false, &c->p_embed);
+  add_param(c, "model.embed_tokens.weight", a.vocab_size, d, 'm', &c->p_embed);
   for (int l = 0; l < L; ++l) {
     const std::string pre = "model.layers." + std::to_string(l) + ".";
-    add_param(c, pre + "input_layernorm.weight", 1, d, true, &c->lp[l].ln1);
-    add_param(c, pre + "post_attention_layernorm.weight", 1, d, true, &c->lp[l].ln2);
+    add_param(c, pre + "input_layernorm.weight", 1, d, 'n', &c->lp[l].ln1);
+    add_param(c, pre + "post_attention_layernorm.weight", 1, d, 'n', &c->lp[l].ln2);
   }
-  add_param(c, "model.norm.weight", 1, d, true, &c->p_norm);
+  add_param(c, "model.norm.weight", 1, d, 'n', &c->p_norm);
   c->n_zero_prefix = c->n_elems;
   size_t dummy;
   for (int l = 0; l < L; ++l) {
     const std::string pre = "model.layers." + std::to_string(l) + ".";
     // q, k, v rows are contiguous: together they are the fused [qkv_dim, d] projection
-    add_param(c, pre + "self_attn.q_proj.weight", qd, d, false, &c->lp[l].wqkv);
-    add_param(c, pre + "self_attn.k_proj.weight", kd, d, false, &dummy);
-    add_param(c, pre + "self_attn.v_proj.weight", kd, d, false, &dummy);
-    add_param(c, pre + "self_attn.o_proj.weight", d, qd, false, &c->lp[l].wo);
+    add_param(c, pre + "self_attn.q_proj.weight", qd, d, 'm', &c->lp[l].wqkv);
+    add_param(c, pre + "self_attn.k_proj.weight", kd, d, 'm', &dummy);
+    add_param(c, pre + "self_attn.v_proj.weight", kd, d, 'm', &dummy);
+    add_param(c, pre + "self_attn.o_proj.weight", d, qd, 'm', &c->lp[l].wo);
     // gate, up contiguous: the fused [2f, d] projection
-    add_param(c, pre + "mlp.gate_proj.weight", f, d, false, &c->lp[l].wgu);
-    add_param(c, pre + "mlp.up_proj.weight", f, d, false, &dummy);
-    add_param(c, pre + "mlp.down_proj.weight", d, f, false, &c->lp[l].wd);
+    add_param(c, pre + "mlp.gate_proj.weight", f, d, 'm', &c->lp[l].wgu);
+    add_param(c, pre + "mlp.up_proj.weight", f, d, 'm', &dummy);
+    add_param(c, pre + "mlp.down_proj.weight", d, f, 'm', &c->lp[l].wd);
   }
-  add_param(c, "lm_head.weight", a.vocab_size, d, false, &c->p_lm);
+  add_param(c, "lm_head.weight", a.vocab_size, d, 'm', &c->p_lm);
+}
+
+// OPT-125m layout (HF models/opt/modeling_opt.py; checkpoint keys of OPTForCausalLM). The tied
+// lm_head is the embedding matrix itself (no separate parameter). q/k/v rows, their biases and the
+// out_proj columns are stored with every 64-wide head padded to 128 (Param::pad).
+void build_params_opt(b200w_ctx* c) {
+  const b200w_arch& a = c->arch;
+  const int d = a.hidden_size, f = a.intermediate_size, L = a.num_layers;
+  const int qd = a.num_heads * a.head_dim;
+  c->lp.assign(L, {});
+  const std::string dec = "model.decoder.";
+  add_param(c, dec + "embed_tokens.weight", a.vocab_size, d, 'm', &c->p_embed);
+  add_param(c, dec + "embed_positions.weight", a.max_positions + OPT_POS_OFFSET, d, 'm', &c->p_pos);
+  size_t dummy;
+  for (int l = 0; l < L; ++l) {
+    const std::string pre = dec + "layers." + std::to_string(l) + ".";
+    auto& p = c->lp[l];
+    add_param(c, pre + "self_attn_layer_norm.weight", 1, d, 'n', &p.ln1);
+    add_param(c, pre + "self_attn_layer_norm.bias", 1, d, 'b', &p.ln1b);
+    add_param(c, pre + "final_layer_norm.weight", 1, d, 'n', &p.ln2);
+    add_param(c, pre + "final_layer_norm.bias", 1, d, 'b', &p.ln2b);
+    add_param(c, pre + "self_attn.q_proj.bias", qd, 1, 'b', &p.bqkv, 1);
+    add_param(c, pre + "self_attn.k_proj.bias", qd, 1, 'b', &dummy, 1);
+    add_param(c, pre + "self_attn.v_proj.bias", qd, 1, 'b', &dummy, 1);
+    add_param(c, pre + "self_attn.out_proj.bias", 1, d, 'b', &p.bo);
+    add_param(c, pre + "fc1.bias", 1, f, 'b', &p.b1);
+    add_param(c, pre + "fc2.bias", 1, d, 'b', &p.b2);
+  }
+  add_param(c, dec + "final_layer_norm.weight", 1, d, 'n', &c->p_norm);
+  add_param(c, dec + "final_layer_norm.bias", 1, d, 'b', &c->p_normb);
+  c->n_zero_prefix = c->n_elems;
+  for (int l = 0; l < L; ++l) {
+    const std::string pre = dec + "layers." + std::to_string(l) + ".";
+    auto& p = c->lp[l];
+    add_param(c, pre + "self_attn.q_proj.weight", qd, d, 'm', &p.wqkv, 1);
+    add_param(c, pre + "self_attn.k_proj.weight", qd, d, 'm', &dummy, 1);
+    add_param(c, pre + "self_attn.v_proj.weight", qd, d, 'm', &dummy, 1);
+    add_param(c, pre + "self_attn.out_proj.weight", d, qd, 'm', &p.wo, 2);
+    add_param(c, pre + "fc1.weight", f, d, 'm', &p.wgu);
+    add_param(c, pre + "fc2.weight", d, f, 'm', &p.wd);
+  }
+  c->p_lm = c->p_embed;  // tied
 }
 
 void alloc_activations(b200w_ctx* c) {
   const b200w_arch& a = c->arch;
+  const bool opt = is_opt(a);
   const size_t T = static_cast<size_t>(c->micro_batch) * a.max_seq_len;
-  const size_t d = a.hidden_size, f = a.intermediate_size, qd = a.num_heads * a.head_dim,
-               qkvd = qkv_dim(a), H = a.num_heads;
+  const size_t d = a.hidden_size, f = a.intermediate_size, qd = qd_of(c), qkvd = qkv_dim(c),
+               H = a.num_heads;
   const int L = a.num_layers;
   c->la.resize(L);
   const int Lsave = c->training ? L : 1;  // forward-only: every layer reuses one set
@@ -305,26 +444,26 @@ void alloc_activations(b200w_ctx* c) {
       x.attn = c->alloc<bf16>(T * qd);
       x.h_mid = c->alloc<bf16>(T * d);
       x.n2 = c->alloc<bf16>(T * d);
-      x.gu = c->alloc<bf16>(T * 2 * f);
+      x.gu = opt ? nullptr : c->alloc<bf16>(T * 2 * f);
       x.act = c->alloc<bf16>(T * f);
       x.rstd1 = c->alloc<float>(T);
       x.rstd2 = c->alloc<float>(T);
+      x.mean1 = opt ? c->alloc<float>(T) : nullptr;
+      x.mean2 = opt ? c->alloc<float>(T) : nullptr;
       x.lse = c->alloc<float>(H * T);
     } else {
       c->la[l] = c->la[0];
     }
   }
   c->h_final = c->alloc<bf16>(T * d);
-  if (!c->training) {
-    // forward-only ping-pong: layer l reads h_in, writes the next layer's h_in
-    // (la[0].h_in and h_final alternate)
-  }
   c->nf = c->alloc<bf16>(T * d);
   c->rstdf = c->alloc<float>(T);
+  if (opt) c->meanf = c->alloc<float>(T);
   c->logits = c->alloc<bf16>(T * a.vocab_size);
   c->nll = c->alloc<float>(T);
   c->targets = c->alloc<int32_t>(T);
   c->scal = c->alloc<float>(8);
+  c->inv_n = c->alloc<float>(1);
   c->cnt_dev = c->alloc<long long>(1);
   c->sumsq = c->alloc<double>(1);
   if (c->training) {
@@ -332,14 +471,23 @@ void alloc_activations(b200w_ctx* c) {
     c->dh_b = c->alloc<bf16>(T * d);
     c->dn = c->alloc<bf16>(T * d);
     c->dact = c->alloc<bf16>(T * f);
-    c->dgu = c->alloc<bf16>(T * 2 * f);
+    if (!opt) c->dgu = c->alloc<bf16>(T * 2 * f);
     c->dattn = c->alloc<bf16>(T * qd);
     c->dqkv = c->alloc<bf16>(T * qkvd);
     c->delta = c->alloc<float>(H * T);
-    c->dw_partial = c->alloc<float>(static_cast<size_t>(rmsnorm_bwd_blocks(static_cast<int>(T))) * d);
+    // norm backward partials [blocks, d] (RMSNorm) or [blocks, 2 d] (LayerNorm); bias column sums
+    // [colsum_blocks, widest projection]
+    size_t part = static_cast<size_t>(rmsnorm_bwd_blocks(static_cast<int>(T))) * d * (opt ? 2 : 1);
+    if (opt) {
+      const size_t widest = std::max<size_t>({qkvd, f, d});
+      part = std::max(part, static_cast<size_t>(colsum_blocks(static_cast<int>(T))) * widest);
+    }
+    c->dw_partial = c->alloc<float>(part);
   }
-  c->rope_tab = c->alloc<float2>(static_cast<size_t>(a.max_seq_len) * (a.head_dim / 2));
-  rope_table(c->rope_tab, a.max_seq_len, a.head_dim, a.rope_theta, c->stream);
+  if (!opt) {
+    c->rope_tab = c->alloc<float2>(static_cast<size_t>(a.max_seq_len) * (a.head_dim / 2));
+    rope_table(c->rope_tab, a.max_seq_len, a.head_dim, a.rope_theta, c->stream);
+  }
 }
 
 // GEMM launch with optional CUDA-event bracketing (bench.py's roofline leg)
@@ -365,19 +513,19 @@ void egemm(b200w_ctx* c, const void* A, bool a_mn, int lda, const void* B, bool 
   }
 }
 
-// ---- forward of one micro-batch (ids already on device) -------------------------------------
-void forward_micro(b200w_ctx* c, const int32_t* ids, int nseq) {
+// ---- forward of one micro-batch (ids already on device): Llama family ------------------------
+void forward_micro_llama(b200w_ctx* c, const int32_t* ids, int nseq) {
   const b200w_arch& a = c->arch;
   const int S = a.max_seq_len, T = nseq * S, d = a.hidden_size, f = a.intermediate_size;
   const int H = a.num_heads, Hkv = a.num_kv_heads, dh = a.head_dim;
-  const int qd = H * dh, kd = Hkv * dh, qkvd = qkv_dim(a);
+  const int qd = H * dh, kd = Hkv * dh, qkvd = qkv_dim(c);
   const float scale = 1.f / sqrtf(static_cast<float>(dh));
   cudaStream_t s = c->stream;
   int64_t& n = c->launches;
   const int L = a.num_layers;
 
   bf16* h = c->la[0].h_in;
-  embed_fwd(ids, c->w + c->p_embed, h, T, d, a.vocab_size, s); ++n;
+  embed_fwd(ids, c->w + c->p_embed, nullptr, h, T, d, a.vocab_size, S, 0, s); ++n;
   for (int l = 0; l < L; ++l) {
     auto& x = c->la[l];
     const auto& p = c->lp[l];
@@ -402,46 +550,97 @@ void forward_micro(b200w_ctx* c, const int32_t* ids, int nseq) {
   if (c->training && h != c->h_final) throw Error("internal: residual stream bookkeeping");
 }
 
-// loss + dlogits (in place)
-void loss_micro(b200w_ctx* c, const int32_t* labels, int nseq, float inv_n) {
+// ---- OPT family (HF models/opt/modeling_opt.py OPTDecoder / OPTDecoderLayer, pre-LN) -----------
+// q is scaled by head_dim^-0.5 inside the attention kernel (HF scales q after q_proj and calls the
+// attention with scaling 1.0: the same product, and the factor 1/8 is exact in bf16).
+void forward_micro_opt(b200w_ctx* c, const int32_t* ids, int nseq) {
+  const b200w_arch& a = c->arch;
+  const int S = a.max_seq_len, T = nseq * S, d = a.hidden_size, f = a.intermediate_size;
+  const int H = a.num_heads, Hkv = a.num_kv_heads;
+  const int qd = qd_of(c), kd = kd_of(c), qkvd = qkv_dim(c);
+  const float scale = 1.f / sqrtf(static_cast<float>(a.head_dim));
+  const float eps = a.rms_norm_eps;
+  cudaStream_t s = c->stream;
+  int64_t& n = c->launches;
+  const int L = a.num_layers;
+
+  bf16* h = c->la[0].h_in;
+  embed_fwd(ids, c->w + c->p_embed, c->w + c->p_pos, h, T, d, a.vocab_size, S, OPT_POS_OFFSET, s); ++n;
+  for (int l = 0; l < L; ++l) {
+    auto& x = c->la[l];
+    const auto& p = c->lp[l];
+    bf16* h_in = c->training ? x.h_in : h;
+    bf16* h_next = c->training ? (l + 1 < L ? c->la[l + 1].h_in : c->h_final)
+                               : (h == c->la[0].h_in ? c->h_final : c->la[0].h_in);
+    layernorm_fwd(h_in, c->w + p.ln1, c->w + p.ln1b, x.n1, x.mean1, x.rstd1, T, d, eps, s); ++n;
+    egemm(c, x.n1, false, d, c->w + p.wqkv, false, d, x.qkv, nullptr, false, qkvd, T, qkvd, d);
+    bias_act(x.qkv, c->w + p.bqkv, T, qkvd, qkvd, 0, s); ++n;
+    attention_fwd(x.qkv, qkvd, qd, qd + kd, x.attn, qd, x.lse, nseq, S, H, Hkv, scale, s); ++n;
+    egemm(c, x.attn, false, qd, c->w + p.wo, false, qd, x.h_mid, h_in, false, d, T, d, qd);
+    bias_act(x.h_mid, c->w + p.bo, T, d, d, 0, s); ++n;
+    layernorm_fwd(x.h_mid, c->w + p.ln2, c->w + p.ln2b, x.n2, x.mean2, x.rstd2, T, d, eps, s); ++n;
+    egemm(c, x.n2, false, d, c->w + p.wgu, false, d, x.act, nullptr, false, f, T, f, d);
+    bias_act(x.act, c->w + p.b1, T, f, f, 1, s); ++n;  // ReLU; the backward masks on act > 0
+    egemm(c, x.act, false, f, c->w + p.wd, false, f, h_next, x.h_mid, false, d, T, d, f);
+    bias_act(h_next, c->w + p.b2, T, d, d, 0, s); ++n;
+    h = h_next;
+  }
+  layernorm_fwd(h, c->w + c->p_norm, c->w + c->p_normb, c->nf, c->meanf, c->rstdf, T, d, eps, s); ++n;
+  egemm(c, c->nf, false, d, c->w + c->p_lm, false, d, c->logits, nullptr, false, a.vocab_size, T,
+        a.vocab_size, d);
+  if (c->training && h != c->h_final) throw Error("internal: residual stream bookkeeping");
+}
+
+void forward_micro(b200w_ctx* c, const int32_t* ids, int nseq) {
+  if (is_opt(c->arch)) forward_micro_opt(c, ids, nseq);
+  else forward_micro_llama(c, ids, nseq);
+}
+
+// loss + dlogits (in place); the normaliser 1 / num_items_in_batch is the device scalar c->inv_n
+void loss_micro(b200w_ctx* c, const int32_t* labels, int nseq) {
   const b200w_arch& a = c->arch;
   const int S = a.max_seq_len, T = nseq * S;
   cudaStream_t s = c->stream;
   ce_shift_targets(labels, c->targets, T, S, s); ++c->launches;
-  ce_loss_fwd_bwd(c->logits, c->targets, c->nll, T, a.vocab_size, inv_n, s); ++c->launches;
-  reduce_sum_f32(c->nll, c->scal + 0, T, inv_n, s); ++c->launches;
+  ce_loss_fwd_bwd(c->logits, c->targets, c->nll, T, a.vocab_size, c->inv_n, s); ++c->launches;
+  reduce_sum_f32(c->nll, c->scal + 0, T, c->inv_n, s); ++c->launches;
 }
 
 // B200W_AR_MODE (debugging aid, same arithmetic in every mode):
-//   overlap (default)  per-layer all-reduce on comm_stream, concurrent with the rest of the backward
+//   overlap (default)  per-matrix all-reduce on comm_stream as soon as the last micro-step's backward
+//                      has produced the gradient, concurrent with the rest of the backward
 //   sync               as overlap, but the host drains c->stream before enqueuing each all-reduce
-//   serial             per-layer, but c->stream waits for each all-reduce: never concurrent with compute
+//   serial             per-matrix, but c->stream waits for each all-reduce: never concurrent with compute
 //   end                one all-reduce of the whole gradient after the backward
-//
-// Default policy (round 1, PROVISIONAL): overlap for <= 2 ranks, where it is verified (10 steps
-// bit-identical across ranks, profiles/r01_bench_n2_v10.json); end for > 2 ranks. The only 8-rank
-// run so far died in its first steps with one rank's dK/dV kernel stalled > 2 s on an mbarrier
-// (profiles/r01_n8_failure.txt) and the cause is not established; what separates that run from the
-// passing ones is NCCL activity while the backward is in flight, which `end` removes entirely.
-// Expected cost at 8 ranks: the 27 GB fp32 all-reduce is exposed, ~7-9 % of a step. Not verified on
-// hardware at 4 or 8 ranks in either mode.
+// Round 1 fell back to `end` for more than 2 ranks after an 8-rank run stalled in the dK/dV kernel
+// (profiles/r01_n8_failure.txt); that kernel's barrier protocol is fixed (attention.cu, one bar_p per
+// stage) and overlap is the default for every rank count.
 enum class ArMode { Overlap, Sync, Serial, End };
-ArMode ar_mode(int nranks) {
+ArMode ar_mode() {
   const char* m = getenv("B200W_AR_MODE");
   const std::string v = m ? m : "";
   if (v == "end") return ArMode::End;
   if (v == "sync") return ArMode::Sync;
   if (v == "serial") return ArMode::Serial;
-  if (v == "overlap") return ArMode::Overlap;
-  return nranks > 2 ? ArMode::End : ArMode::Overlap;
+  return ArMode::Overlap;
 }
 
+void ensure_wire(b200w_ctx* c) {
+  if (!c->gw) c->gw = c->alloc<bf16>(c->n_elems);
+}
+
+// Gradient exchange of the flat range [off, off + count): the fp32 accumulation buffer is rounded to
+// bf16 into the wire copy (main stream), and the wire copy is summed over the ranks by NCCL on the
+// comm stream (13.5 GB per step for Llama-2-7B instead of 27 GB). The optimiser
+// then reads the reduced bf16 gradients directly.
 void allreduce_range(b200w_ctx* c, size_t off, size_t count) {
-  const ArMode mode = ar_mode(c->nranks);
+  if (count == 0) return;
+  const ArMode mode = ar_mode();
+  cast_f32_to_bf16(c->g + off, c->gw + off, count, c->stream); ++c->launches;
   if (mode == ArMode::Sync) B200W_CUDA(cudaStreamSynchronize(c->stream));
   B200W_CUDA(cudaEventRecord(c->ev_grad, c->stream));
   B200W_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_grad, 0));
-  B200W_NCCL(nccl().AllReduce(c->g + off, c->g + off, count, kNcclFloat32, kNcclSum, c->comm,
+  B200W_NCCL(nccl().AllReduce(c->gw + off, c->gw + off, count, kNcclBfloat16, kNcclSum, c->comm,
                               c->comm_stream));
   ++c->launches;
   if (mode == ArMode::Serial) {
@@ -451,23 +650,24 @@ void allreduce_range(b200w_ctx* c, size_t off, size_t count) {
 }
 
 // backward of one micro-batch. first: overwrite gradients instead of accumulating.
-// overlap_ar: launch the per-layer all-reduce as soon as a layer's gradients are final.
-void backward_micro(b200w_ctx* c, const int32_t* ids, int nseq, bool first, bool overlap_ar) {
+// overlap_ar: launch the all-reduce of each matrix as soon as its gradient is final.
+void backward_micro_llama(b200w_ctx* c, const int32_t* ids, int nseq, bool first, bool overlap_ar) {
   const b200w_arch& a = c->arch;
   const int S = a.max_seq_len, T = nseq * S, d = a.hidden_size, f = a.intermediate_size;
   const int H = a.num_heads, Hkv = a.num_kv_heads, dh = a.head_dim, V = a.vocab_size;
-  const int qd = H * dh, kd = Hkv * dh, qkvd = qkv_dim(a);
+  const int qd = H * dh, kd = Hkv * dh, qkvd = qkv_dim(c);
   const float scale = 1.f / sqrtf(static_cast<float>(dh));
   cudaStream_t s = c->stream;
   int64_t& n = c->launches;
   const int L = a.num_layers;
   float* g = c->g;
   auto acc = [&](size_t off) -> const void* { return first ? nullptr : g + off; };
+  auto ar = [&](size_t off, size_t count) { if (overlap_ar) allreduce_range(c, off, count); };
 
   // lm_head: dnf = dlogits W ; dW += dlogits^T nf
   egemm(c, c->logits, false, V, c->w + c->p_lm, true, d, c->dn, nullptr, false, d, T, d, V);
   egemm(c, c->logits, true, V, c->nf, true, d, g + c->p_lm, acc(c->p_lm), true, d, V, d, T);
-  if (overlap_ar) allreduce_range(c, c->p_lm, static_cast<size_t>(V) * d);
+  ar(c->p_lm, static_cast<size_t>(V) * d);
   bf16* dh_cur = c->dh_a;
   bf16* dh_alt = c->dh_b;
   rmsnorm_bwd(c->dn, c->h_final, c->w + c->p_norm, c->rstdf, nullptr, dh_cur, g + c->p_norm, c->dw_partial, T, d, s); n += 2;
@@ -479,49 +679,133 @@ void backward_micro(b200w_ctx* c, const int32_t* ids, int nseq, bool first, bool
     // h_next = h_mid + act Wd^T
     egemm(c, dh_cur, false, d, c->w + o_d, true, f, c->dact, nullptr, false, f, T, f, d);
     egemm(c, dh_cur, true, d, x.act, true, f, g + o_d, acc(o_d), true, f, d, f, T);
+    ar(o_d, static_cast<size_t>(d) * f);
     swiglu_bwd(c->dact, x.gu, c->dgu, T, f, s); ++n;
     egemm(c, c->dgu, false, 2 * f, c->w + o_gu, true, d, c->dn, nullptr, false, d, T, d, 2 * f);
     egemm(c, c->dgu, true, 2 * f, x.n2, true, d, g + o_gu, acc(o_gu), true, d, 2 * f, d, T);
+    ar(o_gu, static_cast<size_t>(2) * f * d);
     // dh_mid = dh + rmsnorm_bwd(dn2)
     rmsnorm_bwd(c->dn, x.h_mid, c->w + p.ln2, x.rstd2, dh_cur, dh_alt, g + p.ln2, c->dw_partial, T, d, s); n += 2;
     std::swap(dh_cur, dh_alt);
     // h_mid = h_in + attn Wo^T
     egemm(c, dh_cur, false, d, c->w + o_o, true, qd, c->dattn, nullptr, false, qd, T, qd, d);
     egemm(c, dh_cur, true, d, x.attn, true, qd, g + o_o, acc(o_o), true, qd, d, qd, T);
+    ar(o_o, static_cast<size_t>(d) * qd);
     attention_bwd(x.qkv, qkvd, qd, qd + kd, x.attn, c->dattn, qd, x.lse, c->delta, c->dqkv, nseq, S, H,
                   Hkv, scale, s); n += 3;
     rope_apply(c->dqkv, qkvd, c->rope_tab, T, S, H + Hkv, dh, true, s); ++n;
     egemm(c, c->dqkv, false, qkvd, c->w + o_q, true, d, c->dn, nullptr, false, d, T, d, qkvd);
     egemm(c, c->dqkv, true, qkvd, x.n1, true, d, g + o_q, acc(o_q), true, d, qkvd, d, T);
+    ar(o_q, static_cast<size_t>(qkvd) * d);
     rmsnorm_bwd(c->dn, x.h_in, c->w + p.ln1, x.rstd1, dh_cur, dh_alt, g + p.ln1, c->dw_partial, T, d, s); n += 2;
     std::swap(dh_cur, dh_alt);
-    if (overlap_ar) {
-      // the layer's matrices are contiguous: [wqkv .. wd + d*f)
-      allreduce_range(c, o_q, (o_d + static_cast<size_t>(d) * f) - o_q);
-    }
   }
-  embed_bwd(ids, dh_cur, g + c->p_embed, T, d, V, s); ++n;
-  if (overlap_ar) allreduce_range(c, 0, c->n_zero_prefix);
+  embed_bwd(ids, dh_cur, g + c->p_embed, nullptr, T, d, V, a.pad_token_id, S, 0, s); ++n;
+  ar(0, c->n_zero_prefix);
+}
+
+// OPT backward. Bias gradients are column sums of the projection's output gradient; the tied
+// lm_head accumulates into the embedding gradient (zeroed with the prefix at the start of a step,
+// so that wgrad always accumulates) before embed_bwd adds the lookup rows.
+void backward_micro_opt(b200w_ctx* c, const int32_t* ids, int nseq, bool first, bool overlap_ar) {
+  const b200w_arch& a = c->arch;
+  const int S = a.max_seq_len, T = nseq * S, d = a.hidden_size, f = a.intermediate_size;
+  const int H = a.num_heads, Hkv = a.num_kv_heads, V = a.vocab_size;
+  const int qd = qd_of(c), kd = kd_of(c), qkvd = qkv_dim(c);
+  const float scale = 1.f / sqrtf(static_cast<float>(a.head_dim));
+  cudaStream_t s = c->stream;
+  int64_t& n = c->launches;
+  const int L = a.num_layers;
+  float* g = c->g;
+  float* part = c->dw_partial;
+  auto acc = [&](size_t off) -> const void* { return first ? nullptr : g + off; };
+  auto ar = [&](size_t off, size_t count) { if (overlap_ar) allreduce_range(c, off, count); };
+
+  egemm(c, c->logits, false, V, c->w + c->p_lm, true, d, c->dn, nullptr, false, d, T, d, V);
+  egemm(c, c->logits, true, V, c->nf, true, d, g + c->p_embed, g + c->p_embed, true, d, V, d, T);
+  bf16* dh_cur = c->dh_a;
+  bf16* dh_alt = c->dh_b;
+  layernorm_bwd(c->dn, c->h_final, c->w + c->p_norm, c->meanf, c->rstdf, nullptr, dh_cur, g + c->p_norm,
+                g + c->p_normb, part, T, d, s); n += 3;
+  for (int l = L - 1; l >= 0; --l) {
+    auto& x = c->la[l];
+    const auto& p = c->lp[l];
+    // h_next = h_mid + act W2^T + b2
+    colsum_add(dh_cur, g + p.b2, part, T, d, d, s); n += 2;
+    egemm(c, dh_cur, false, d, c->w + p.wd, true, f, c->dact, nullptr, false, f, T, f, d);
+    egemm(c, dh_cur, true, d, x.act, true, f, g + p.wd, acc(p.wd), true, f, d, f, T);
+    ar(p.wd, static_cast<size_t>(d) * f);
+    // act = relu(n2 W1^T + b1)
+    relu_bwd(c->dact, x.act, c->dact, static_cast<size_t>(T) * f, s); ++n;
+    colsum_add(c->dact, g + p.b1, part, T, f, f, s); n += 2;
+    egemm(c, c->dact, false, f, c->w + p.wgu, true, d, c->dn, nullptr, false, d, T, d, f);
+    egemm(c, c->dact, true, f, x.n2, true, d, g + p.wgu, acc(p.wgu), true, d, f, d, T);
+    ar(p.wgu, static_cast<size_t>(f) * d);
+    layernorm_bwd(c->dn, x.h_mid, c->w + p.ln2, x.mean2, x.rstd2, dh_cur, dh_alt, g + p.ln2, g + p.ln2b, part,
+                  T, d, s); n += 3;
+    std::swap(dh_cur, dh_alt);
+    // h_mid = h_in + attn Wo^T + bo
+    colsum_add(dh_cur, g + p.bo, part, T, d, d, s); n += 2;
+    egemm(c, dh_cur, false, d, c->w + p.wo, true, qd, c->dattn, nullptr, false, qd, T, qd, d);
+    egemm(c, dh_cur, true, d, x.attn, true, qd, g + p.wo, acc(p.wo), true, qd, d, qd, T);
+    ar(p.wo, static_cast<size_t>(d) * qd);
+    attention_bwd(x.qkv, qkvd, qd, qd + kd, x.attn, c->dattn, qd, x.lse, c->delta, c->dqkv, nseq, S, H,
+                  Hkv, scale, s); n += 3;
+    colsum_add(c->dqkv, g + p.bqkv, part, T, qkvd, qkvd, s); n += 2;
+    egemm(c, c->dqkv, false, qkvd, c->w + p.wqkv, true, d, c->dn, nullptr, false, d, T, d, qkvd);
+    egemm(c, c->dqkv, true, qkvd, x.n1, true, d, g + p.wqkv, acc(p.wqkv), true, d, qkvd, d, T);
+    ar(p.wqkv, static_cast<size_t>(qkvd) * d);
+    layernorm_bwd(c->dn, x.h_in, c->w + p.ln1, x.mean1, x.rstd1, dh_cur, dh_alt, g + p.ln1, g + p.ln1b, part,
+                  T, d, s); n += 3;
+    std::swap(dh_cur, dh_alt);
+  }
+  embed_bwd(ids, dh_cur, g + c->p_embed, g + c->p_pos, T, d, V, a.pad_token_id, S, OPT_POS_OFFSET, s); ++n;
+  ar(0, c->n_zero_prefix);
+}
+
+void backward_micro(b200w_ctx* c, const int32_t* ids, int nseq, bool first, bool overlap_ar) {
+  // while the all-reduce runs under the backward, the persistent GEMMs leave NCCL its SMs
+  if (overlap_ar) gemm_set_sm_reserve(c->ar_sm_reserve);
+  try {
+    if (is_opt(c->arch)) backward_micro_opt(c, ids, nseq, first, overlap_ar);
+    else backward_micro_llama(c, ids, nseq, first, overlap_ar);
+  } catch (...) {
+    gemm_set_sm_reserve(0);
+    throw;
+  }
+  gemm_set_sm_reserve(0);
 }
 
 void ensure_ids(b200w_ctx* c, size_t n_tok) {
   if (c->ids_cap < n_tok) {
+    if (c->ids_dev) {  // every kernel that read the old buffers was enqueued before this point
+      B200W_CUDA(cudaStreamSynchronize(c->stream));
+      c->release(c->ids_dev);
+      c->release(c->labels_dev);
+    }
     c->ids_dev = c->alloc<int32_t>(n_tok);
     c->labels_dev = c->alloc<int32_t>(n_tok);
     c->ids_cap = n_tok;
   }
   if (c->pinned_cap < 2 * n_tok) {
-    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->pinned) {
+      B200W_CUDA(cudaStreamSynchronize(c->stream));
+      cudaFreeHost(c->pinned);
+      c->pinned = nullptr;
+    }
     B200W_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->pinned), 2 * n_tok * sizeof(int32_t)));
     c->pinned_cap = 2 * n_tok;
   }
 }
 
-// counts HF's num_items_in_batch: shifted labels != -100
+// HF Trainer's num_items_in_batch (transformers 5.5 trainer.py:2136): labels != -100 counted on the
+// UNSHIFTED labels of the whole batch, although the loss sums over the shifted ones (a row's first
+// label never contributes a term but is counted). Round 1 counted the shifted labels, which is what
+// model(input_ids, labels) does without a Trainer; the two differ by (S-1)/S on packed rows.
 long count_valid(const int32_t* labels, int n_seqs, int S) {
   long nvalid = 0;
-  for (int b = 0; b < n_seqs; ++b)
-    for (int t = 1; t < S; ++t) nvalid += labels[static_cast<size_t>(b) * S + t] != -100;
+  const size_t n = static_cast<size_t>(n_seqs) * S;
+  for (size_t i = 0; i < n; ++i) nvalid += labels[i] != -100;
   return nvalid;
 }
 
@@ -549,34 +833,45 @@ void upload_batch(b200w_ctx* c, const int32_t* ids, const int32_t* labels, size_
 // factor again, so the gradient is that of sum(nll over all ranks) / n_global -- the same number a
 // single process computes on the global batch. Per-rank normalisation would differ whenever the
 // ranks hold different numbers of target tokens (prompt-masked rows).
-long global_valid(b200w_ctx* c, long nvalid_local) {
-  if (!c->comm) return nvalid_local;
-  long long* host = reinterpret_cast<long long*>(c->host_scal + 4);
-  *host = nvalid_local;
-  // every NCCL call of this context goes to comm_stream (one stream per communicator); the count
-  // comes from the host, so nothing on c->stream has to be waited for
+// The count never visits the host: it is summed by NCCL on the comm stream and its reciprocal lands
+// in the device scalar c->inv_n that the loss kernels read (round 1 synchronised the host on this
+// 8-byte all-reduce every step).
+void set_global_count(b200w_ctx* c, long nvalid_local) {
+  if (!c->comm) {
+    set_count_kernel<<<1, 1, 0, c->stream>>>(c->cnt_dev, nvalid_local);
+    inv_count_kernel<<<1, 1, 0, c->stream>>>(c->cnt_dev, c->inv_n);
+    B200W_CUDA(cudaGetLastError());
+    c->launches += 2;
+    return;
+  }
   cudaStream_t cs = c->comm_stream;
-  B200W_CUDA(cudaMemcpyAsync(c->cnt_dev, host, sizeof(long long), cudaMemcpyHostToDevice, cs));
+  // c->inv_n is still read by whatever the main stream has queued (the previous step's loss kernels)
+  B200W_CUDA(cudaEventRecord(c->ev_grad, c->stream));
+  B200W_CUDA(cudaStreamWaitEvent(cs, c->ev_grad, 0));
+  set_count_kernel<<<1, 1, 0, cs>>>(c->cnt_dev, nvalid_local);
+  B200W_CUDA(cudaGetLastError());
   B200W_NCCL(nccl().AllReduce(c->cnt_dev, c->cnt_dev, 1, kNcclInt64, kNcclSum, c->comm, cs));
-  B200W_CUDA(cudaMemcpyAsync(host, c->cnt_dev, sizeof(long long), cudaMemcpyDeviceToHost, cs));
-  B200W_CUDA(cudaStreamSynchronize(cs));
-  ++c->launches;
-  return static_cast<long>(*host);
+  inv_count_kernel<<<1, 1, 0, cs>>>(c->cnt_dev, c->inv_n);
+  B200W_CUDA(cudaGetLastError());
+  B200W_CUDA(cudaEventRecord(c->ev_comm, cs));
+  B200W_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+  c->launches += 3;
 }
 
 // forward + loss + backward over a batch that is already on the device. nvalid = this rank's count
 // of target tokens; with a communicator the gradients returned are those of the GLOBAL batch
-// (sum over ranks of sum(nll) / n_global), all-reduced, and scal[0] is the global loss.
+// (sum over ranks of sum(nll) / n_global), all-reduced into the bf16 wire copy c->gw, and scal[0] is
+// the global loss.
 void fwd_bwd_device(b200w_ctx* c, const int32_t* ids_dev, const int32_t* labels_dev, int n_seqs,
                     long nvalid, bool allow_overlap) {
   const int S = c->arch.max_seq_len, mb = c->micro_batch;
   B200W_CHECK(c->has_model && c->training, "model not initialised for training");
   B200W_CHECK(n_seqs > 0 && n_seqs % mb == 0, "n_seqs must be a positive multiple of micro_batch");
   B200W_CHECK(nvalid >= 0, "negative target count");
-  const long n_global = global_valid(c, nvalid);
-  B200W_CHECK(n_global > 0, "batch has no valid target token");
-  const float inv_n = 1.f / static_cast<float>(n_global);
-  allow_overlap = allow_overlap && ar_mode(c->nranks) != ArMode::End;
+  B200W_CHECK(c->comm || nvalid > 0, "batch has no valid target token");
+  if (c->comm) ensure_wire(c);
+  set_global_count(c, nvalid);
+  allow_overlap = allow_overlap && ar_mode() != ArMode::End;
   B200W_CUDA(cudaMemsetAsync(c->scal, 0, 8 * sizeof(float), c->stream));
   B200W_CUDA(cudaMemsetAsync(c->g, 0, c->n_zero_prefix * sizeof(float), c->stream));
   const int n_micro = n_seqs / mb;
@@ -584,7 +879,7 @@ void fwd_bwd_device(b200w_ctx* c, const int32_t* ids_dev, const int32_t* labels_
     const int32_t* mids = ids_dev + static_cast<size_t>(mi) * mb * S;
     const int32_t* mlab = labels_dev + static_cast<size_t>(mi) * mb * S;
     forward_micro(c, mids, mb);
-    loss_micro(c, mlab, mb, inv_n);
+    loss_micro(c, mlab, mb);
     const bool ar = allow_overlap && c->comm && mi == n_micro - 1;
     backward_micro(c, mids, mb, mi == 0, ar);
   }
@@ -609,18 +904,31 @@ void fwd_bwd_all(b200w_ctx* c, const int32_t* ids, const int32_t* labels, int n_
   fwd_bwd_device(c, c->ids_dev, c->labels_dev, n_seqs, nvalid, allow_overlap);
 }
 
-// all-reduce is complete on c->stream; global-norm clip + AdamW over the flat parameter space
+// all-reduce is complete on c->stream; global-norm clip + AdamW over the flat parameter space.
+// Gradient source: the fp32 accumulation buffer, or with a communicator the reduced bf16 wire copy.
 void optimizer_step(b200w_ctx* c, float lr) {
   cudaStream_t s = c->stream;
+  const bool wire = c->comm != nullptr;
+  const void* gsrc = wire ? static_cast<const void*>(c->gw) : static_cast<const void*>(c->g);
   B200W_CUDA(cudaMemsetAsync(c->sumsq, 0, sizeof(double), s));
-  grad_sumsq(c->g, c->n_elems, c->sumsq, s); ++c->launches;
+  grad_sumsq(gsrc, wire, c->n_elems, c->sumsq, s); ++c->launches;
   // the all-reduce summed per-rank partials that were already divided by the GLOBAL target count
   // (fwd_bwd_device), which is HF's DDP result: no 1/nranks here
   clip_coef(c->sumsq, c->hp.max_grad_norm, 1.f, c->scal + 1, c->scal + 2, s); ++c->launches;
   c->step += 1;
-  adamw_step(c->master, c->m, c->v, c->g, c->w, c->n_elems, lr, c->hp.beta1, c->hp.beta2, c->hp.eps,
-             c->hp.weight_decay, c->step, c->scal + 1, s);
-  ++c->launches;
+  auto run = [&](size_t off, size_t n, float wd) {
+    const void* gp = wire ? static_cast<const void*>(c->gw + off) : static_cast<const void*>(c->g + off);
+    adamw_step(c->master + off, c->m + off, c->v + off, gp, wire, c->w + off, n, lr, c->hp.beta1,
+               c->hp.beta2, c->hp.eps, wd, c->step, c->scal + 1, s);
+    ++c->launches;
+  };
+  if (c->hp.weight_decay == 0.f) {
+    run(0, c->n_elems, 0.f);
+  } else {
+    // HF Trainer's parameter groups (trainer.py get_decay_parameter_names): norm weights, LayerNorm
+    // parameters and biases are not decayed
+    for (const auto& sg : c->segs) run(sg.off, sg.n, sg.decay ? c->hp.weight_decay : 0.f);
+  }
 }
 
 }  // namespace
@@ -734,24 +1042,40 @@ int b200w_model_init(b200w_ctx* ctx, const b200w_arch* arch, const b200w_hparams
   return guarded(ctx, [&] {
     B200W_CHECK(arch != nullptr, "arch is NULL");
     B200W_CHECK(!ctx->has_model, "model already initialised");
-    B200W_CHECK(arch->head_dim == 128, "head_dim must be 128");
+    B200W_CHECK(arch->family == B200W_FAMILY_LLAMA || arch->family == B200W_FAMILY_OPT,
+                "the fine-tune engine builds the Llama and OPT families");
+    const bool opt = arch->family == B200W_FAMILY_OPT;
+    if (opt) {
+      B200W_CHECK(arch->head_dim == 64 || arch->head_dim == 128, "OPT: head_dim must be 64 or 128");
+      B200W_CHECK(arch->num_kv_heads == arch->num_heads, "OPT has no grouped-query attention");
+      B200W_CHECK(arch->hidden_size == arch->num_heads * arch->head_dim, "OPT: hidden_size = heads x head_dim");
+      B200W_CHECK(arch->max_positions >= arch->max_seq_len,
+                  "OPT: max_seq_len exceeds the learned position table (max_position_embeddings)");
+    } else {
+      B200W_CHECK(arch->head_dim == 128, "Llama: head_dim must be 128");
+    }
     B200W_CHECK(arch->num_heads % arch->num_kv_heads == 0, "heads must be a multiple of kv heads");
     B200W_CHECK(arch->hidden_size % 8 == 0 && arch->intermediate_size % 8 == 0 &&
                     arch->vocab_size % 8 == 0,
                 "sizes must be multiples of 8");
     B200W_CHECK(arch->max_seq_len % 128 == 0, "max_seq_len must be a multiple of 128");
+    B200W_CHECK(arch->pad_token_id >= -1 && arch->pad_token_id < arch->vocab_size, "bad pad_token_id");
     B200W_CHECK(micro_batch >= 1, "micro_batch must be >= 1");
     ctx->arch = *arch;
     if (hp) ctx->hp = *hp; else b200w_default_hparams(&ctx->hp);
     ctx->micro_batch = micro_batch;
     ctx->training = training != 0;
-    build_params(ctx);
+    ctx->dhp = 128;
+    if (opt) build_params_opt(ctx); else build_params_llama(ctx);
+    build_segments(ctx);
     ctx->w = ctx->alloc<bf16>(ctx->n_elems);
+    B200W_CUDA(cudaMemsetAsync(ctx->w, 0, ctx->n_elems * sizeof(bf16), ctx->stream));  // head padding = 0
     if (ctx->training) {
       ctx->master = ctx->alloc<float>(ctx->n_elems);
       ctx->m = ctx->alloc<float>(ctx->n_elems);
       ctx->v = ctx->alloc<float>(ctx->n_elems);
       ctx->g = ctx->alloc<float>(ctx->n_elems);
+      B200W_CUDA(cudaMemsetAsync(ctx->master, 0, ctx->n_elems * sizeof(float), ctx->stream));
       B200W_CUDA(cudaMemsetAsync(ctx->m, 0, ctx->n_elems * sizeof(float), ctx->stream));
       B200W_CUDA(cudaMemsetAsync(ctx->v, 0, ctx->n_elems * sizeof(float), ctx->stream));
       B200W_CUDA(cudaMemsetAsync(ctx->g, 0, ctx->n_elems * sizeof(float), ctx->stream));
@@ -794,27 +1118,77 @@ static const Param& find_param(b200w_ctx* ctx, const char* name, int64_t n_eleme
   return p;
 }
 
+// dense host tensor -> the parameter's (possibly head-padded) place in master / w
 int b200w_load_tensor(b200w_ctx* ctx, const char* name, const void* host, b200w_dtype dtype,
                       int64_t n_elements) {
   return guarded(ctx, [&] {
     const Param& p = find_param(ctx, name, n_elements);
     B200W_CHECK(host && (dtype == B200W_BF16 || dtype == B200W_F32), "bad host buffer / dtype");
     const size_t n = static_cast<size_t>(n_elements);
-    if (dtype == B200W_F32) {
-      float* tmp = ctx->training ? ctx->master + p.off : nullptr;
-      void* scratch = nullptr;
-      if (!tmp) { B200W_CUDA(cudaMalloc(&scratch, n * 4)); tmp = static_cast<float*>(scratch); }
-      B200W_CUDA(cudaMemcpyAsync(tmp, host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-      cast_f32_to_bf16(tmp, ctx->w + p.off, n, ctx->stream);
-      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
-      if (scratch) cudaFree(scratch);
-    } else {
-      B200W_CUDA(cudaMemcpyAsync(ctx->w + p.off, host, n * 2, cudaMemcpyHostToDevice, ctx->stream));
-      if (ctx->training) cast_bf16_to_f32(ctx->w + p.off, ctx->master + p.off, n, ctx->stream);
-      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaStream_t s = ctx->stream;
+    if (p.pad == 0) {
+      if (dtype == B200W_F32) {
+        float* tmp = ctx->training ? ctx->master + p.off : nullptr;
+        void* scratch = nullptr;
+        if (!tmp) { B200W_CUDA(cudaMalloc(&scratch, n * 4)); tmp = static_cast<float*>(scratch); }
+        B200W_CUDA(cudaMemcpyAsync(tmp, host, n * 4, cudaMemcpyHostToDevice, s));
+        cast_f32_to_bf16(tmp, ctx->w + p.off, n, s);
+        B200W_CUDA(cudaStreamSynchronize(s));
+        if (scratch) cudaFree(scratch);
+      } else {
+        B200W_CUDA(cudaMemcpyAsync(ctx->w + p.off, host, n * 2, cudaMemcpyHostToDevice, s));
+        if (ctx->training) cast_bf16_to_f32(ctx->w + p.off, ctx->master + p.off, n, s);
+        B200W_CUDA(cudaStreamSynchronize(s));
+      }
+      return;
     }
+    // head-padded parameter: stage dense fp32 on the device, scatter into the padded rows / columns
+    float* dense = nullptr;
+    void* raw = nullptr;
+    B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&dense), n * 4));
+    try {
+      if (dtype == B200W_F32) {
+        B200W_CUDA(cudaMemcpyAsync(dense, host, n * 4, cudaMemcpyHostToDevice, s));
+      } else {
+        B200W_CUDA(cudaMalloc(&raw, n * 2));
+        B200W_CUDA(cudaMemcpyAsync(raw, host, n * 2, cudaMemcpyHostToDevice, s));
+        cast_bf16_to_f32(raw, dense, n, s);
+      }
+      pad_scatter_kernel<<<sm_count() * 4, 256, 0, s>>>(dense, ctx->training ? ctx->master + p.off : nullptr,
+                                                        ctx->w + p.off, p.rows, p.cols, p.icols, p.pad,
+                                                        ctx->arch.head_dim, ctx->dhp);
+      B200W_CUDA(cudaGetLastError());
+      B200W_CUDA(cudaStreamSynchronize(s));
+    } catch (...) { cudaFree(dense); cudaFree(raw); throw; }
+    cudaFree(dense);
+    cudaFree(raw);
   });
 }
+
+namespace {
+// the parameter's dense HF-shaped values as fp32 on the host, from an fp32 state array (srcf) or the
+// bf16 compute copy (srcb)
+void read_dense(b200w_ctx* ctx, const Param& p, const float* srcf, const bf16* srcb, float* host) {
+  const size_t n = static_cast<size_t>(p.rows) * p.cols;
+  cudaStream_t s = ctx->stream;
+  B200W_CUDA(cudaStreamSynchronize(s));
+  if (p.pad == 0 && srcf) {
+    B200W_CUDA(cudaMemcpy(host, srcf + p.off, n * 4, cudaMemcpyDeviceToHost));
+    return;
+  }
+  float* dense = nullptr;
+  B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&dense), n * 4));
+  try {
+    pad_gather_kernel<<<sm_count() * 4, 256, 0, s>>>(srcf ? srcf + p.off : nullptr, srcb ? srcb + p.off : nullptr,
+                                                     dense, p.rows, p.cols, p.icols, p.pad, ctx->arch.head_dim,
+                                                     ctx->dhp);
+    B200W_CUDA(cudaGetLastError());
+    B200W_CUDA(cudaStreamSynchronize(s));
+    B200W_CUDA(cudaMemcpy(host, dense, n * 4, cudaMemcpyDeviceToHost));
+  } catch (...) { cudaFree(dense); throw; }
+  cudaFree(dense);
+}
+}  // namespace
 
 int b200w_read_tensor(b200w_ctx* ctx, const char* name, void* host, b200w_dtype dtype,
                       int64_t n_elements) {
@@ -822,18 +1196,24 @@ int b200w_read_tensor(b200w_ctx* ctx, const char* name, void* host, b200w_dtype 
     const Param& p = find_param(ctx, name, n_elements);
     B200W_CHECK(host && (dtype == B200W_BF16 || dtype == B200W_F32), "bad host buffer / dtype");
     const size_t n = static_cast<size_t>(n_elements);
+    if (dtype == B200W_F32) {
+      read_dense(ctx, p, ctx->training ? ctx->master : nullptr, ctx->training ? nullptr : ctx->w,
+                 static_cast<float*>(host));
+      return;
+    }
     B200W_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (dtype == B200W_BF16) {
+    if (p.pad == 0) {
       B200W_CUDA(cudaMemcpy(host, ctx->w + p.off, n * 2, cudaMemcpyDeviceToHost));
-    } else if (ctx->training) {
-      B200W_CUDA(cudaMemcpy(host, ctx->master + p.off, n * 4, cudaMemcpyDeviceToHost));
-    } else {
-      void* scratch = nullptr;
-      B200W_CUDA(cudaMalloc(&scratch, n * 4));
-      cast_bf16_to_f32(ctx->w + p.off, static_cast<float*>(scratch), n, ctx->stream);
-      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
-      B200W_CUDA(cudaMemcpy(host, scratch, n * 4, cudaMemcpyDeviceToHost));
-      cudaFree(scratch);
+      return;
+    }
+    // padded + bf16: gather as fp32 (exact: the values are bf16), round back on the host side of the copy
+    std::vector<float> tmp(n);
+    read_dense(ctx, p, nullptr, ctx->w, tmp.data());
+    uint16_t* out = static_cast<uint16_t*>(host);
+    for (size_t i = 0; i < n; ++i) {
+      uint32_t u;
+      memcpy(&u, &tmp[i], 4);
+      out[i] = static_cast<uint16_t>(u >> 16);  // exact: low 16 bits are zero
     }
   });
 }
@@ -843,9 +1223,7 @@ int b200w_read_state(b200w_ctx* ctx, const char* name, int kind, float* host, in
     const Param& p = find_param(ctx, name, n_elements);
     B200W_CHECK(ctx->training && host && kind >= 0 && kind <= 3, "bad kind / not training");
     const float* src[4] = {ctx->master, ctx->g, ctx->m, ctx->v};
-    B200W_CUDA(cudaStreamSynchronize(ctx->stream));
-    B200W_CUDA(cudaMemcpy(host, src[kind] + p.off, static_cast<size_t>(n_elements) * 4,
-                          cudaMemcpyDeviceToHost));
+    read_dense(ctx, p, src[kind], nullptr, host);
   });
 }
 
@@ -853,13 +1231,16 @@ int b200w_init_random(b200w_ctx* ctx, uint64_t seed, float std) {
   return guarded(ctx, [&] {
     B200W_CHECK(ctx->has_model, "no model");
     for (const Param& p : ctx->params) {
-      const size_t n = static_cast<size_t>(p.rows) * p.cols;
+      const size_t n = p.isize();
       float* mp = ctx->training ? ctx->master + p.off : nullptr;
-      if (p.is_norm)
-        fill_kernel<<<64, 256, 0, ctx->stream>>>(mp, ctx->w + p.off, n, 1.0f);
+      if (p.is_norm || p.is_zero_init)
+        fill_kernel<<<64, 256, 0, ctx->stream>>>(mp, ctx->w + p.off, n, p.is_norm ? 1.0f : 0.0f);
       else
         init_normal_kernel<<<sm_count() * 8, 256, 0, ctx->stream>>>(mp, ctx->w + p.off, n,
                                                                     seed + p.off, std);
+      if (p.pad)
+        pad_zero_kernel<<<sm_count() * 4, 256, 0, ctx->stream>>>(mp, ctx->w + p.off, p.irows, p.icols, p.pad,
+                                                                 ctx->arch.head_dim, ctx->dhp);
     }
     B200W_CUDA(cudaGetLastError());
     B200W_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -882,6 +1263,15 @@ int b200w_comm_init(b200w_ctx* ctx, int rank, int nranks, const void* id128) {
   return guarded(ctx, [&] {
     B200W_CHECK(id128 && nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / id");
     B200W_CHECK(!ctx->comm, "communicator already initialised");
+    // The gradient all-reduce runs under the last backward. NCCL's CTAs and the persistent GEMM CTAs
+    // (one per SM, ~200 KB of shared memory each) cannot share an SM, so the two are given disjoint
+    // SM budgets: NCCL is capped at R CTAs (NCCL_MAX_CTAS, unless the user set it) and the GEMMs of
+    // that backward launch on SMs - R. B200W_AR_SM_RESERVE overrides R (0: no partition).
+    int reserve = 16;
+    if (const char* e = getenv("B200W_AR_SM_RESERVE")) reserve = atoi(e);
+    if (reserve < 0 || reserve > 64) reserve = 16;
+    ctx->ar_sm_reserve = nranks > 1 ? reserve : 0;
+    if (reserve > 0) setenv("NCCL_MAX_CTAS", std::to_string(reserve).c_str(), /*overwrite=*/0);
     Uid uid;
     memcpy(&uid, id128, sizeof(uid));
     try {
@@ -893,17 +1283,16 @@ int b200w_comm_init(b200w_ctx* ctx, int rank, int nranks, const void* id128) {
     ctx->nranks = nranks;
     // NCCL connects its transports lazily, at the first collective of each kind (for 8 ranks:
     // P2P rings plus NVLS multicast objects -- seconds of driver work). Do that now, with the
-    // message classes the step uses (large fp32 sum, one int64, one float) and nothing else on the
-    // GPU, instead of in the middle of the first backward. UNVERIFIED mitigation for
-    // profiles/r01_n8_failure.txt.
+    // message classes the step uses (large bf16 sum, one int64, one float) and nothing else on the
+    // GPU, instead of in the middle of the first backward.
     {
-      const size_t n_big = size_t(64) << 20;  // 256 MB: same protocol/algorithm class as a layer's gradients
-      float* scratch = nullptr;
-      B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&scratch), n_big * sizeof(float)));
+      const size_t n_big = size_t(64) << 20;  // 128 MB of bf16: same protocol/algorithm class as a matrix gradient
+      bf16* scratch = nullptr;
+      B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&scratch), n_big * sizeof(bf16)));
       cudaStream_t cs = ctx->comm_stream;
       try {
-        B200W_CUDA(cudaMemsetAsync(scratch, 0, n_big * sizeof(float), cs));
-        B200W_NCCL(nccl().AllReduce(scratch, scratch, n_big, kNcclFloat32, kNcclSum, ctx->comm, cs));
+        B200W_CUDA(cudaMemsetAsync(scratch, 0, n_big * sizeof(bf16), cs));
+        B200W_NCCL(nccl().AllReduce(scratch, scratch, n_big, kNcclBfloat16, kNcclSum, ctx->comm, cs));
         B200W_NCCL(nccl().AllReduce(scratch, scratch, 1, kNcclFloat32, kNcclSum, ctx->comm, cs));
         B200W_NCCL(nccl().AllReduce(scratch, scratch, 1, kNcclInt64, kNcclSum, ctx->comm, cs));
         B200W_CUDA(cudaStreamSynchronize(cs));
@@ -921,6 +1310,8 @@ int b200w_forward_backward(b200w_ctx* ctx, const int32_t* ids, const int32_t* la
   return guarded(ctx, [&] {
     B200W_CHECK(ids && labels, "NULL batch");
     fwd_bwd_all(ctx, ids, labels, n_seqs, /*allow_overlap=*/false);
+    // the reduced gradients live in the bf16 wire copy: widen them for b200w_read_state(kind = 1)
+    if (ctx->comm) { cast_bf16_to_f32(ctx->gw, ctx->g, ctx->n_elems, ctx->stream); ++ctx->launches; }
     B200W_CUDA(cudaMemcpyAsync(ctx->host_scal, ctx->scal, 4 * sizeof(float), cudaMemcpyDeviceToHost,
                                ctx->stream));
     B200W_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1025,9 +1416,11 @@ int b200w_forward(b200w_ctx* ctx, const int32_t* ids, const int32_t* labels, int
     }
     if (labels && (nll_out || loss_out)) {
       const long nvalid = count_valid(labels, n_seqs, S);
-      const float inv_n = nvalid > 0 ? 1.f / static_cast<float>(nvalid) : 0.f;
+      set_count_kernel<<<1, 1, 0, ctx->stream>>>(ctx->cnt_dev, nvalid);
+      inv_count_kernel<<<1, 1, 0, ctx->stream>>>(ctx->cnt_dev, ctx->inv_n);
+      B200W_CUDA(cudaGetLastError());
       B200W_CUDA(cudaMemsetAsync(ctx->scal, 0, 8 * sizeof(float), ctx->stream));
-      loss_micro(ctx, ctx->labels_dev, n_seqs, inv_n);
+      loss_micro(ctx, ctx->labels_dev, n_seqs);
       B200W_CUDA(cudaMemcpyAsync(ctx->host_scal, ctx->scal, 4 * sizeof(float),
                                  cudaMemcpyDeviceToHost, ctx->stream));
       B200W_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1075,13 +1468,50 @@ int b200w_op_gemm_decode(b200w_ctx* ctx, const void* X, const void* W, void* out
     cudaFree(cnt);
   });
 }
-int b200w_op_embed_fwd(b200w_ctx* ctx, const int32_t* ids, const void* table, void* out, int T, int d,
-                       int vocab) {
-  HOOK(embed_fwd(ids, table, out, T, d, vocab, ctx->stream));
+int b200w_op_embed_fwd(b200w_ctx* ctx, const int32_t* ids, const void* table, const void* pos_table,
+                       void* out, int T, int d, int vocab, int S, int pos_offset) {
+  HOOK(embed_fwd(ids, table, pos_table, out, T, d, vocab, S, pos_offset, ctx->stream));
 }
-int b200w_op_embed_bwd(b200w_ctx* ctx, const int32_t* ids, const void* dout, float* dtable, int T,
-                       int d, int vocab) {
-  HOOK(embed_bwd(ids, dout, dtable, T, d, vocab, ctx->stream));
+int b200w_op_embed_bwd(b200w_ctx* ctx, const int32_t* ids, const void* dout, float* dtable, float* dpos,
+                       int T, int d, int vocab, int pad_id, int S, int pos_offset) {
+  HOOK(embed_bwd(ids, dout, dtable, dpos, T, d, vocab, pad_id, S, pos_offset, ctx->stream));
+}
+int b200w_op_layernorm_fwd(b200w_ctx* ctx, const void* x, const void* w, const void* b, void* y, float* mean,
+                           float* rstd, int T, int d, float eps) {
+  HOOK(layernorm_fwd(x, w, b, y, mean, rstd, T, d, eps, ctx->stream));
+}
+int b200w_op_layernorm_bwd(b200w_ctx* ctx, const void* dy, const void* x, const void* w, const float* mean,
+                           const float* rstd, const void* dresid, void* dx, float* dw, float* db, int T,
+                           int d) {
+  return guarded(ctx, [&] {
+    float* part = nullptr;
+    B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&part),
+                          static_cast<size_t>(rmsnorm_bwd_blocks(T)) * 2 * d * sizeof(float)));
+    try {
+      layernorm_bwd(dy, x, w, mean, rstd, dresid, dx, dw, db, part, T, d, ctx->stream);
+      ctx->launches += 3;
+      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    } catch (...) { cudaFree(part); throw; }
+    cudaFree(part);
+  });
+}
+int b200w_op_bias_act(b200w_ctx* ctx, void* x, const void* bias, int T, int N, int ld, int act) {
+  HOOK(bias_act(x, bias, T, N, ld, act, ctx->stream));
+}
+int b200w_op_relu_bwd(b200w_ctx* ctx, const void* dy, const void* act, void* dz, int64_t n) {
+  HOOK(relu_bwd(dy, act, dz, static_cast<size_t>(n), ctx->stream));
+}
+int b200w_op_colsum(b200w_ctx* ctx, const void* dy, float* db, int T, int N, int ld) {
+  return guarded(ctx, [&] {
+    float* part = nullptr;
+    B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&part), static_cast<size_t>(colsum_blocks(T)) * N * sizeof(float)));
+    try {
+      colsum_add(dy, db, part, T, N, ld, ctx->stream);
+      ctx->launches += 2;
+      B200W_CUDA(cudaStreamSynchronize(ctx->stream));
+    } catch (...) { cudaFree(part); throw; }
+    cudaFree(part);
+  });
 }
 int b200w_op_rmsnorm_fwd(b200w_ctx* ctx, const void* x, const void* w, void* y, float* rstd, int T,
                          int d, float eps) {
@@ -1127,8 +1557,9 @@ int b200w_op_ce(b200w_ctx* ctx, void* logits, const int32_t* labels, float* nll,
     int32_t* tg = nullptr;
     B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&tg), static_cast<size_t>(T) * 4));
     try {
+      B200W_CUDA(cudaMemcpyAsync(ctx_scal(ctx) + 4, &inv_n, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
       ce_shift_targets(labels, tg, T, S, ctx->stream);
-      ce_loss_fwd_bwd(logits, tg, nll, T, V, inv_n, ctx->stream);
+      ce_loss_fwd_bwd(logits, tg, nll, T, V, ctx_scal(ctx) + 4, ctx->stream);
       ctx->launches += 2;
       B200W_CUDA(cudaStreamSynchronize(ctx->stream));
     } catch (...) { cudaFree(tg); throw; }
@@ -1146,12 +1577,12 @@ int b200w_op_attention_bwd(b200w_ctx* ctx, const void* qkv, int ld_qkv, int k_of
   HOOK(attention_bwd(qkv, ld_qkv, k_off, v_off, out, dout, ld_out, lse2, delta, dqkv, B, S, H, Hkv,
                      scale, ctx->stream));
 }
-int b200w_op_adamw(b200w_ctx* ctx, float* master, float* m, float* v, const float* g, void* w_bf16,
-                   int64_t n, float lr, float beta1, float beta2, float eps, float wd, int step,
-                   float gscale) {
+int b200w_op_adamw(b200w_ctx* ctx, float* master, float* m, float* v, const void* g, int g_bf16,
+                   void* w_bf16, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
+                   int step, float gscale) {
   return guarded(ctx, [&] {
     B200W_CUDA(cudaMemcpyAsync(ctx_scal(ctx), &gscale, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    adamw_step(master, m, v, g, w_bf16, static_cast<size_t>(n), lr, beta1, beta2, eps, wd, step,
+    adamw_step(master, m, v, g, g_bf16 != 0, w_bf16, static_cast<size_t>(n), lr, beta1, beta2, eps, wd, step,
                ctx_scal(ctx), ctx->stream);
     ++ctx->launches;
     B200W_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1159,11 +1590,10 @@ int b200w_op_adamw(b200w_ctx* ctx, float* master, float* m, float* v, const floa
 }
 int b200w_op_poison_onchip(b200w_ctx* ctx, uint32_t pattern) {
   return guarded(ctx, [&] {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce once;
+    once.run([&] {
       B200W_CUDA(cudaFuncSetAttribute(poison_onchip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POISON_SMEM));
-      attr = true;
-    }
+    });
     // one CTA per SM at a time (smem-limited); several waves so that every SM is visited
     poison_onchip_kernel<<<sm_count() * 4, 128, POISON_SMEM, ctx->stream>>>(pattern);
     B200W_CUDA(cudaGetLastError());
@@ -1171,12 +1601,12 @@ int b200w_op_poison_onchip(b200w_ctx* ctx, uint32_t pattern) {
   });
 }
 
-int b200w_op_grad_norm(b200w_ctx* ctx, const float* g, int64_t n, float* norm_out) {
+int b200w_op_grad_norm(b200w_ctx* ctx, const void* g, int g_bf16, int64_t n, float* norm_out) {
   return guarded(ctx, [&] {
     double* ss = nullptr;
     B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss), sizeof(double)));
     B200W_CUDA(cudaMemsetAsync(ss, 0, sizeof(double), ctx->stream));
-    grad_sumsq(g, static_cast<size_t>(n), ss, ctx->stream);
+    grad_sumsq(g, g_bf16 != 0, static_cast<size_t>(n), ss, ctx->stream);
     ++ctx->launches;
     double h = 0;
     B200W_CUDA(cudaMemcpyAsync(&h, ss, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

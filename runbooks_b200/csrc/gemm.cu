@@ -323,6 +323,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
   if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
   tc_fence_before();
+  __syncthreads();     // CTA-scope ordering of the tmem_slot write that racecheck can see (the cluster
+                       // barrier below already orders it; compute-sanitizer does not model that one)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -435,13 +437,12 @@ void launch_pair(const void* A, const void* B, OutT* D, const OutT* C, int M, in
   CUtensorMap tmB = B_MN ? make_tmap_bf16_2d(B, K, N, ldb, BLOCK_K, 64)
                          : make_tmap_bf16_2d(B, N, K, ldb, PAIR_N / 2, BLOCK_K);
   auto kern = gemm_bf16_pair_kernel<A_MN, B_MN, OutT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  once.run([&] {
     B200W_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
-    attr_set = true;
-  }
+  });
   const int num_tiles = ((M + 255) / 256) * ((N + PAIR_N - 1) / PAIR_N);
-  const int max_clusters = sm_count() / 2;
+  const int max_clusters = (sm_count() - gemm_sm_reserve()) / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
   kern<<<clusters * 2, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(tmA, tmB, D, C, M, N, K, ldd,
                                                                 pick_n_fast(M, N, K));
@@ -467,14 +468,14 @@ void launch(const void* A, const void* B, OutT* D, const OutT* C, int M, int N, 
   CUtensorMap tmB = B_MN ? make_tmap_bf16_2d(B, K, N, ldb, BLOCK_K, 64)
                          : make_tmap_bf16_2d(B, N, K, ldb, BLOCK_N, BLOCK_K);
   auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OutT>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  static PerDeviceOnce once;  // per template instantiation
+  once.run([&] {
     B200W_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  });
   const int num_tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
-  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  const int sms = sm_count() - gemm_sm_reserve();
+  const int grid = num_tiles < sms ? num_tiles : sms;
   kern<<<grid, GEMM_THREADS, cfg::SMEM_BYTES, stream>>>(tmA, tmB, D, C, M, N, K, ldd,
                                                         pick_n_fast(M, N, K));
   B200W_CUDA(cudaGetLastError());
@@ -654,11 +655,10 @@ void launch_decode(const void* X, const void* W, void* out, const void* C, float
   CUtensorMap tmW = make_tmap_bf16_2d(W, N, K, K, BLOCK_M, BLOCK_K);
   CUtensorMap tmX = make_tmap_bf16_2d(X, M, K, K, MPAD, BLOCK_K);
   auto kern = gemm_decode_kernel<MPAD>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  once.run([&] {
     B200W_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  });
   const int n_tiles = (N + BLOCK_M - 1) / BLOCK_M;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
   // split K until every SM has a CTA, keeping at least 8 K-blocks per split

@@ -46,13 +46,22 @@ CUtensorMap make_tmap_bf16_2d(const void* base, uint64_t rows, uint64_t cols, ui
 }
 
 int sm_count() {
-  static int n = 0;
+  static int cache[64] = {0};
+  int dev = 0;
+  B200W_CUDA(cudaGetDevice(&dev));
+  int& n = cache[dev & 63];
   if (!n) {
-    int dev = 0;
-    B200W_CUDA(cudaGetDevice(&dev));
-    B200W_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    int v = 0;
+    B200W_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    n = v;
   }
   return n;
 }
+
+namespace {
+thread_local int g_sm_reserve = 0;
+}
+void gemm_set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : n; }
+int gemm_sm_reserve() { return g_sm_reserve; }
 
 }  // namespace b200w

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <stdexcept>
 #include <string>
 
@@ -34,6 +35,35 @@ struct Error : std::runtime_error {
 CUtensorMap make_tmap_bf16_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                               uint32_t box_rows, uint32_t box_cols);
 
+// SM count of the CURRENT device (cached per device: a process may hold contexts on several GPUs)
 int sm_count();
+
+// First-use work that is per DEVICE, not per process: cudaFuncSetAttribute(MaxDynamicSharedMemorySize)
+// applies to the current device only, so a process-wide `static bool` breaks the second GPU of a
+// one-process-many-contexts host (INTEGRATION.md's cgo layout).
+//   static PerDeviceOnce once; once.run([&] { cudaFuncSetAttribute(...); });
+class PerDeviceOnce {
+ public:
+  template <typename F>
+  void run(F&& f) {
+    int dev = 0;
+    B200W_CUDA(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    std::lock_guard<std::mutex> lock(mu_);
+    if (done_ & bit) return;
+    f();
+    done_ |= bit;
+  }
+
+ private:
+  std::mutex mu_;
+  uint64_t done_ = 0;
+};
+
+// gemm_bf16 leaves this many SMs free (grid = SMs - reserve): set around the backward that runs
+// concurrently with the NCCL gradient all-reduce, so that NCCL's CTAs find SMs without waiting for a
+// persistent GEMM CTA to end and the GEMM's CTAs never queue behind NCCL's. Per host thread.
+void gemm_set_sm_reserve(int n);
+int gemm_sm_reserve();
 
 }  // namespace b200w

@@ -572,12 +572,11 @@ int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* posit
     const int slices = ATT_THREADS / (dh / 8);   // staging area: slices * ATT_GT * dh floats
     const int sc_stride = std::max(a.max_ctx, slices * dh);
     const size_t att_smem = (static_cast<size_t>(ATT_GT) * dh + static_cast<size_t>(ATT_GT) * sc_stride + 32) * 4;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce once;
+    once.run([&] {
       B200W_CUDA(cudaFuncSetAttribute(decode_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       B200W_CUDA(cudaFuncSetAttribute(decode_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
-    }
+    });
     B200W_CHECK(att_smem <= 200 * 1024, "max_ctx too large for the decode attention kernel");
 
     int64_t step_launches = 0;
@@ -591,7 +590,7 @@ int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* posit
     B200W_CUDA(cudaMemcpyAsync(m->slot, m->pin + 2 * B, n * 4, cudaMemcpyHostToDevice, s));
     bf16* h = m->h;
     bf16* h2 = m->h2;
-    embed_fwd(m->tok, m->w + m->p_embed, h, n, d, V, s); ++nl;
+    embed_fwd(m->tok, m->w + m->p_embed, nullptr, h, n, d, V, 1, 0, s); ++nl;
     auto gemm = [&](const bf16* A, int K, size_t woff, int N, bf16* D, const bf16* C, int act = 0) {
       gemm_decode(A, m->w + woff, D, C, m->ws, m->counters, n, N, K, N, act, s); ++nl;
     };

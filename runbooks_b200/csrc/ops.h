@@ -32,10 +32,13 @@ void attention_bwd(const void* qkv, int ld_qkv, int k_off, int v_off, const void
                    int S, int H, int Hkv, float scale, cudaStream_t s);
 
 // ---- ops.cu --------------------------------------------------------------------------------
-void embed_fwd(const int32_t* ids, const void* table, void* out, int T, int d, int vocab,
-               cudaStream_t s);
-void embed_bwd(const int32_t* ids, const void* dout, float* dtable, int T, int d, int vocab,
-               cudaStream_t s);
+// out[t] = table[ids[t]] (+ pos_table[t % S + pos_offset] when pos_table != nullptr: OPT's learned
+// positions). embed_bwd: dtable[ids[t]] += dout[t] unless ids[t] == pad_id (nn.Embedding padding_idx;
+// -1 = none); dpos (nullable) receives the position-table gradient. fp32 atomics.
+void embed_fwd(const int32_t* ids, const void* table, const void* pos_table, void* out, int T, int d,
+               int vocab, int S, int pos_offset, cudaStream_t s);
+void embed_bwd(const int32_t* ids, const void* dout, float* dtable, float* dpos, int T, int d, int vocab,
+               int pad_id, int S, int pos_offset, cudaStream_t s);
 
 void rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int T, int d, float eps,
                  cudaStream_t s);
@@ -61,21 +64,39 @@ void swiglu_bwd(const void* dh, const void* gu, void* dgu, int T, int f, cudaStr
 void ce_shift_targets(const int32_t* labels, int32_t* targets, int T, int S, cudaStream_t s);
 // logits [T,V] bf16 -> per-token nll (fp32, 0 where target == -100); logits are overwritten IN
 // PLACE by dlogits = (softmax - onehot) * inv_n (bf16).
-void ce_loss_fwd_bwd(void* logits, const int32_t* targets, float* nll, int T, int V, float inv_n,
+// inv_n: DEVICE scalar (with a communicator it is 1 / the all-reduced target count, which never
+// visits the host).
+void ce_loss_fwd_bwd(void* logits, const int32_t* targets, float* nll, int T, int V, const float* inv_n,
                      cudaStream_t s);
-// out[0] += scale * sum(x[0..n)) ; deterministic single-block reduction
-void reduce_sum_f32(const float* x, float* out, int n, float scale, cudaStream_t s);
+// out[0] += scale[0] * sum(x[0..n)) ; deterministic single-block reduction; scale: DEVICE scalar
+void reduce_sum_f32(const float* x, float* out, int n, const float* scale, cudaStream_t s);
 
-// sumsq[0] += sum(g^2) in double
-void grad_sumsq(const float* g, size_t n, double* sumsq, cudaStream_t s);
+// sumsq[0] += sum(g^2) in double. g: fp32, or bf16 when g_bf16 (the all-reduced wire copy)
+void grad_sumsq(const void* g, bool g_bf16, size_t n, double* sumsq, cudaStream_t s);
 // torch.optim.AdamW step over a flat parameter range; g is pre-multiplied by *gscale (device
 // scalar: the clip coefficient); writes the bf16 compute copy.
-void adamw_step(float* master, float* m, float* v, const float* g, void* w_bf16, size_t n,
+void adamw_step(float* master, float* m, float* v, const void* g, bool g_bf16, void* w_bf16, size_t n,
                 float lr, float beta1, float beta2, float eps, float wd, int step,
                 const float* gscale, cudaStream_t s);
 // gscale[0] = min(1, max_norm / (sqrt(sumsq * div^2) + 1e-6)) * div ; gnorm_out[0] = sqrt(sumsq)*div
 void clip_coef(const double* sumsq, float max_norm, float div, float* gscale, float* gnorm_out,
                cudaStream_t s);
+
+// LayerNorm with bias (OPT family). mean / rstd: fp32 [T], saved for the backward.
+void layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int T,
+                   int d, float eps, cudaStream_t s);
+// dx = (dresid ? dresid : 0) + dLN/dx; dw += sum dy * xhat, db += sum dy (fp32).
+// part: fp32 scratch [rmsnorm_bwd_blocks(T), 2 d]; three launches.
+void layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
+                   const void* dresid, void* dx, float* dw, float* db, float* part, int T, int d,
+                   cudaStream_t s);
+// x[t, c] = act(x[t, c] + bias[c]) in place over N columns of rows with stride ld. act: 0 none, 1 relu
+void bias_act(void* x, const void* bias, int T, int N, int ld, int act, cudaStream_t s);
+// dz = dy * (act > 0): backward of ReLU from the saved post-activation; dz may alias dy
+void relu_bwd(const void* dy, const void* act, void* dz, size_t n, cudaStream_t s);
+// db[c] += sum_t dy[t, c] (fp32, deterministic). part: fp32 scratch [colsum_blocks(T), N]
+int colsum_blocks(int T);
+void colsum_add(const void* dy, float* db, float* part, int T, int N, int ld, cudaStream_t s);
 
 void attn_bwd_delta(const void* out, const void* dout, int ld, float* delta, int T, int H,
                     cudaStream_t s);

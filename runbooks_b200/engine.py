@@ -6,13 +6,23 @@ bench.py drive. It holds no arithmetic; every number comes out of libb200w.so.
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, asdict
+from dataclasses import dataclass
 from typing import Dict, Iterable, Optional, Tuple
 
 import numpy as np
 
 from . import _lib
 from ._lib import Arch as _CArch, HParams as _CHParams, B200WError
+
+
+FAMILY_LLAMA, FAMILY_FALCON, FAMILY_OPT = 0, 1, 2
+
+
+def _reject(cond: bool, what: str):
+    """An unimplemented setting that changes the arithmetic must fail the Job, never be ignored
+    (same policy as contract.load_params)."""
+    if cond:
+        raise ValueError(f"unsupported checkpoint config: {what}")
 
 
 @dataclass
@@ -28,6 +38,9 @@ class LlamaArch:
     max_seq_len: int = 4096    # sequences are packed to this length
     rms_norm_eps: float = 1e-5
     rope_theta: float = 10000.0
+    pad_token_id: int = -1     # nn.Embedding(padding_idx): that row gets no lookup gradient; -1 = None
+    family = FAMILY_LLAMA
+    max_positions = 0
 
     @classmethod
     def llama2_7b(cls, seq_len: int = 4096) -> "LlamaArch":
@@ -36,9 +49,18 @@ class LlamaArch:
     @classmethod
     def from_hf_config(cls, cfg: dict, seq_len: Optional[int] = None) -> "LlamaArch":
         if cfg.get("model_type", "llama") != "llama":
-            raise ValueError(f"unsupported model_type {cfg.get('model_type')!r} (llama only)")
+            raise ValueError(f"unsupported model_type {cfg.get('model_type')!r} (llama / opt)")
         heads = cfg["num_attention_heads"]
         rope = cfg.get("rope_parameters") or {}
+        scaling = cfg.get("rope_scaling") or {}
+        rope_type = rope.get("rope_type") or scaling.get("rope_type") or scaling.get("type") or "default"
+        _reject(rope_type != "default", f"rope_type {rope_type!r} (only the default rotary embedding is built)")
+        _reject(bool(cfg.get("attention_bias")), "attention_bias=true")
+        _reject(bool(cfg.get("mlp_bias")), "mlp_bias=true")
+        _reject(cfg.get("hidden_act", "silu") != "silu", f"hidden_act {cfg.get('hidden_act')!r}")
+        _reject(bool(cfg.get("tie_word_embeddings")), "tie_word_embeddings=true for a Llama checkpoint")
+        _reject(cfg.get("sliding_window") not in (None, 0), "sliding_window attention")
+        pad = cfg.get("pad_token_id")
         return cls(
             vocab_size=cfg["vocab_size"], hidden_size=cfg["hidden_size"],
             intermediate_size=cfg["intermediate_size"], num_layers=cfg["num_hidden_layers"],
@@ -47,10 +69,11 @@ class LlamaArch:
             max_seq_len=seq_len or cfg.get("max_position_embeddings", 4096),
             rms_norm_eps=cfg.get("rms_norm_eps", 1e-6),
             rope_theta=float(cfg.get("rope_theta") or rope.get("rope_theta") or 10000.0),
+            pad_token_id=-1 if pad is None else int(pad),
         )
 
     def to_hf_config(self) -> dict:
-        return {
+        cfg = {
             "architectures": ["LlamaForCausalLM"], "model_type": "llama",
             "vocab_size": self.vocab_size, "hidden_size": self.hidden_size,
             "intermediate_size": self.intermediate_size, "num_hidden_layers": self.num_layers,
@@ -60,6 +83,93 @@ class LlamaArch:
             "hidden_act": "silu", "tie_word_embeddings": False, "attention_bias": False,
             "mlp_bias": False, "torch_dtype": "bfloat16",
         }
+        if self.pad_token_id >= 0:
+            cfg["pad_token_id"] = self.pad_token_id
+        return cfg
+
+    def c_fields(self) -> dict:
+        return dict(vocab_size=self.vocab_size, hidden_size=self.hidden_size,
+                    intermediate_size=self.intermediate_size, num_layers=self.num_layers,
+                    num_heads=self.num_heads, num_kv_heads=self.num_kv_heads, head_dim=self.head_dim,
+                    max_seq_len=self.max_seq_len, rms_norm_eps=self.rms_norm_eps, rope_theta=self.rope_theta,
+                    family=self.family, pad_token_id=self.pad_token_id, max_positions=self.max_positions)
+
+
+@dataclass
+class OptArch:
+    """facebook/opt-125m family (HF models/opt/modeling_opt.py; the reference's config #1,
+    examples/facebook-opt-125m/finetuned-model.yaml): learned positions at +2, pre-LayerNorm with bias,
+    biased projections, ReLU MLP, lm_head tied to the token embedding."""
+    vocab_size: int
+    hidden_size: int
+    intermediate_size: int     # ffn_dim
+    num_layers: int
+    num_heads: int
+    max_positions: int = 2048  # max_position_embeddings (the table holds 2 more rows)
+    max_seq_len: int = 2048    # packed sequence length, <= max_positions, multiple of 128
+    layer_norm_eps: float = 1e-5
+    pad_token_id: int = 1
+    family = FAMILY_OPT
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_heads
+
+    @property
+    def num_kv_heads(self) -> int:
+        return self.num_heads
+
+    @classmethod
+    def opt_125m(cls, seq_len: int = 2048) -> "OptArch":
+        return cls(50272, 768, 3072, 12, 12, 2048, seq_len)
+
+    @classmethod
+    def from_hf_config(cls, cfg: dict, seq_len: Optional[int] = None) -> "OptArch":
+        if cfg.get("model_type") != "opt":
+            raise ValueError(f"unsupported model_type {cfg.get('model_type')!r}")
+        d = cfg["hidden_size"]
+        _reject(not cfg.get("do_layer_norm_before", True), "do_layer_norm_before=false (opt-350m layout)")
+        _reject(cfg.get("word_embed_proj_dim", d) != d, "word_embed_proj_dim != hidden_size (project_in/out)")
+        _reject(cfg.get("activation_function", "relu") != "relu", f"activation_function {cfg.get('activation_function')!r}")
+        _reject(not cfg.get("enable_bias", True), "enable_bias=false")
+        _reject(not cfg.get("layer_norm_elementwise_affine", True), "layer_norm_elementwise_affine=false")
+        _reject(cfg.get("_remove_final_layer_norm", False), "_remove_final_layer_norm")
+        _reject(not cfg.get("tie_word_embeddings", True), "untied lm_head for an OPT checkpoint")
+        _reject((d // cfg["num_attention_heads"]) not in (64, 128), "head_dim other than 64 / 128")
+        maxpos = cfg.get("max_position_embeddings", 2048)
+        s = seq_len or maxpos
+        pad = cfg.get("pad_token_id", 1)
+        return cls(cfg["vocab_size"], d, cfg.get("ffn_dim", 4 * d), cfg["num_hidden_layers"],
+                   cfg["num_attention_heads"], maxpos, min(s, maxpos), 1e-5, -1 if pad is None else int(pad))
+
+    def to_hf_config(self) -> dict:
+        return {
+            "architectures": ["OPTForCausalLM"], "model_type": "opt", "vocab_size": self.vocab_size,
+            "hidden_size": self.hidden_size, "ffn_dim": self.intermediate_size,
+            "num_hidden_layers": self.num_layers, "num_attention_heads": self.num_heads,
+            "max_position_embeddings": self.max_positions, "word_embed_proj_dim": self.hidden_size,
+            "do_layer_norm_before": True, "activation_function": "relu", "enable_bias": True,
+            "layer_norm_elementwise_affine": True, "tie_word_embeddings": True, "dropout": 0.0,
+            "attention_dropout": 0.0, "layerdrop": 0.0, "pad_token_id": self.pad_token_id,
+            "bos_token_id": 2, "eos_token_id": 2, "torch_dtype": "bfloat16",
+        }
+
+    def c_fields(self) -> dict:
+        return dict(vocab_size=self.vocab_size, hidden_size=self.hidden_size,
+                    intermediate_size=self.intermediate_size, num_layers=self.num_layers,
+                    num_heads=self.num_heads, num_kv_heads=self.num_heads, head_dim=self.head_dim,
+                    max_seq_len=self.max_seq_len, rms_norm_eps=self.layer_norm_eps, rope_theta=0.0,
+                    family=self.family, pad_token_id=self.pad_token_id, max_positions=self.max_positions)
+
+
+def arch_from_hf_config(cfg: dict, seq_len: Optional[int] = None):
+    """config.json -> LlamaArch | OptArch; anything else (or any unimplemented variant) raises."""
+    mt = cfg.get("model_type", "llama")
+    if mt == "llama":
+        return LlamaArch.from_hf_config(cfg, seq_len)
+    if mt == "opt":
+        return OptArch.from_hf_config(cfg, seq_len)
+    raise ValueError(f"unsupported model_type {mt!r}: the fine-tune engine builds llama and opt")
 
 
 def _as_i32(a) -> np.ndarray:
@@ -78,7 +188,7 @@ class Engine:
         if st != 0:
             raise B200WError(st, (self._lib.b200w_last_error(None) or b"").decode())
         self._h = h
-        self.arch: Optional[LlamaArch] = None
+        self.arch = None   # LlamaArch | OptArch
         self.micro_batch = 0
 
     # -- plumbing -----------------------------------------------------------------------------
@@ -105,10 +215,10 @@ class Engine:
         self._check(self._lib.b200w_sync(self._h))
 
     # -- model --------------------------------------------------------------------------------
-    def init_model(self, arch: LlamaArch, micro_batch: int = 1, training: bool = True,
+    def init_model(self, arch, micro_batch: int = 1, training: bool = True,
                    max_grad_norm: float = 1.0, weight_decay: float = 0.0,
                    betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8):
-        ca = _CArch(**asdict(arch))
+        ca = _CArch(**arch.c_fields())
         hp = _CHParams()
         self._lib.b200w_default_hparams(C.byref(hp))
         hp.max_grad_norm, hp.weight_decay = max_grad_norm, weight_decay
@@ -125,7 +235,8 @@ class Engine:
         for i in range(n.value):
             self._check(self._lib.b200w_param_info(self._h, i, buf, 256, C.byref(r), C.byref(c)))
             name = buf.value.decode()
-            yield name, ((c.value,) if name.endswith("norm.weight") else (r.value, c.value))
+            one_d = r.value == 1 or c.value == 1      # norm weights, LayerNorm parameters, biases
+            yield name, ((r.value * c.value,) if one_d else (r.value, c.value))
 
     def load_tensor(self, name: str, arr: np.ndarray):
         """arr: float32, or uint16 holding raw bf16 bits."""

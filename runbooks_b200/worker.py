@@ -60,16 +60,17 @@ def plan_steps(n_seqs: int, params: TrainParams, world: int):
 
 
 def train_rank(rank: int, world: int, uid: bytes, content: str) -> None:
-    from .engine import Engine, LlamaArch
+    from .engine import Engine, arch_from_hf_config
 
     model_dir, data_dir = os.path.join(content, "model"), os.path.join(content, "data")
     out_dir = os.path.join(content, "artifacts")
     params = contract.load_params(os.path.join(content, "params.json"))
     hf_cfg = contract.read_hf_config(model_dir)
     seq_len = params.max_seq_length or min(4096, int(hf_cfg.get("max_position_embeddings", 4096)))
+    seq_len = min(seq_len, int(hf_cfg.get("max_position_embeddings", seq_len)))
     if seq_len % 128:
         raise ValueError(f"max_seq_length {seq_len} must be a multiple of 128")
-    arch = LlamaArch.from_hf_config(hf_cfg, seq_len)
+    arch = arch_from_hf_config(hf_cfg, seq_len)   # llama | opt; unimplemented variants raise
 
     t0 = time.time()
     eng = Engine(rank)
@@ -77,13 +78,24 @@ def train_rank(rank: int, world: int, uid: bytes, content: str) -> None:
                    weight_decay=params.weight_decay, betas=(params.adam_beta1, params.adam_beta2),
                    eps=params.adam_epsilon)
     wanted = {n for n, _ in eng.params()}
-    seen = set()
+    seen, unused = set(), []
+    t_load, load_bytes = time.time(), 0
     for name, arr in contract.iter_safetensors(model_dir):
+        name = contract.canonical_tensor_name(name, hf_cfg)
         if name in wanted:
             eng.load_tensor(name, arr)
             seen.add(name)
+            load_bytes += arr.nbytes
+        elif not contract.is_ignorable_tensor(name, hf_cfg):
+            unused.append(name)
     if wanted - seen:
         raise KeyError(f"checkpoint lacks {sorted(wanted - seen)[:3]} ... ({len(wanted - seen)} tensors)")
+    if unused:
+        # a tensor the engine does not consume (a bias on a "bias-free" layer, an adapter, ...) means the
+        # checkpoint's arithmetic is not the one that would be trained: fail the Job instead
+        raise ValueError(f"checkpoint holds tensors this engine does not use: {sorted(unused)[:4]} "
+                         f"({len(unused)} tensors)")
+    load_seconds = time.time() - t_load
     if world > 1:
         eng.comm_init(rank, world, uid)
 
@@ -95,7 +107,9 @@ def train_rank(rank: int, world: int, uid: bytes, content: str) -> None:
     per_rank = per_step // world
     warmup = contract.warmup_steps_for(total_steps, params.warmup_steps)
     if rank == 0:
-        log(event="start", model=hf_cfg.get("_name_or_path", "llama"), params=int(sum(np.prod(s) for _, s in eng.params())),
+        log(event="start", model=hf_cfg.get("_name_or_path", hf_cfg.get("model_type", "llama")),
+            params=int(sum(np.prod(s) for _, s in eng.params())),
+            checkpoint_read_gb_per_s=round(load_bytes / 1e9 / max(load_seconds, 1e-9), 3),
             sequences=int(len(ids)), seq_len=seq_len, world_size=world, total_steps=total_steps,
             global_batch=per_step, load_seconds=round(time.time() - t0, 2), device_gb=round(eng.device_bytes() / 1e9, 2),
             warmup_steps=warmup, ignored_params=sorted(params.extra))
@@ -130,11 +144,16 @@ def train_rank(rank: int, world: int, uid: bytes, content: str) -> None:
 
 def save(eng, hf_cfg, out_dir, model_dir, step):
     t = time.time()
+    plist = list(eng.params())
+    sizes = {n: int(np.prod(s)) * 2 for n, s in plist}
     files = contract.save_hf_checkpoint(
-        out_dir, hf_cfg, ((n, eng.read_tensor(n, s, bf16_bits=True)) for n, s in eng.params()), copy_from=model_dir)
+        out_dir, hf_cfg, ((n, eng.read_tensor(n, s, bf16_bits=True)) for n, s in plist), copy_from=model_dir,
+        sizes=sizes)
     with open(os.path.join(out_dir, "trainer_state.json"), "w") as f:
         json.dump({"global_step": step}, f)
-    log(event="save", dir=out_dir, files=files, seconds=round(time.time() - t, 2))
+    secs = time.time() - t
+    log(event="save", dir=out_dir, files=files, seconds=round(secs, 2),
+        write_gb_per_s=round(sum(sizes.values()) / 1e9 / max(secs, 1e-9), 3))
 
 
 def _rank_main(rank, world, uid, content, q):

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     lib = C.CDLL(lib_path)
     for s in header_symbols():
         assert hasattr(lib, s), f"libb200w.so does not export {s}"
-    assert lib.b200w_abi_version() == 1
+    assert lib.b200w_abi_version() == 2
 
 
 def test_python_prototypes_cover_the_header(lib_path):

@@ -119,6 +119,71 @@ def test_two_train_steps_match_hf(case, micro):
     e.close()
 
 
+def test_trainer_step_count_padding_idx_and_decay_groups():
+    """The three places where round 1 deviated from HF Trainer, against the golden produced by the real
+    HF objects (oracle/make_golden.py run_trainer_case): num_items_in_batch counted on the UNSHIFTED
+    labels (trainer.py:2136), nn.Embedding(padding_idx=config.pad_token_id), and weight_decay applied
+    to Trainer's decay group only (norm weights excluded)."""
+    fx = np.load("tests/golden/llama_tiny_trainer.npz")
+    v = [int(x) for x in fx["arch"]]
+    eps, theta = (float(x) for x in fx["arch_f"])
+    pad, wd = int(fx["pad_token_id"]), float(fx["weight_decay"])
+    oa = O.Arch(*v, rms_norm_eps=eps, rope_theta=theta, pad_token_id=pad)
+    arch = LlamaArch(*v, rms_norm_eps=eps, rope_theta=theta, pad_token_id=pad)
+    B, seed = (int(x) for x in fx["batch"])
+    params = O.seeded_params(oa, seed)
+    assert int(fx["num_items"]) == int((fx["labels"] != -100).sum())          # unshifted count ...
+    assert int(fx["num_items"]) > int((fx["labels"][:, 1:] != -100).sum())    # ... which differs here
+    e = Engine(0)
+    e.init_model(arch, micro_batch=B, training=True, weight_decay=wd)
+    e.load_state_dict(params)
+    loss = e.forward_backward(fx["ids"], fx["labels"])
+    assert abs(loss - float(fx["loss"])) < 1e-3 * float(fx["loss"])
+    g = e.read_state("model.embed_tokens.weight", params["model.embed_tokens.weight"].shape, "grad")
+    assert float(np.abs(g[pad]).max()) == 0.0 and float(np.abs(fx["pad_row_grad"]).max()) == 0.0
+    assert rel_err(g.reshape(-1)[::61], fx["grad/model.embed_tokens.weight"]) < 3e-2
+    e.close()
+    e = Engine(0)
+    e.init_model(arch, micro_batch=1, training=True, weight_decay=wd)
+    e.load_state_dict(params)
+    lr1, lr2 = (float(x) for x in fx["lrs"])     # 1e-3 / 5e-4: makes the decay visible above bf16 noise
+    loss1, gn1 = e.train_step(fx["ids"], fx["labels"], lr=lr1)
+    loss2, gn2 = e.train_step(fx["ids2"], fx["labels2"], lr=lr2)
+    assert abs(loss1 - float(fx["loss"])) < 1e-3 * float(fx["loss"])
+    assert abs(loss2 - float(fx["loss2"])) < 3e-3 * float(fx["loss2"])   # after a 1e-3 Adam step of bf16-noisy grads
+    assert abs(gn1 - float(fx["gnorm"])) < 5e-3 * float(fx["gnorm"])
+    worst = 0.0
+    for name, shape in e.params():
+        w = e.read_state(name, shape, "master").reshape(-1)[::61]
+        worst = max(worst, rel_err(w, fx["param2/" + name]))
+    print(f"trainer golden: updated weights rel_err {worst:.3e} (weight_decay {wd}, no-decay group {list(fx['no_decay'])[:2]}...)")
+    assert worst < 2.5e-2   # an lr 1e-3 Adam step is ~lr * sign(g) on weights of std 0.02: 5 % moves, sign-noise dominated
+    e.close()
+
+
+def test_weight_decay_follows_trainer_parameter_groups():
+    """Noise-free check of the decay grouping: the same step with weight_decay 0 and 0.5 differs by
+    exactly -lr * wd * w on decayed tensors and by nothing on Trainer's no-decay group (norm weights;
+    trainer.py:1280-1290). Round 1 decayed the whole flat parameter space."""
+    fx, oa, arch, B, seed = _load("llama_tiny_mha")
+    params = O.seeded_params(oa, seed)
+    lr, wd = 1e-3, 0.5
+    out = {}
+    for w_ in (0.0, wd):
+        e = Engine(0)
+        e.init_model(arch, micro_batch=B, training=True, weight_decay=w_)
+        e.load_state_dict(params)
+        e.train_step(fx["ids"], fx["labels"], lr=lr)
+        out[w_] = {n: e.read_state(n, s, "master") for n, s in e.params()}
+        e.close()
+    for name, w0 in params.items():
+        diff = out[wd][name] - out[0.0][name]
+        if O.decays(name):
+            assert rel_err(diff, -lr * wd * w0) < 1e-3, name
+        else:
+            assert float(np.abs(diff).max()) <= 1e-7, name     # embed_bwd's fp32 atomics reorder: clip coef moves by 1 ulp
+
+
 def test_engine_rejects_bad_batches():
     from runbooks_b200._lib import B200WError
     fx, oa, arch, B, seed = _load("llama_tiny_mha")

@@ -19,13 +19,92 @@ def test_embed_fwd_bwd(engine):
     table = torch.randn(V, d, generator=G(0)).bfloat16()
     ids = torch.randint(0, V, (T,), generator=G(1), dtype=torch.int32)
     out = torch.empty(T, d, device="cuda", dtype=torch.bfloat16)
-    call(engine, "b200w_op_embed_fwd", ids.cuda(), dev(table), out, T, d, V)
+    call(engine, "b200w_op_embed_fwd", ids.cuda(), dev(table), None, out, T, d, V, T, 0)
     assert torch.equal(out.cpu(), table[ids.long()])  # a gather is bit-exact
     dout = torch.randn(T, d, generator=G(2)).bfloat16()
     dtab = torch.zeros(V, d, device="cuda", dtype=torch.float32)
-    call(engine, "b200w_op_embed_bwd", ids.cuda(), dev(dout), dtab, T, d, V)
+    call(engine, "b200w_op_embed_bwd", ids.cuda(), dev(dout), dtab, None, T, d, V, -1, T, 0)
     ref = torch.zeros(V, d).index_add_(0, ids.long(), dout.float())
     assert rel_err(dtab, ref) < 1e-6
+    # nn.Embedding(padding_idx=7): that row receives no gradient from the lookup
+    dtab.zero_()
+    call(engine, "b200w_op_embed_bwd", ids.cuda(), dev(dout), dtab, None, T, d, V, 7, T, 0)
+    ref[7] = 0
+    assert rel_err(dtab, ref) < 1e-6 and float(dtab[7].abs().max()) == 0.0
+
+
+def test_embed_with_learned_positions(engine):
+    """OPT: token row + position row (t % S) + 2 (HF modeling_opt.py OPTLearnedPositionalEmbedding)."""
+    V, d, S, B = 200, 128, 64, 3
+    T = B * S
+    table = (0.05 * torch.randn(V, d, generator=G(0))).bfloat16()
+    pos = (0.05 * torch.randn(S + 2, d, generator=G(1))).bfloat16()
+    ids = torch.randint(0, V, (T,), generator=G(2), dtype=torch.int32)
+    out = torch.empty(T, d, device="cuda", dtype=torch.bfloat16)
+    call(engine, "b200w_op_embed_fwd", ids.cuda(), dev(table), dev(pos), out, T, d, V, S, 2)
+    p_idx = torch.arange(T) % S + 2
+    ref = table[ids.long()].float() + pos[p_idx].float()
+    assert rel_err(out.float(), ref) < 3e-3
+    dout = torch.randn(T, d, generator=G(3)).bfloat16()
+    dtab = torch.zeros(V, d, device="cuda", dtype=torch.float32)
+    dpos = torch.zeros(S + 2, d, device="cuda", dtype=torch.float32)
+    call(engine, "b200w_op_embed_bwd", ids.cuda(), dev(dout), dtab, dpos, T, d, V, 1, S, 2)
+    rt = torch.zeros(V, d).index_add_(0, ids.long(), dout.float())
+    rt[1] = 0
+    rp = torch.zeros(S + 2, d).index_add_(0, p_idx, dout.float())
+    assert rel_err(dtab, rt) < 1e-6 and rel_err(dpos, rp) < 1e-6
+
+
+@pytest.mark.parametrize("T,d", [(37, 128), (130, 768), (64, 4544), (5, 8192)])
+def test_layernorm_fwd_bwd(engine, T, d):
+    """oracle: torch.nn.functional.layer_norm (what OPTDecoderLayer / FalconDecoderLayer call)."""
+    x = torch.randn(T, d, generator=G(3)).bfloat16()
+    w = (1 + 0.1 * torch.randn(d, generator=G(4))).bfloat16()
+    b = (0.1 * torch.randn(d, generator=G(7))).bfloat16()
+    dy = torch.randn(T, d, generator=G(5)).bfloat16()
+    dres = torch.randn(T, d, generator=G(6)).bfloat16()
+    y = torch.empty(T, d, device="cuda", dtype=torch.bfloat16)
+    mean = torch.empty(T, device="cuda", dtype=torch.float32)
+    rstd = torch.empty(T, device="cuda", dtype=torch.float32)
+    call(engine, "b200w_op_layernorm_fwd", dev(x), dev(w), dev(b), y, mean, rstd, T, d, 1e-5)
+    xr, wr, br = (t.float().requires_grad_(True) for t in (x, w, b))
+    yr = torch.nn.functional.layer_norm(xr, (d,), wr, br, 1e-5)
+    assert rel_err(y.float(), yr.detach()) < 3e-3
+    assert rel_err(mean, x.float().mean(-1)) < 1e-5
+    yr.backward(dy.float())
+    dx = torch.empty(T, d, device="cuda", dtype=torch.bfloat16)
+    dw = torch.zeros(d, device="cuda", dtype=torch.float32)
+    db = torch.zeros(d, device="cuda", dtype=torch.float32)
+    call(engine, "b200w_op_layernorm_bwd", dev(dy), dev(x), dev(w), mean, rstd, dev(dres), dx, dw, db, T, d)
+    assert rel_err(dx.float(), xr.grad + dres.float()) < 3e-3
+    assert rel_err(dw, wr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+    call(engine, "b200w_op_layernorm_bwd", dev(dy), dev(x), dev(w), mean, rstd, None, dx, dw, db, T, d)
+    assert rel_err(dx.float(), xr.grad) < 3e-3
+    assert rel_err(dw, 2 * wr.grad) < 1e-4         # dw / db accumulate
+
+
+def test_bias_relu_and_their_backward(engine):
+    T, N, ld = 300, 1000, 1024
+    x = torch.randn(T, ld, generator=G(1)).bfloat16()
+    bias = torch.randn(N, generator=G(2)).bfloat16()
+    for act in (0, 1):
+        xd = dev(x)
+        call(engine, "b200w_op_bias_act", xd, dev(bias), T, N, ld, act)
+        ref = x.float().clone()
+        ref[:, :N] += bias.float()
+        if act:
+            ref[:, :N] = ref[:, :N].relu()
+        assert torch.equal(xd.cpu(), ref.bfloat16())   # pad columns [N, ld) untouched
+    a = torch.randn(T, N, generator=G(3)).relu().bfloat16()
+    dy = torch.randn(T, N, generator=G(4)).bfloat16()
+    dz = torch.empty(T, N, device="cuda", dtype=torch.bfloat16)
+    call(engine, "b200w_op_relu_bwd", dev(dy), dev(a), dz, T * N)
+    assert torch.equal(dz.cpu(), torch.where(a > 0, dy, torch.zeros_like(dy)))
+    db = torch.zeros(N, device="cuda", dtype=torch.float32)
+    call(engine, "b200w_op_colsum", dev(x), db, T, N, ld)
+    assert rel_err(db, x.float()[:, :N].sum(0)) < 1e-5
+    call(engine, "b200w_op_colsum", dev(x), db, T, N, ld)      # accumulates
+    assert rel_err(db, 2 * x.float()[:, :N].sum(0)) < 1e-5
 
 
 @pytest.mark.parametrize("T,d", [(37, 256), (130, 4096), (5, 8192), (64, 520)])
@@ -151,11 +230,11 @@ def test_adamw_and_grad_norm(engine):
     wd_ = torch.empty(n, device="cuda", dtype=torch.bfloat16)
     norm = __import__("ctypes").c_float()
     import ctypes as C
-    call(engine, "b200w_op_grad_norm", gd, n, C.byref(norm))
+    call(engine, "b200w_op_grad_norm", gd, 0, n, C.byref(norm))
     assert abs(norm.value - float(g.norm())) < 1e-5 * float(g.norm())
     pr, mr, vr = p.clone(), m.clone(), v.clone()
     for step, (lr, gs) in enumerate([(5e-5, 0.7), (2.5e-5, 1.0), (1e-5, 0.3)], start=1):
-        call(engine, "b200w_op_adamw", pd, md, vd, gd, wd_, n, lr, 0.9, 0.999, 1e-8, 0.01, step, gs)
+        call(engine, "b200w_op_adamw", pd, md, vd, gd, 0, wd_, n, lr, 0.9, 0.999, 1e-8, 0.01, step, gs)
         pr, mr, vr = O.adamw_update(pr, g * gs, mr, vr, step, lr, wd=0.01)
     # v = EMA of g^2: fp32 FMA contraction differs from torch's separate mul/add (1e-5 level)
     assert rel_err(pd, pr) < 1e-6 and rel_err(md, mr) < 1e-5 and rel_err(vd, vr) < 1e-4
@@ -175,6 +254,6 @@ def test_adamw_matches_torch_optimizer(engine):
     for step, g in enumerate(grads, start=1):
         tp.grad = g.clone()
         opt.step()
-        call(engine, "b200w_op_adamw", pd, md, vd, dev(g, torch.float32), wd_, n, 5e-5, 0.9, 0.999, 1e-8,
+        call(engine, "b200w_op_adamw", pd, md, vd, dev(g, torch.float32), 0, wd_, n, 5e-5, 0.9, 0.999, 1e-8,
              0.0, step, 1.0)
     assert rel_err(pd.cpu() - p0, tp.detach() - p0) < 1e-4

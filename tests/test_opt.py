@@ -1,0 +1,124 @@
+"""The reference's config #1 family (facebook/opt-125m: examples/facebook-opt-125m/finetuned-model.yaml,
+SURVEY.md 8 a15) through the CUDA fine-tune engine, against the golden captured from the real HF
+OPTForCausalLM + torch.optim.AdamW (tests/golden/opt_tiny.npz, oracle/make_golden.py run_opt) and the
+fp32 oracle restatement (oracle/opt_oracle.py). head_dim is 64: on the device every head is stored
+zero-padded to 128 so that the dh = 128 tcgen05 attention kernels serve it; load /
+read_tensor see the dense HF shapes.
+
+Tolerances as in tests/test_engine.py: loss / grad-norm / updated weights 1e-3 (north_star), logits
+1.5e-2, gradients 3e-2 relative Frobenius (bf16 compute vs fp32 golden)."""
+import numpy as np
+import pytest
+
+from oracle import opt_oracle as OO
+from util import bf16_bits, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _load():
+    from runbooks_b200.engine import OptArch
+    fx = np.load("tests/golden/opt_tiny.npz")
+    V, d, f, L, H, P = (int(x) for x in fx["arch"])
+    oa = OO.OptArch(V, d, f, L, H, P)
+    S = fx["ids"].shape[1]
+    arch = OptArch(V, d, f, L, H, max_positions=P, max_seq_len=S, pad_token_id=oa.pad_token_id)
+    return fx, oa, arch, OO.seeded_params(oa, int(fx["seed"]))
+
+
+def _engine(arch, params, micro_batch, **kw):
+    from runbooks_b200.engine import Engine
+    e = Engine(0)
+    e.init_model(arch, micro_batch=micro_batch, training=True, **kw)
+    e.load_state_dict(params)
+    return e
+
+
+def test_opt_load_read_round_trip_through_the_padded_layout():
+    fx, oa, arch, params = _load()
+    e = _engine(arch, params, 2)
+    for name, shape in e.params():
+        assert tuple(shape) == params[name].shape, name
+        assert np.array_equal(e.read_tensor(name, shape), params[name]), name            # fp32 master
+        assert np.array_equal(e.read_tensor(name, shape, bf16_bits=True), bf16_bits(params[name])), name
+    e.close()
+
+
+def test_opt_forward_logits_and_greedy():
+    fx, oa, arch, params = _load()
+    e = _engine(arch, params, 2)
+    logits, nll, _ = e.forward(fx["ids"], fx["labels"])
+    gold = fx["logits"].reshape(-1, oa.vocab_size)
+    err = rel_err(logits, gold)
+    print(f"opt: logits rel_err {err:.3e}")
+    assert err < 1.5e-2
+    top2 = np.sort(gold, axis=-1)[:, -2:]
+    safe = (top2[:, 1] - top2[:, 0]) > 2 * np.abs(logits - gold).max()
+    assert safe.mean() > 0.3
+    assert np.array_equal(logits.argmax(-1)[safe], gold.argmax(-1)[safe])   # bit-exact greedy ids
+    e.close()
+
+
+def test_opt_gradients_match_hf():
+    fx, oa, arch, params = _load()
+    e = _engine(arch, params, 2)
+    loss = e.forward_backward(fx["ids"], fx["labels"])
+    assert abs(loss - float(fx["loss"])) < 1e-3 * float(fx["loss"])
+    worst = 0.0
+    for name, shape in e.params():
+        g = e.read_state(name, shape, "grad")
+        gn_hf = float(fx["gradnorm/" + name])
+        if name.endswith("k_proj.bias"):
+            # mathematically zero (softmax is invariant to a per-query constant): both sides hold rounding noise
+            assert np.linalg.norm(g) < 1e-3 * float(fx["gnorm"]), name
+            continue
+        err = rel_err(g.reshape(-1)[::17], fx["grad/" + name])
+        worst = max(worst, err)
+        assert err < 3e-2, (name, err)
+        assert abs(float(np.linalg.norm(g.astype(np.float64))) - gn_hf) < 1e-2 * gn_hf, name
+    # nn.Embedding(padding_idx): the pad row's gradient is the tied head's contribution only
+    print(f"opt: worst gradient rel_err {worst:.3e}")
+    e.close()
+
+
+@pytest.mark.parametrize("micro", ["full", "accumulate"])
+def test_opt_two_train_steps_match_hf(micro):
+    fx, oa, arch, params = _load()
+    e = _engine(arch, params, 2 if micro == "full" else 1)
+    loss1, gn1 = e.train_step(fx["ids"], fx["labels"], lr=5e-5)
+    loss2, gn2 = e.train_step(fx["ids2"], fx["labels2"], lr=2.5e-5)
+    print(f"opt/{micro}: loss {loss1:.6f}/{loss2:.6f} (HF {float(fx['loss']):.6f}/{float(fx['loss2']):.6f}) "
+          f"gnorm {gn1:.5f}/{gn2:.5f} (HF {float(fx['gnorm']):.5f}/{float(fx['gnorm2']):.5f})")
+    assert abs(loss1 - float(fx["loss"])) < 1e-3 * float(fx["loss"])
+    assert abs(loss2 - float(fx["loss2"])) < 1e-3 * float(fx["loss2"])
+    assert abs(gn1 - float(fx["gnorm"])) < 5e-3 * float(fx["gnorm"])
+    assert abs(gn2 - float(fx["gnorm2"])) < 5e-3 * float(fx["gnorm2"])
+    worst = 0.0
+    for name, shape in e.params():
+        if name.endswith("k_proj.bias"):
+            continue     # zero gradient + Adam = +-lr noise on both sides (oracle/opt_oracle.py header)
+        w = e.read_state(name, shape, "master").reshape(-1)[::17]
+        worst = max(worst, rel_err(w, fx["param2/" + name]))
+        wb = e.read_tensor(name, shape, bf16_bits=True).reshape(-1)[::17]
+        assert np.array_equal(wb, bf16_bits(w)), name
+    print(f"opt/{micro}: updated weights rel_err {worst:.3e}")
+    assert worst < 1e-3
+    e.close()
+
+
+def test_opt_head_padding_stays_zero():
+    """Every gradient that reaches the zero padding of a 64-wide head is exactly zero, so AdamW leaves it
+    at zero: after two steps the padded rows / columns of the device layout still hold 0 -- checked
+    through the grads of the padded tensors being dense-equal to a model that never had padding (the HF
+    golden above) and through a forward that still matches after training."""
+    fx, oa, arch, params = _load()
+    e = _engine(arch, params, 2, weight_decay=0.01)
+    e.train_step(fx["ids"], fx["labels"], lr=5e-5)
+    e.train_step(fx["ids2"], fx["labels2"], lr=2.5e-5)
+    sd = {n: e.read_tensor(n, s) for n, s in e.params()}
+    logits, _, _ = e.forward(fx["ids"], fx["labels"])
+    # reload the dense tensors into a fresh engine: identical logits only if the padding held no signal
+    e2 = _engine(arch, sd, 2)
+    logits2, _, _ = e2.forward(fx["ids"], fx["labels"])
+    assert np.array_equal(logits, logits2)
+    e.close(); e2.close()

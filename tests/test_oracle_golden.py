@@ -43,6 +43,37 @@ def test_two_steps_match_hf(case):
         assert rel(r2["params"][k].reshape(-1)[::61] - w0, fx["param2/" + k] - w0) < 2e-3, k
 
 
+def test_trainer_step_semantics_match_hf():
+    """The Trainer step details that round 1 got wrong, pinned by the real HF objects
+    (oracle/make_golden.py run_trainer_case): num_items_in_batch on the UNSHIFTED labels
+    (trainer.py:2136), nn.Embedding(padding_idx=pad_token_id), weight decay on Trainer's decay group
+    only (trainer.py:1280-1290). fp32 vs fp32: tight bars."""
+    fx = np.load("tests/golden/llama_tiny_trainer.npz")
+    v = [int(x) for x in fx["arch"]]
+    eps, theta = (float(x) for x in fx["arch_f"])
+    a = O.Arch(*v, rms_norm_eps=eps, rope_theta=theta, pad_token_id=int(fx["pad_token_id"]))
+    params = O.seeded_params(a, int(fx["batch"][1]))
+    wd = float(fx["weight_decay"])
+    lr1, lr2 = (float(x) for x in fx["lrs"])
+    assert O.trainer_num_items(fx["labels"]) == int(fx["num_items"])
+    assert sorted(k for k in params if not O.decays(k)) == sorted(str(x) for x in fx["no_decay"])
+    r1 = O.train_step(params, fx["ids"], fx["labels"], a, lr=lr1, step=1, weight_decay=wd)
+    assert abs(r1["loss"] - float(fx["loss"])) < 2e-5 * float(fx["loss"])
+    assert abs(r1["gnorm"] - float(fx["gnorm"])) < 2e-5 * float(fx["gnorm"])
+    assert float(np.abs(r1["grads"]["model.embed_tokens.weight"][a.pad_token_id]).max()) == 0.0
+    for k in params:
+        assert rel(r1["grads"][k].reshape(-1)[::61], fx["grad/" + k]) < 1e-4, k
+    r2 = O.train_step(r1["params"], fx["ids2"], fx["labels2"], a, lr=lr2, state=dict(m=r1["m"], v=r1["v"]), step=2,
+                      weight_decay=wd)
+    assert abs(r2["loss"] - float(fx["loss2"])) < 5e-5 * float(fx["loss2"])
+    for k in params:
+        assert rel(r2["params"][k].reshape(-1)[::61], fx["param2/" + k]) < 2e-5, k
+    # the shifted-label count (what model(ids, labels) alone divides by) is a different number here
+    shifted = O.train_step(params, fx["ids"], fx["labels"], a, lr=lr1)["loss"] * int(fx["num_items"]) / int(
+        (fx["labels"][:, 1:] != -100).sum())
+    assert abs(shifted - float(fx["loss"])) > 1e-3 * float(fx["loss"])
+
+
 def test_ops_match_hf_modules():
     fx = np.load("tests/golden/llama_ops.npz")
     y = O.rmsnorm(torch.tensor(fx["rms_x"]), torch.tensor(fx["rms_w"]), 1e-5)

@@ -192,6 +192,15 @@ B200W_API int b200w_infer_init_random(b200w_ctx* ctx, uint64_t seed, float std);
  * Prompt ingestion is the same call with the outputs of all but the last prompt token ignored. */
 B200W_API int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* positions,
                      const int32_t* slots, int n, int32_t* next_tokens, float* logits_out);
+/* Prompt ingestion in ONE pass: tokens HOST int32 [n_seqs, padded_len] (real tokens first, any valid id
+ * as padding after them), lengths[n_seqs] in 1..min(padded_len, max_ctx), padded_len a multiple of 128.
+ * K/V of the real positions land in cache slots[b] at positions [0, lengths[b]); next_tokens (HOST,
+ * n_seqs) = greedy token after each prompt; logits_out HOST float [n_seqs, vocab] or NULL. Runs the
+ * big-M tcgen05 GEMMs and the flash-attention forward of the fine-tune path instead of `length`
+ * sweeps over the weights. Decode continues with b200w_infer_step at position lengths[b]. */
+B200W_API int b200w_infer_prefill(b200w_ctx* ctx, const int32_t* tokens, const int32_t* lengths,
+                        const int32_t* slots, int n_seqs, int padded_len, int32_t* next_tokens,
+                        float* logits_out);
 B200W_API int64_t b200w_infer_device_bytes(b200w_ctx* ctx);
 
 /* ---- per-kernel hooks for the parity tests (DEVICE pointers, bf16 unless noted) ------------ */

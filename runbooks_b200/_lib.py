@@ -81,6 +81,7 @@ PROTOTYPES = {
     "b200w_infer_load_tensor": (C.c_int, [c_ctx, C.c_char_p, vp, C.c_int, C.c_int64]),
     "b200w_infer_init_random": (C.c_int, [c_ctx, C.c_uint64, C.c_float]),
     "b200w_infer_step": (C.c_int, [c_ctx, vp, vp, vp, C.c_int, vp, vp]),
+    "b200w_infer_prefill": (C.c_int, [c_ctx, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
     "b200w_infer_device_bytes": (C.c_int64, [c_ctx]),
     "b200w_op_gemm": (C.c_int, [c_ctx, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

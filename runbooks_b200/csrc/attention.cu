@@ -259,7 +259,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
       mbar_init(&bar_vfree[i], 1);
     }
     mbar_init(bar_o, 1);
-    mbar_init(bar_p, NCOMPUTE);
+    mbar_init(bar_p, NCOMPUTE / 32);
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(tmem_slot, FWD_TMEM_COLS);
@@ -350,25 +350,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
       mbar_wait(&bar_s[buf], (j >> 1) & 1);
       __syncwarp();
       tc_fence_after();
-      uint32_t sr[2][32];  // the whole 64-column row: both half-row threads derive the same max
-      tmem_ld32(tmem_base + buf * 64 + lane_base, sr[0]);
-      tmem_ld32(tmem_base + buf * 64 + lane_base + 32, sr[1]);
+      // the whole 64-column row is needed for the row max (both half-row threads derive the same one), but
+      // only `mine` is exponentiated: two separately named arrays, selected by ADDRESS (hc), keep everything
+      // in registers (round 1 indexed sr[hc] dynamically, which ptxas put in local memory: 44 B of spills)
+      uint32_t mine[32], other[32];
+      tmem_ld32(tmem_base + buf * 64 + lane_base + hc * 32, mine);
+      tmem_ld32(tmem_base + buf * 64 + lane_base + (hc ^ 1) * 32, other);
       tmem_ld_wait();
 
       const int col0 = j * FWD_BKV;
       const bool diag = (col0 + FWD_BKV - 1) > q0;  // block reaches past the first row's diagonal
       float mx = -INFINITY;
       if (diag) {
+        const int cm = col0 + hc * 32, co = col0 + (hc ^ 1) * 32;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          float s = __uint_as_float(sr[c >> 5][c & 31]);
-          if (col0 + c > row_seq) s = -INFINITY;
-          sr[c >> 5][c & 31] = __float_as_uint(s);
-          mx = fmaxf(mx, s);
+        for (int c = 0; c < 32; ++c) {
+          float sm_ = __uint_as_float(mine[c]);
+          if (cm + c > row_seq) sm_ = -INFINITY;
+          mine[c] = __float_as_uint(sm_);
+          float so_ = __uint_as_float(other[c]);
+          if (co + c > row_seq) so_ = -INFINITY;
+          mx = fmaxf(mx, fmaxf(sm_, so_));
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(sr[c >> 5][c & 31]));
+        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, fmaxf(__uint_as_float(mine[c]), __uint_as_float(other[c])));
       }
       mx *= scale_log2;  // scale > 0, so max commutes with it
       // lazy rescale: keep the old reference max unless the new one is > 2^8 above it. Block 0 always
@@ -383,9 +389,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
         float p8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          // sr[hc] is a compile-time-unknown index only through hc; keep both halves addressable
-          const float s = __uint_as_float(hc ? sr[1][c8 * 8 + e] : sr[0][c8 * 8 + e]);
-          p8[e] = ex2(fmaf(s, scale_log2, -m_new));
+          p8[e] = ex2(fmaf(__uint_as_float(mine[c8 * 8 + e]), scale_log2, -m_new));
           psum += p8[e];
         }
         pk[c8] = pack8(p8);
@@ -398,14 +402,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
         __syncwarp();
         tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {  // rare after the first blocks; my 64 of O's columns
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem_O + lane_base + hc * 64 + c * 32, r);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {  // 16 columns at a time: pk[] is live across this, registers are tight
+            uint32_t r[16];
+            tmem_ld16(tmem_O + lane_base + hc * 64 + c * 16, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st32(tmem_O + lane_base + hc * 64 + c * 32, r);
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st16(tmem_O + lane_base + hc * 64 + c * 16, r);
           }
           tmem_st_wait();
         }
@@ -415,7 +419,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
         *reinterpret_cast<uint4*>(sP + sw128_offset(row_local, hc * 4 + c8)) = pk[c8];
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      __syncwarp();                      // orders the other 31 lanes' writes before lane 0's arrive
+      if (lane == 0) mbar_arrive(bar_p);  // one arrival per compute warp (round 1: one per thread)
     }
 
     mbar_wait(bar_o, (njb - 1) & 1);
@@ -508,7 +513,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       mbar_init(&bar_s[i], 1);
       mbar_init(&bar_d[i], 1);
     }
-    for (int i = 0; i < KV_NBARP; ++i) mbar_init(&bar_p[i], BWD_NCOMPUTE);
+    for (int i = 0; i < KV_NBARP; ++i) mbar_init(&bar_p[i], BWD_NCOMPUTE / 32);
     fence_barrier_init();
   }
   if (warp == 16) tmem_alloc(tmem_slot, KV_TMEM_COLS);
@@ -518,15 +523,22 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_dV = tmem_base + 256, tmem_dK = tmem_base + 384;
 
-  auto iter_head = [&](int it) { return hk * G + it / nqb; };
-  auto iter_qrow = [&](int it) { return (2 * jb + it % nqb) * BWD_BQ; };  // inside the sequence
+  // iteration `it` = (query head hk*G + it / nqb, query block 2 jb + it % nqb): walked with running
+  // counters (a division and a modulo per thread and iteration showed up in the instruction census)
+  struct IterPos {
+    int h, qb;
+    __device__ __forceinline__ void next(int nqb_) { if (++qb == nqb_) { qb = 0; ++h; } }
+  };
+  const int qb_base = 2 * jb;
 
   if (warp == 17) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      auto load_q = [&](int it, int buf) {
+      IterPos ip{hk * G, 0};
+      auto load_q = [&](int buf) {  // loads the block at `ip`, then advances it
         mbar_arrive_expect_tx(&bar_q[buf], 4 * ATOM64);
-        const int h = iter_head(it), row = tok0 + iter_qrow(it);
+        const int h = ip.h, row = tok0 + (qb_base + ip.qb) * BWD_BQ;
+        ip.next(nqb);
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
           tma_load_2d(sQ + (buf * 2 + a) * ATOM64, &tm_qkv, &bar_q[buf], h * DH + a * 64, row);
@@ -543,14 +555,14 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           tma_load_2d(sV + a * ATOM128 + r * ATOM64, &tm_qkv, bar_kv, v_off + hk * DH + a * 64,
                       tok0 + kv0 + r * 64);
         }
-      load_q(0, 0);
-      if (n_iter > 1) load_q(1, 1);
-      if (n_iter > 2) load_q(2, 2);
+      load_q(0);
+      if (n_iter > 1) load_q(1);
+      if (n_iter > 2) load_q(2);
       int buf = 0;
       uint32_t par = 0;
       for (int it = 0; it + 3 < n_iter; ++it) {  // block it+3 reuses block it's buffer
         mbar_wait(&bar_qfree[buf], par);
-        load_q(it + 3, buf);
+        load_q(buf);
         if (++buf == 3) { buf = 0; par ^= 1; }
       }
     }
@@ -603,21 +615,22 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const uint32_t lane_base = (q * 32u) << 16;
     // lse / delta*scale of the 64 query rows of a block: fetched into a register one iteration
     // ahead by 128 of the compute threads, parked in smem just before the per-iteration bar.sync
-    auto fetch_stat = [&](int it) -> float {
-      const int h = iter_head(it);
-      const size_t base = static_cast<size_t>(h) * Ttot + tok0 + iter_qrow(it);
+    auto fetch_stat = [&](const IterPos& p) -> float {
+      const size_t base = static_cast<size_t>(p.h) * Ttot + tok0 + (qb_base + p.qb) * BWD_BQ;
       return (tid < 64) ? lse2[base + tid] : delta[base + tid - 64];
     };
     const float stat_mul = (tid < 64) ? 1.f : scale;  // delta is kept pre-multiplied by the scale
-    if (tid < 128) sStat[tid] = fetch_stat(0) * stat_mul;
+    IterPos cur{hk * G, 0};
+    if (tid < 128) sStat[tid] = fetch_stat(cur) * stat_mul;
     bwd_compute_bar_sync();
 
     for (int it = 0; it < n_iter; ++it) {
       const int tb = it & 1;
-      const int q_seq0 = iter_qrow(it);
+      const int q_seq0 = (qb_base + cur.qb) * BWD_BQ;
+      cur.next(nqb);  // now the position of block it + 1
       float stat_next = 0.f;
       const bool have_next = (it + 1 < n_iter) && tid < 128;
-      if (have_next) stat_next = fetch_stat(it + 1);  // latency hidden behind this block's math
+      if (have_next) stat_next = fetch_stat(cur);  // latency hidden behind this block's math
       mbar_wait(&bar_s[tb], (it >> 1) & 1);
       __syncwarp();
       tc_fence_after();
@@ -654,7 +667,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&bar_p[tb]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[tb]);  // one arrival per compute warp
       if (have_next) sStat[(tb ^ 1) * 128 + tid] = stat_next * stat_mul;
       bwd_compute_bar_sync();  // stats(it+1) visible; stats(it) no longer read
     }
@@ -731,8 +745,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __res
     }
     for (int i = 0; i < 2; ++i) mbar_init(&bar_s[i], 1);
     mbar_init(bar_dq, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&bar_p[i], BWD_NCOMPUTE);
-    mbar_init(bar_qready, BWD_NCOMPUTE);
+    for (int i = 0; i < 2; ++i) mbar_init(&bar_p[i], BWD_NCOMPUTE / 32);
+    mbar_init(bar_qready, BWD_NCOMPUTE / 32);
     fence_barrier_init();
   }
   if (warp == 16) tmem_alloc(tmem_slot, DQ_TMEM_COLS);
@@ -823,7 +837,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __res
       tmem_st16(tmem_dO + lane_base + hc * 16, rd);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_qready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_qready);
     }
     const size_t stat_idx = static_cast<size_t>(h) * (static_cast<size_t>(B) * S) + tok0 + row_seq;
     const float my_lse = lse2[stat_idx];
@@ -862,7 +877,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __res
       tmem_st8(tmem_base + 128 + tb * 64 + lane_base + hc * 8, dsp);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&bar_p[tb]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[tb]);  // one arrival per compute warp
     }
 
     mbar_wait(bar_dq, 0);

@@ -14,6 +14,7 @@
 // (single elected thread), warp 2 = TMEM allocator, warps 4..7 = epilogue. Two TMEM accumulator
 // stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "host_common.h"
+#include "ops.h"
 #include "ptx.cuh"
 
 namespace b200w {
@@ -505,25 +506,63 @@ void dispatch_major(bool a_mn, bool b_mn, const void* A, const void* B, OutT* D,
 // 7B model are split along K so that all SMs stream. Partial sums meet in an fp32 workspace
 // through red.global.add; the last CTA of a tile finalises it and leaves the workspace zeroed.
 // ==========================================================================================
-// epilogue activation of the decode GEMM: 0 = none, 1 = exact (erf) GeLU — transformers
-// get_activation("gelu"), what FalconMLP applies between its two projections
+// epilogue activation of the decode GEMM: 0 = none, 1 = exact (erf) GeLU -- transformers
+// get_activation("gelu"), what FalconMLP applies between its two projections -- 2 = ReLU (OPT)
 __device__ __forceinline__ float decode_act(float x, int act) {
-  return act == 1 ? 0.5f * x * (1.f + erff(x * 0.70710678118654752f)) : x;
+  return act == 1 ? 0.5f * x * (1.f + erff(x * 0.70710678118654752f)) : (act == 2 ? fmaxf(x, 0.f) : x);
 }
 
+// Epilogue description of one decode GEMM. Output feature n lands in out[b, n] (row stride ldo) or,
+// for n >= n_split, in out2[b, n - n_split] (row stride ldo2): Falcon's parallel block computes
+// [q k v | dense_h_to_4h] from one LayerNorm output in ONE launch, the two halves going to the
+// attention input and to the K-concatenated [attention output | MLP hidden] operand of the next GEMM.
+// v = acc (+ bias[n]) (+ C[b, n]); act is applied to features n >= act_from.
+struct DecodeEpi {
+  __nv_bfloat16* out;
+  int ldo;
+  __nv_bfloat16* out2;
+  int ldo2;
+  int n_split;
+  const __nv_bfloat16* C;   // residual, row stride ldc (only for n < n_split)
+  int ldc;
+  const __nv_bfloat16* bias;
+  int act;
+  int act_from;
+};
+__device__ __forceinline__ void decode_store(const DecodeEpi& e, int b, int n, float v) {
+  if (e.bias) v += __bfloat162float(e.bias[n]);
+  if (n < e.n_split) {
+    if (e.C) v += __bfloat162float(e.C[static_cast<size_t>(b) * e.ldc + n]);
+    if (n >= e.act_from) v = decode_act(v, e.act);
+    e.out[static_cast<size_t>(b) * e.ldo + n] = __float2bfloat16_rn(v);
+  } else {
+    if (n >= e.act_from) v = decode_act(v, e.act);
+    e.out2[static_cast<size_t>(b) * e.ldo2 + (n - e.n_split)] = __float2bfloat16_rn(v);
+  }
+}
+
+// Two CTAs per SM (~100 KB of pipeline each): the CTA of the NEXT kernel in the stream is resident and
+// streaming its weights (which depend on nothing) while this one finishes -- see the PDL notes below.
 template <int MPAD>
 struct DecodeCfg {
   static constexpr int B_STAGE_BYTES = MPAD * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = (100 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
+// Programmatic dependent launch: every decode-step kernel is launched with the
+// programmatic-stream-serialization attribute. This kernel's CTAs become resident while the previous
+// kernel is still running, set up barriers / TMEM and -- the point -- fill their whole TMA pipeline with
+// WEIGHT tiles, which no kernel of the step writes; only then pdl_wait() (predecessor complete and
+// visible), and the activation tiles X follow. The ~5-8 us of launch latency + pipeline fill that each of
+// the ~130 GEMMs of a decode step used to expose (profiles/r02_decode_launches.txt: 33 us per launch for
+// a 6-25 us HBM floor) are spent under the predecessor instead.
 template <int MPAD>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
-                   __nv_bfloat16* out, const __nv_bfloat16* C, float* ws, unsigned* counters, int M,
-                   int N, int K, int ldo, int kb_per_split, int act) {
+                   const DecodeEpi epi, float* ws, unsigned* counters, int M, int N, int K,
+                   int kb_per_split) {
   using cfg = DecodeCfg<MPAD>;
   constexpr int STAGES = cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -544,6 +583,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   const bool split = gridDim.y > 1;
 
   if (threadIdx.x == 0) {
+    pdl_trigger();  // the next kernel's CTAs may take the SM slots that free up from now on
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmX);
     for (int s = 0; s < STAGES; ++s) {
@@ -561,10 +601,19 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
+      // pipeline fill with weight tiles only (independent of the predecessor) ...
+      const int pre = nkb < STAGES ? nkb : STAGES;
+      for (int i = 0; i < pre; ++i) {
+        mbar_arrive_expect_tx(&full_bar[i], cfg::STAGE_BYTES);
+        tma_load_2d(smem + i * cfg::STAGE_BYTES, &tmW, &full_bar[i], (kb0 + i) * BLOCK_K, n0);
+      }
+      pdl_wait();  // ... then the predecessor's activations
+      for (int i = 0; i < pre; ++i)
+        tma_load_2d(smem + i * cfg::STAGE_BYTES + A_STAGE_BYTES, &tmX, &full_bar[i], (kb0 + i) * BLOCK_K, 0);
       int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint32_t phase = 0;  // parity of the FIRST pass through the ring; the steady state starts on pass 2
+      for (int kb = kb0 + pre; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase);
         uint8_t* sa = smem + stage * cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], cfg::STAGE_BYTES);
         tma_load_2d(sa, &tmW, &full_bar[stage], kb * BLOCK_K, n0);                   // weights
@@ -595,6 +644,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const int q = warp & 3;
     const int n = n0 + q * 32 + lane;
     const bool n_ok = n < N;
+    pdl_wait();  // this warp reads C / writes out and the split-K workspace: all shared with the predecessor
     mbar_wait(done_bar, 0);
     __syncwarp();
     tc_fence_after();
@@ -610,10 +660,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           if (b < M) {
             const float v = __uint_as_float(r[j]);
             if (split) atomicAdd(ws + static_cast<size_t>(b) * N + n, v);  // 32 lanes -> 128 B, coalesced
-            else {
-              const float cv = C ? __bfloat162float(C[static_cast<size_t>(b) * ldo + n]) : 0.f;
-              out[static_cast<size_t>(b) * ldo + n] = __float2bfloat16_rn(decode_act(v + cv, act));
-            }
+            else decode_store(epi, b, n, v);
           }
         }
       }
@@ -633,8 +680,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           float* p = ws + static_cast<size_t>(b) * N + n;
           const float v = __ldcg(p);
           *p = 0.f;
-          const float cv = C ? __bfloat162float(C[static_cast<size_t>(b) * ldo + n]) : 0.f;
-          out[static_cast<size_t>(b) * ldo + n] = __float2bfloat16_rn(decode_act(v + cv, act));
+          decode_store(epi, b, n, v);
         }
       }
       if (threadIdx.x == 0) counters[blockIdx.x] = 0;
@@ -649,11 +695,11 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 }
 
 template <int MPAD>
-void launch_decode(const void* X, const void* W, void* out, const void* C, float* ws, unsigned* counters,
-                   int M, int N, int K, int ldo, int act, cudaStream_t stream) {
+void launch_decode(const void* X, int ldx, const void* W, int ldw, const DecodeEpi& epi, float* ws,
+                   unsigned* counters, int M, int N, int K, cudaStream_t stream) {
   using cfg = DecodeCfg<MPAD>;
-  CUtensorMap tmW = make_tmap_bf16_2d(W, N, K, K, BLOCK_M, BLOCK_K);
-  CUtensorMap tmX = make_tmap_bf16_2d(X, M, K, K, MPAD, BLOCK_K);
+  CUtensorMap tmW = make_tmap_bf16_2d(W, N, K, ldw, BLOCK_M, BLOCK_K);
+  CUtensorMap tmX = make_tmap_bf16_2d(X, M, K, ldx, MPAD, BLOCK_K);
   auto kern = gemm_decode_kernel<MPAD>;
   static PerDeviceOnce once;
   once.run([&] {
@@ -661,19 +707,17 @@ void launch_decode(const void* X, const void* W, void* out, const void* C, float
   });
   const int n_tiles = (N + BLOCK_M - 1) / BLOCK_M;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-  // split K until every SM has a CTA, keeping at least 8 K-blocks per split
+  // split K until two CTAs per SM are in flight, keeping at least 8 K-blocks per split
   int splits = 1;
   if (ws && counters) {
-    splits = sm_count() / n_tiles;
+    splits = 2 * sm_count() / n_tiles;
     if (splits > num_kb / 8) splits = num_kb / 8;
     if (splits < 1) splits = 1;
   }
   const int per = (num_kb + splits - 1) / splits;
   splits = (num_kb + per - 1) / per;
-  kern<<<dim3(n_tiles, splits), GEMM_THREADS, cfg::SMEM_BYTES, stream>>>(
-      tmW, tmX, static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(C), ws, counters, M, N,
-      K, ldo, per, act);
-  B200W_CUDA(cudaGetLastError());
+  launch_pdl(kern, dim3(n_tiles, splits), dim3(GEMM_THREADS), cfg::SMEM_BYTES, stream, tmW, tmX, epi, ws,
+             counters, M, N, K, per);
 }
 
 // Tile raster order. M-fastest re-reads A once per wave of N-tiles unless A stays in L2; N-fastest
@@ -687,16 +731,36 @@ static int pick_n_fast(int M, int N, int K) {
   return b_bytes < a_bytes ? 1 : 0;
 }
 
-// out[M, N] = X[M, K] W[N, K]^T (+ C), M <= 128: the decode-time projection. ws: zeroed fp32
-// workspace of >= M*N floats and counters: zeroed unsigned[ceil(N/128)] enable split-K (both are
-// left zeroed again); pass nullptr to disable.
+// out[M, N] = act(X[M, K] W[N, K]^T (+ bias) (+ C)), M <= 128: the decode-time projection. ws: zeroed
+// fp32 workspace of >= M*N floats and counters: zeroed unsigned[ceil(N/128)] enable split-K (both are
+// left zeroed again); pass nullptr to disable. ldx / ldw: row strides of X and W (elements).
+void gemm_decode_ex(const void* X, int ldx, const void* W, int ldw, const GemmDecodeOut& o, float* ws,
+                    unsigned* counters, int M, int N, int K, cudaStream_t stream) {
+  B200W_CHECK(M >= 1 && M <= 128 && N > 0 && K > 0, "decode GEMM handles 1..128 rows");
+  B200W_CHECK(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "TMA needs 16-byte aligned row strides");
+  DecodeEpi e;
+  e.out = static_cast<__nv_bfloat16*>(o.out);
+  e.ldo = o.ldo;
+  e.out2 = static_cast<__nv_bfloat16*>(o.out2);
+  e.ldo2 = o.ldo2;
+  e.n_split = o.out2 ? o.n_split : N;
+  e.C = static_cast<const __nv_bfloat16*>(o.C);
+  e.ldc = o.ldc ? o.ldc : o.ldo;
+  e.bias = static_cast<const __nv_bfloat16*>(o.bias);
+  e.act = o.act;
+  e.act_from = o.act_from;
+  if (M <= 32) launch_decode<32>(X, ldx, W, ldw, e, ws, counters, M, N, K, stream);
+  else if (M <= 64) launch_decode<64>(X, ldx, W, ldw, e, ws, counters, M, N, K, stream);
+  else launch_decode<128>(X, ldx, W, ldw, e, ws, counters, M, N, K, stream);
+}
 void gemm_decode(const void* X, const void* W, void* out, const void* C, float* ws, unsigned* counters,
                  int M, int N, int K, int ldo, int act, cudaStream_t stream) {
-  B200W_CHECK(M >= 1 && M <= 128 && N > 0 && K > 0, "decode GEMM handles 1..128 rows");
-  B200W_CHECK(K % 8 == 0, "TMA needs 16-byte aligned row strides");
-  if (M <= 32) launch_decode<32>(X, W, out, C, ws, counters, M, N, K, ldo, act, stream);
-  else if (M <= 64) launch_decode<64>(X, W, out, C, ws, counters, M, N, K, ldo, act, stream);
-  else launch_decode<128>(X, W, out, C, ws, counters, M, N, K, ldo, act, stream);
+  GemmDecodeOut o{};
+  o.out = out;
+  o.ldo = ldo;
+  o.C = C;
+  o.act = act;
+  gemm_decode_ex(X, K, W, K, o, ws, counters, M, N, K, stream);
 }
 
 // Public launcher (C++). out_fp32: D/C are float, else bf16. C may alias D (accumulate in place).

@@ -7,6 +7,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 namespace b200w {
 
@@ -59,6 +60,23 @@ class PerDeviceOnce {
   std::mutex mu_;
   uint64_t done_ = 0;
 };
+
+// Kernel launch with the programmatic-stream-serialization attribute (see ptx.cuh pdl_wait): only for
+// kernels that call pdl_wait() before they touch anything their predecessor wrote.
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200W_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...));
+}
 
 // gemm_bf16 leaves this many SMs free (grid = SMs - reserve): set around the backward that runs
 // concurrently with the NCCL gradient all-reduce, so that NCCL's CTAs find SMs without waiting for a

@@ -18,6 +18,26 @@ void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int 
 // act: 0 none, 1 exact GeLU applied to (acc + C).
 void gemm_decode(const void* X, const void* W, void* out, const void* C, float* ws, unsigned* counters,
                  int M, int N, int K, int ldo, int act, cudaStream_t s);
+// The general form. Output feature n goes to out[b, n] (row stride ldo) or, when out2 != nullptr and
+// n >= n_split, to out2[b, n - n_split] (row stride ldo2). v = acc (+ bias[n]) (+ C[b, n], row stride
+// ldc, only for the first output); act (0 none, 1 exact GeLU, 2 ReLU) applies to features n >= act_from.
+// ldx / ldw: row strides of X [M, K] and W [N, K], so that both may be column windows of wider
+// matrices. Launched with programmatic dependent launch: the weight stream starts under the
+// predecessor kernel (gemm.cu).
+struct GemmDecodeOut {
+  void* out = nullptr;
+  int ldo = 0;
+  void* out2 = nullptr;
+  int ldo2 = 0;
+  int n_split = 0;
+  const void* C = nullptr;
+  int ldc = 0;
+  const void* bias = nullptr;
+  int act = 0;
+  int act_from = 0;
+};
+void gemm_decode_ex(const void* X, int ldx, const void* W, int ldw, const GemmDecodeOut& o, float* ws,
+                    unsigned* counters, int M, int N, int K, cudaStream_t s);
 
 // ---- attention.cu --------------------------------------------------------------------------
 // Causal self-attention over packed sequences. qkv: [T, ld_qkv] with q at column 0, k at

@@ -90,6 +90,17 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still running. Everything it does
+// before pdl_wait() must be independent of the predecessor's output (barrier setup, TMEM allocation,
+// streaming WEIGHTS); pdl_wait() returns once the predecessor has completed and its writes are
+// visible. pdl_trigger() lets the successor's CTAs be scheduled as soon as every CTA of this grid
+// has called it (or exited). Both are no-ops for a kernel launched the ordinary way.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
 // TMA
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

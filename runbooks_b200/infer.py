@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import B200WError, InferArch as _CArch
 from .engine import Engine
 
-FAMILY = {"llama": 0, "falcon": 1}
+FAMILY = {"llama": 0, "falcon": 1, "opt": 2}
 
 
 @dataclass
@@ -30,6 +30,7 @@ class ServeArch:
     norm_eps: float = 1e-5
     rope_theta: float = 10000.0
     tie_embeddings: bool = False
+    max_positions: int = 0        # OPT: max_position_embeddings (learned table, +2 rows)
 
     @classmethod
     def falcon_7b(cls, max_ctx: int = 2048) -> "ServeArch":
@@ -53,20 +54,28 @@ class ServeArch:
         if mt == "llama":
             heads = cfg["num_attention_heads"]
             rope = cfg.get("rope_parameters") or {}
+            from .engine import LlamaArch
+            LlamaArch.from_hf_config(cfg)              # same rejections as the trainer (rope scaling, biases, ...)
             return cls("llama", cfg["vocab_size"], cfg["hidden_size"], cfg["intermediate_size"],
                        cfg["num_hidden_layers"], heads, cfg.get("num_key_value_heads") or heads,
                        cfg.get("head_dim") or cfg["hidden_size"] // heads,
                        max_ctx or min(4096, cfg.get("max_position_embeddings", 4096)),
                        cfg.get("rms_norm_eps", 1e-6), float(cfg.get("rope_theta") or rope.get("rope_theta") or 1e4),
                        bool(cfg.get("tie_word_embeddings", False)))
-        raise ValueError(f"unsupported model_type {mt!r} (falcon, llama)")
+        if mt == "opt":
+            from .engine import OptArch
+            o = OptArch.from_hf_config(cfg)            # rejects the variants that are not built
+            ctx = min(max_ctx or o.max_positions, o.max_positions)
+            return cls("opt", o.vocab_size, o.hidden_size, o.intermediate_size, o.num_layers, o.num_heads,
+                       o.num_heads, o.head_dim, ctx, o.layer_norm_eps, 10000.0, True, o.max_positions)
+        raise ValueError(f"unsupported model_type {mt!r} (falcon, llama, opt)")
 
 
 class InferEngine(Engine):
     def init_infer(self, arch: ServeArch, max_batch: int = 32):
         ca = _CArch(FAMILY[arch.family], arch.vocab_size, arch.hidden_size, arch.intermediate_size,
                     arch.num_layers, arch.num_heads, arch.num_kv_heads, arch.head_dim, arch.max_ctx,
-                    arch.norm_eps, arch.rope_theta, 1 if arch.tie_embeddings else 0)
+                    arch.norm_eps, arch.rope_theta, 1 if arch.tie_embeddings else 0, arch.max_positions)
         self._check(self._lib.b200w_infer_init(self._h, C.byref(ca), max_batch))
         self.serve_arch, self.max_batch = arch, max_batch
 
@@ -78,7 +87,7 @@ class InferEngine(Engine):
         for i in range(n.value):
             self._check(self._lib.b200w_infer_param_info(self._h, i, buf, 256, C.byref(r), C.byref(c)))
             name = buf.value.decode()
-            one_d = r.value == 1 and ("norm" in name or "ln_f" in name)
+            one_d = r.value == 1      # norm weights, LayerNorm parameters, biases
             yield name, ((c.value,) if one_d else (r.value, c.value))
 
     def infer_load_tensor(self, name: str, arr: np.ndarray):
@@ -109,6 +118,41 @@ class InferEngine(Engine):
         return nxt, logits
 
 
+    def prefill(self, prompts: List[List[int]], slots: List[int], want_logits: bool = False):
+        """One pass over whole prompts (b200w_infer_prefill): K/V of every prompt position goes to its
+        cache slot; returns (greedy token after each prompt, logits [n, V] or None)."""
+        n = len(prompts)
+        longest = max(len(p) for p in prompts)
+        S = ((longest + 127) // 128) * 128
+        tok = np.zeros((n, S), dtype=np.int32)
+        for i, p in enumerate(prompts):
+            tok[i, :len(p)] = p
+        lens = np.array([len(p) for p in prompts], dtype=np.int32)
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        nxt = np.empty(n, dtype=np.int32)
+        logits = np.empty((n, self.serve_arch.vocab_size), dtype=np.float32) if want_logits else None
+        self._check(self._lib.b200w_infer_prefill(self._h, tok.ctypes.data, lens.ctypes.data, sl.ctypes.data, n, S,
+                                                  nxt.ctypes.data, logits.ctypes.data if want_logits else None))
+        return nxt, logits
+
+
+def sample_token(logits: np.ndarray, temperature: float, top_p: float, rng: np.random.Generator) -> int:
+    """Host-side sampling of one row (the engine itself is greedy): softmax(logits / T) restricted to the
+    smallest prefix of the sorted distribution whose mass reaches top_p (nucleus sampling)."""
+    z = logits.astype(np.float64) / max(temperature, 1e-6)
+    z -= z.max()
+    p = np.exp(z)
+    p /= p.sum()
+    if top_p < 1.0:
+        order = np.argsort(-p)
+        keep = np.searchsorted(np.cumsum(p[order]), top_p) + 1
+        mask = np.zeros_like(p)
+        mask[order[:keep]] = 1.0
+        p = p * mask
+        p /= p.sum()
+    return int(rng.choice(len(p), p=p))
+
+
 @dataclass
 class _Req:
     prompt: List[int]
@@ -117,42 +161,78 @@ class _Req:
     fed: int = 0          # tokens fed so far (prompt + generated)
     slot: int = -1
     done: bool = False
+    temperature: float = 0.0
+    top_p: float = 1.0
+    rng: Optional[np.random.Generator] = None
+
+    @property
+    def greedy(self) -> bool:
+        return self.temperature <= 0.0
 
 
 class Generator:
-    """Greedy continuous batching over the engine's cache slots."""
+    """Continuous batching over the engine's cache slots. A request's prompt is ingested in one prefill
+    pass when it is admitted (engines without `prefill`, i.e. the CPU test stubs, feed it one token per
+    step through the decode path); from then on every active request advances one token per step."""
 
-    def __init__(self, engine: InferEngine, eos_id: Optional[int] = None):
+    def __init__(self, engine: InferEngine, eos_id: Optional[int] = None, use_prefill: bool = True):
         self.e, self.eos = engine, eos_id
         self.free = list(range(engine.max_batch))
         self.active: List[_Req] = []
+        self.use_prefill = use_prefill and hasattr(engine, "prefill")
 
-    def add(self, prompt: List[int], max_tokens: int) -> _Req:
+    def add(self, prompt: List[int], max_tokens: int, temperature: float = 0.0, top_p: float = 1.0,
+            seed: Optional[int] = None) -> _Req:
         if not prompt:
             raise ValueError("empty prompt")
+        V = self.e.serve_arch.vocab_size
+        bad = [t for t in prompt if not 0 <= int(t) < V]
+        if bad:   # a per-request error (HTTP 400), never an engine failure that would take the server down
+            raise ValueError(f"token id {bad[0]} outside the model vocabulary ({V})")
         if len(prompt) + max_tokens > self.e.serve_arch.max_ctx:
             raise ValueError("prompt + max_tokens exceeds the KV cache length")
         if not self.free:
             raise RuntimeError("no free cache slot")
-        r = _Req(list(prompt), max_tokens, [], 0, self.free.pop())
+        r = _Req(list(prompt), max_tokens, [], 0, self.free.pop(), False, float(temperature), float(top_p),
+                 np.random.default_rng(seed) if temperature > 0 else None)
         self.active.append(r)
+        if self.use_prefill and len(prompt) > 1:
+            nxt, lg = self.e.prefill([r.prompt], [r.slot], want_logits=not r.greedy)
+            r.fed = len(r.prompt)
+            self._emit(r, int(nxt[0]) if r.greedy else sample_token(lg[0], r.temperature, r.top_p, r.rng))
+            self._retire()
         return r
+
+    def _emit(self, r: _Req, t: int):
+        r.out.append(t)
+        if len(r.out) >= r.max_tokens or (self.eos is not None and t == self.eos):
+            r.done = True
+
+    def cancel(self, r: _Req):
+        """Stop a request now (stop string hit, client gone): its slot is free for the next admission."""
+        if r in self.active:
+            r.done = True
+            self.active.remove(r)
+            self.free.append(r.slot)
+
+    def _retire(self):
+        for r in [r for r in self.active if r.done]:
+            self.active.remove(r)
+            self.free.append(r.slot)
 
     def step(self):
         """One engine step for every active request."""
         if not self.active:
             return
         toks = [(r.prompt[r.fed] if r.fed < len(r.prompt) else r.out[-1]) for r in self.active]
-        nxt, _ = self.e.step(toks, [r.fed for r in self.active], [r.slot for r in self.active])
-        for r, t in zip(self.active, nxt):
+        need_logits = any(not r.greedy for r in self.active)
+        nxt, lg = self.e.step(toks, [r.fed for r in self.active], [r.slot for r in self.active],
+                              want_logits=need_logits)
+        for i, (r, t) in enumerate(zip(self.active, nxt)):
             r.fed += 1
             if r.fed >= len(r.prompt):        # the token just fed was the last known one
-                r.out.append(int(t))
-                if len(r.out) >= r.max_tokens or (self.eos is not None and int(t) == self.eos):
-                    r.done = True
-        for r in [r for r in self.active if r.done]:
-            self.active.remove(r)
-            self.free.append(r.slot)
+                self._emit(r, int(t) if r.greedy else sample_token(lg[i], r.temperature, r.top_p, r.rng))
+        self._retire()
 
     def generate(self, prompts: List[List[int]], max_tokens: int) -> List[List[int]]:
         reqs = [self.add(p, max_tokens) for p in prompts]

@@ -160,11 +160,48 @@ def test_serve_arch_from_hf_configs():
     with pytest.raises(ValueError):
         ServeArch.from_hf_config(dict(falcon7b, alibi=True))
     with pytest.raises(ValueError):
-        ServeArch.from_hf_config({"model_type": "opt"})
+        ServeArch.from_hf_config({"model_type": "gpt2"})
+    # the reference's system-test model (test/system.sh:46-78, examples/facebook-opt-125m/base-server.yaml)
+    opt125m = {"model_type": "opt", "vocab_size": 50272, "hidden_size": 768, "ffn_dim": 3072, "num_hidden_layers": 12,
+               "num_attention_heads": 12, "max_position_embeddings": 2048, "do_layer_norm_before": True,
+               "word_embed_proj_dim": 768, "activation_function": "relu", "enable_bias": True, "pad_token_id": 1}
+    o = ServeArch.from_hf_config(opt125m)
+    assert (o.family, o.head_dim, o.num_kv_heads, o.intermediate_size, o.tie_embeddings, o.max_positions, o.max_ctx) == (
+        "opt", 64, 12, 3072, True, 2048, 2048)
+    with pytest.raises(ValueError):          # opt-350m's post-LN / projected-embedding layout is not built
+        ServeArch.from_hf_config(dict(opt125m, do_layer_norm_before=False))
+    with pytest.raises(ValueError):
+        ServeArch.from_hf_config(dict(opt125m, word_embed_proj_dim=512))
     ll = ServeArch.from_hf_config({"model_type": "llama", "vocab_size": 32000, "hidden_size": 4096,
                                    "intermediate_size": 11008, "num_hidden_layers": 32, "num_attention_heads": 32,
                                    "rms_norm_eps": 1e-5, "max_position_embeddings": 4096})
     assert (ll.family, ll.num_kv_heads, ll.head_dim, ll.max_ctx, ll.tie_embeddings) == ("llama", 32, 128, 4096, False)
+
+
+def test_unimplemented_checkpoint_variants_fail_instead_of_training_something_else():
+    """a Llama-3.1 rope_scaling, a biased variant or another activation must raise, not be
+    ignored (the Job would exit 0 with different arithmetic)."""
+    from runbooks_b200.engine import LlamaArch, OptArch, arch_from_hf_config
+    base = {"model_type": "llama", "vocab_size": 32000, "hidden_size": 4096, "intermediate_size": 11008,
+            "num_hidden_layers": 32, "num_attention_heads": 32, "rms_norm_eps": 1e-5, "max_position_embeddings": 4096}
+    a = arch_from_hf_config(dict(base, pad_token_id=0))
+    assert isinstance(a, LlamaArch) and a.pad_token_id == 0 and arch_from_hf_config(base).pad_token_id == -1
+    for bad in ({"rope_scaling": {"rope_type": "llama3", "factor": 8.0}}, {"rope_parameters": {"rope_type": "linear", "factor": 2}},
+                {"attention_bias": True}, {"mlp_bias": True}, {"hidden_act": "gelu"}, {"tie_word_embeddings": True}):
+        with pytest.raises(ValueError):
+            arch_from_hf_config(dict(base, **bad))
+    assert arch_from_hf_config(dict(base, rope_scaling=None, rope_parameters={"rope_type": "default", "rope_theta": 5e5})).rope_theta == 5e5
+    o = arch_from_hf_config({"model_type": "opt", "vocab_size": 50272, "hidden_size": 768, "ffn_dim": 3072,
+                             "num_hidden_layers": 12, "num_attention_heads": 12, "max_position_embeddings": 2048})
+    assert isinstance(o, OptArch) and (o.head_dim, o.pad_token_id, o.max_seq_len) == (64, 1, 2048)
+    with pytest.raises(ValueError):
+        arch_from_hf_config({"model_type": "mistral"})
+    # tensors the engine would silently drop
+    assert contract.is_ignorable_tensor("lm_head.weight", {"model_type": "opt"})
+    assert contract.is_ignorable_tensor("model.layers.0.self_attn.rotary_emb.inv_freq", {"model_type": "llama"})
+    assert not contract.is_ignorable_tensor("model.layers.0.self_attn.q_proj.bias", {"model_type": "llama"})
+    assert not contract.is_ignorable_tensor("lm_head.weight", {"model_type": "llama"})
+    assert contract.canonical_tensor_name("decoder.embed_tokens.weight", {"model_type": "opt"}) == "model.decoder.embed_tokens.weight"
 
 
 def test_warmup_semantics_match_training_arguments(tmp_path):

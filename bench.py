@@ -398,10 +398,76 @@ def run_ours(args):
         clocks=clocks, loss=round(float(loss), 4), grad_norm=round(float(gn), 4),
         device_gb=round(e.device_bytes() / 1e9, 1),
     )
+    e.close()
+    if world == 1 and not args.no_decode:
+        try:
+            line["decode"] = decode_leg(local)
+        except Exception as ex:  # noqa: BLE001 — the fine-tune line must not be lost to the second metric
+            line["decode"] = dict(error=f"{type(ex).__name__}: {ex}")
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
     emit(line)
+
+
+# --------------------------------------------------------------------------------------------
+# decode leg (BASELINE.json configs[3], SURVEY.md 8d second metric): Falcon-7B-Instruct layout,
+# random-init bf16 weights, batch 32, context 1024, greedy, through b200w_infer_step with HOST buffers
+# --------------------------------------------------------------------------------------------
+def decode_leg(device: int = 0, batch: int = 32, ctx: int = 1024, steps: int = 64, warm: int = 4):
+    import numpy as np
+
+    from runbooks_b200.infer import InferEngine, ServeArch
+
+    arch = ServeArch.falcon_7b(max_ctx=ctx + steps + warm + 8)
+    e = InferEngine(device)
+    e.init_infer(arch, max_batch=batch)
+    e.infer_init_random(0, 0.02)
+    rng = np.random.default_rng(0)
+    slots = list(range(batch))
+    prompts = rng.integers(0, arch.vocab_size, size=(batch, ctx)).tolist()
+    # the context is built by the one-pass prefill (also timed: it is the other half of serving a request)
+    chunk = 8                                  # 8 x 1024 tokens per prefill call
+    e.prefill(prompts[:chunk], slots[:chunk])  # warm-up (buffer growth, first-use attributes)
+    e.sync()
+    t0 = time.perf_counter()
+    tok = []
+    for i in range(0, batch, chunk):
+        nxt, _ = e.prefill(prompts[i:i + chunk], slots[i:i + chunk])
+        tok.extend(int(t) for t in nxt)
+    e.sync()
+    prefill_s = time.perf_counter() - t0
+    tok = np.array(tok, dtype=np.int32)
+    for w in range(warm):                      # eager run, graph capture, replays
+        tok, _ = e.step(tok, [ctx + w] * batch, slots)
+    e.sync()
+    launches0 = e.launch_count()
+    e.timer_start()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        tok, _ = e.step(tok, [ctx + warm + i] * batch, slots)   # H2D of 3 x 32 ints, D2H of 32 ints inside
+    ms = e.timer_stop()
+    wall = (time.perf_counter() - t0) * 1e3
+    launches = e.launch_count() - launches0
+    n_params = sum(int(np.prod(s)) for _, s in e.infer_params())
+    kv_bytes = batch * (ctx + warm + steps // 2) * arch.num_layers * 2 * arch.num_kv_heads * arch.head_dim * 2
+    bytes_step = 2 * n_params + kv_bytes
+    pk = peaks()
+    per = max(ms, wall) / steps
     e.close()
+    return dict(
+        metric="Falcon-7B greedy decode tokens/s, batch 32, context 1024, 1xB200 (BASELINE.json configs[3])",
+        value=round(batch / (per / 1e3), 1), unit="tokens/s", ms_per_step=round(per, 3),
+        device_ms_per_step=round(ms / steps, 3), steps=steps, dtype="bf16", data="synthetic (random-init weights, random prompts)",
+        e2e=dict(value=round(batch / (wall / steps / 1e3), 1), unit="tokens/s", h2d_bytes_per_step=3 * batch * 4,
+                 d2h_bytes_per_step=batch * 4),
+        gpu_launches_per_step=round(launches / steps, 1),
+        roofline=dict(bound="hbm", achieved=round(bytes_step / (per / 1e3) / 1e9, 1), peak=pk["hbm"], unit="GB/s",
+                      frac=round(bytes_step / (per / 1e3) / 1e9 / pk["hbm"], 4), traffic=None,
+                      algorithmic_bytes_per_step=int(bytes_step), params=n_params,
+                      note="bytes = 2 x parameters (every weight read once per step, the tied embedding as lm_head) "
+                           "+ K/V of batch x context; peak = measured copy bandwidth (MEASURED_PEAKS.json)"),
+        prefill=dict(tokens=batch * ctx, seconds=round(prefill_s, 3), tokens_per_s=round(batch * ctx / prefill_s, 1),
+                     note="one-pass prompt ingestion (b200w_infer_prefill), 4 calls of 8 x 1024 tokens"))
 
 
 _REAL_STDOUT = None
@@ -437,6 +503,8 @@ def main():
                     help="sequences per accumulation micro-step (activation memory scales with it)")
     ap.add_argument("--layers", type=int, default=0, help="development only: fewer layers")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-decode", action="store_true", help="skip the Falcon-7B decode leg (N=1 only)")
+    ap.add_argument("--decode-only", action="store_true", help="run only the decode leg and print its object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     MICRO_BATCH = args.micro_batch
@@ -446,7 +514,9 @@ def main():
     # (profiles/r01_n8_failure.txt: one rank raised, did not exit, and 7 GPUs spun for 10 minutes.)
     code = 0
     try:
-        if args.impl == "reference":
+        if args.decode_only:
+            emit(decode_leg(int(os.environ.get("LOCAL_RANK", "0"))))
+        elif args.impl == "reference":
             run_reference(args)
         else:
             run_ours(args)

@@ -94,8 +94,14 @@ B200W_API void b200w_default_hparams(b200w_hparams* hp);
 
 /* ---- model state -------------------------------------------------------------------------- */
 /* Allocates weights (bf16 compute copy + fp32 master), Adam moments, gradients and the
- * activation arena for micro-batches of `micro_batch` sequences. training=0 skips optimiser
- * state (inference / forward-only). */
+ * activation arena for micro-batches of `micro_batch` sequences. training: 0 = no optimiser state
+ * (inference / forward-only); 1 = replicated state (every rank holds master / m / v of all
+ * parameters); 2 = SHARDED state (SURVEY.md 8e, config #5 groundwork): call b200w_comm_init FIRST; rank
+ * r then keeps fp32 master / m / v only for slice r of every gradient-exchange range (1/nranks of 12
+ * bytes per parameter), the gradient exchange is a reduce-scatter, AdamW runs on the owned slices
+ * and the bf16 compute copy is all-gathered -- the wire bytes of one all-reduce. Same results as
+ * mode 1 (bit-identical at 2 ranks). b200w_read_state then serves kind 0 from the compute copy and
+ * refuses kinds 1-3. */
 B200W_API int b200w_model_init(b200w_ctx* ctx, const b200w_arch* arch, const b200w_hparams* hp,
                      int micro_batch, int training);
 /* Parameter names follow the HF checkpoint keys ("model.embed_tokens.weight",

@@ -35,11 +35,13 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Uid, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*CommAbort)(void*) = nullptr;  // optional
   const char* (*GetErrorString)(int) = nullptr;
 };
-constexpr int kNcclInt64 = 4, kNcclFloat32 = 7, kNcclBfloat16 = 9, kNcclSum = 0;
+constexpr int kNcclInt64 = 4, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclBfloat16 = 9, kNcclSum = 0;
 
 NcclApi& nccl() {
   static NcclApi api;
@@ -58,6 +60,8 @@ NcclApi& nccl() {
     api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.ReduceScatter = reinterpret_cast<decltype(api.ReduceScatter)>(sym("ncclReduceScatter"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
     api.CommAbort = reinterpret_cast<decltype(api.CommAbort)>(dlsym(api.lib, "ncclCommAbort"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
@@ -133,9 +137,12 @@ __global__ void inv_count_kernel(const long long* cnt, float* inv_n) {
   inv_n[0] = cnt[0] > 0 ? 1.f / static_cast<float>(cnt[0]) : 0.f;
 }
 
-__global__ void init_normal_kernel(float* master, bf16* w, size_t n, uint64_t seed, float std) {
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+// element j of the output holds the value of index i0 + j of the parameter's random stream (a rank that
+// owns a slice of the fp32 master generates exactly the values the full tensor would hold there)
+__global__ void init_normal_kernel(float* master, bf16* w, size_t n, uint64_t seed, float std, size_t i0 = 0) {
+  for (size_t j = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < n;
+       j += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t i = i0 + j;
     // splitmix64 counter hash -> two uniforms -> Box-Muller
     uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -144,8 +151,8 @@ __global__ void init_normal_kernel(float* master, bf16* w, size_t n, uint64_t se
     const float u1 = (static_cast<uint32_t>(z >> 32) + 1.0f) * (1.0f / 4294967296.0f);
     const float u2 = static_cast<uint32_t>(z) * (1.0f / 4294967296.0f);
     const float r = sqrtf(-2.f * __logf(u1)) * __cosf(6.2831853f * u2) * std;
-    if (master) master[i] = r;
-    w[i] = __float2bfloat16_rn(r);
+    if (master) master[j] = r;
+    if (w) w[j] = __float2bfloat16_rn(r);
   }
 }
 // Fills this SM's shared memory and all 512 TMEM columns with `pattern` (b200w_op_poison_onchip).
@@ -179,7 +186,7 @@ __global__ void fill_kernel(float* master, bf16* w, size_t n, float val) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     if (master) master[i] = val;
-    w[i] = __float2bfloat16_rn(val);
+    if (w) w[i] = __float2bfloat16_rn(val);
   }
 }
 }  // namespace
@@ -208,6 +215,12 @@ struct b200w_ctx {
   bf16* w = nullptr;
   float *master = nullptr, *m = nullptr, *v = nullptr, *g = nullptr;
   bf16* gw = nullptr;       // bf16 wire copy of the gradients (data parallel only)
+  // Exchange ranges: the prefix's decay segments, then every matrix (the unit of the overlapped
+  // gradient collective). With sharded optimiser state (training == 2) rank r owns slice r of every
+  // range: master / m / v exist only for the owned slices, packed at offset range.off / nranks.
+  struct Range { size_t off, cnt; bool decay; };
+  std::vector<Range> ranges;
+  bool shard = false;
   float2* rope_tab = nullptr;
 
   struct LayerP { size_t ln1, ln1b, ln2, ln2b, wqkv, bqkv, wo, bo, wgu, b1, wd, b2; };
@@ -352,6 +365,17 @@ void build_segments(b200w_ctx* c) {
     else
       c->segs.push_back({p.off, p.isize(), p.decay});
   }
+}
+
+// ranges = the decay segments of the accumulated prefix + one range per fused matrix, in offset order
+void build_ranges(b200w_ctx* c, const std::vector<std::pair<size_t, size_t>>& matrices) {
+  c->ranges.clear();
+  for (const auto& sg : c->segs) {
+    if (sg.off >= c->n_zero_prefix) break;
+    const size_t end = std::min(sg.off + sg.n, c->n_zero_prefix);
+    c->ranges.push_back({sg.off, end - sg.off, sg.decay});
+  }
+  for (const auto& mtx : matrices) c->ranges.push_back({mtx.first, mtx.second, true});
 }
 
 void build_params_llama(b200w_ctx* c) {
@@ -633,20 +657,37 @@ void ensure_wire(b200w_ctx* c) {
 // bf16 into the wire copy (main stream), and the wire copy is summed over the ranks by NCCL on the
 // comm stream (13.5 GB per step for Llama-2-7B instead of 27 GB). The optimiser
 // then reads the reduced bf16 gradients directly.
-void allreduce_range(b200w_ctx* c, size_t off, size_t count) {
-  if (count == 0) return;
+// Sharded optimiser state: the collective is a reduce-scatter -- rank r receives the sum of slice r of
+// the range, in place, which is all its share of the optimiser needs (SURVEY.md 8e, config #5:
+// reduce_scatter -> local AdamW on the shard -> all_gather, the wire bytes of one all-reduce).
+void exchange_one(b200w_ctx* c, size_t off, size_t count) {
   const ArMode mode = ar_mode();
   cast_f32_to_bf16(c->g + off, c->gw + off, count, c->stream); ++c->launches;
   if (mode == ArMode::Sync) B200W_CUDA(cudaStreamSynchronize(c->stream));
   B200W_CUDA(cudaEventRecord(c->ev_grad, c->stream));
   B200W_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_grad, 0));
-  B200W_NCCL(nccl().AllReduce(c->gw + off, c->gw + off, count, kNcclBfloat16, kNcclSum, c->comm,
-                              c->comm_stream));
+  if (c->shard) {
+    const size_t n = count / c->nranks;
+    B200W_NCCL(nccl().ReduceScatter(c->gw + off, c->gw + off + c->rank * n, n, kNcclBfloat16, kNcclSum, c->comm,
+                                    c->comm_stream));
+  } else {
+    B200W_NCCL(nccl().AllReduce(c->gw + off, c->gw + off, count, kNcclBfloat16, kNcclSum, c->comm,
+                                c->comm_stream));
+  }
   ++c->launches;
   if (mode == ArMode::Serial) {
     B200W_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
     B200W_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
   }
+}
+void allreduce_range(b200w_ctx* c, size_t off, size_t count) {
+  if (count == 0) return;
+  if (!c->shard) return exchange_one(c, off, count);
+  // sharded: slices are defined per exchange range, so a request is served range by range
+  bool any = false;
+  for (const auto& r : c->ranges)
+    if (r.off >= off && r.off + r.cnt <= off + count) { exchange_one(c, r.off, r.cnt); any = true; }
+  if (!any) throw Error("internal: gradient exchange request does not match the exchange ranges");
 }
 
 // backward of one micro-batch. first: overwrite gradients instead of accumulating.
@@ -909,13 +950,44 @@ void fwd_bwd_all(b200w_ctx* c, const int32_t* ids, const int32_t* labels, int n_
 void optimizer_step(b200w_ctx* c, float lr) {
   cudaStream_t s = c->stream;
   const bool wire = c->comm != nullptr;
-  const void* gsrc = wire ? static_cast<const void*>(c->gw) : static_cast<const void*>(c->g);
   B200W_CUDA(cudaMemsetAsync(c->sumsq, 0, sizeof(double), s));
+  c->step += 1;
+  if (c->shard) {
+    // each rank: sum of squares over its slices -> all-reduce of the scalar -> clip coefficient (identical on
+    // every rank) -> AdamW on the owned slices -> all-gather of the bf16 compute copy, range by range
+    const int N = c->nranks, r = c->rank;
+    for (const auto& rg : c->ranges) {
+      const size_t n = rg.cnt / N;
+      grad_sumsq(c->gw + rg.off + r * n, true, n, c->sumsq, s); ++c->launches;
+    }
+    B200W_CUDA(cudaEventRecord(c->ev_grad, s));
+    B200W_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_grad, 0));
+    B200W_NCCL(nccl().AllReduce(c->sumsq, c->sumsq, 1, kNcclFloat64, kNcclSum, c->comm, c->comm_stream));
+    B200W_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
+    B200W_CUDA(cudaStreamWaitEvent(s, c->ev_comm, 0));
+    clip_coef(c->sumsq, c->hp.max_grad_norm, 1.f, c->scal + 1, c->scal + 2, s); c->launches += 2;
+    for (const auto& rg : c->ranges) {
+      const size_t n = rg.cnt / N, lo = rg.off + r * n, co = rg.off / N;
+      adamw_step(c->master + co, c->m + co, c->v + co, c->gw + lo, true, c->w + lo, n, lr, c->hp.beta1, c->hp.beta2,
+                 c->hp.eps, rg.decay ? c->hp.weight_decay : 0.f, c->step, c->scal + 1, s);
+      ++c->launches;
+    }
+    B200W_CUDA(cudaEventRecord(c->ev_grad, s));
+    B200W_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_grad, 0));
+    for (const auto& rg : c->ranges) {
+      const size_t n = rg.cnt / N;
+      B200W_NCCL(nccl().AllGather(c->w + rg.off + r * n, c->w + rg.off, n, kNcclBfloat16, c->comm, c->comm_stream));
+      ++c->launches;
+    }
+    B200W_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
+    B200W_CUDA(cudaStreamWaitEvent(s, c->ev_comm, 0));
+    return;
+  }
+  const void* gsrc = wire ? static_cast<const void*>(c->gw) : static_cast<const void*>(c->g);
   grad_sumsq(gsrc, wire, c->n_elems, c->sumsq, s); ++c->launches;
   // the all-reduce summed per-rank partials that were already divided by the GLOBAL target count
   // (fwd_bwd_device), which is HF's DDP result: no 1/nranks here
   clip_coef(c->sumsq, c->hp.max_grad_norm, 1.f, c->scal + 1, c->scal + 2, s); ++c->launches;
-  c->step += 1;
   auto run = [&](size_t off, size_t n, float wd) {
     const void* gp = wire ? static_cast<const void*>(c->gw + off) : static_cast<const void*>(c->g + off);
     adamw_step(c->master + off, c->m + off, c->v + off, gp, wire, c->w + off, n, lr, c->hp.beta1,
@@ -929,6 +1001,20 @@ void optimizer_step(b200w_ctx* c, float lr) {
     // parameters and biases are not decayed
     for (const auto& sg : c->segs) run(sg.off, sg.n, sg.decay ? c->hp.weight_decay : 0.f);
   }
+}
+
+// sharded state: the owned part [lo, lo + n) of parameter p and where it sits in the packed master / m / v
+struct OwnedPart { size_t lo, n, compact; };
+bool owned_part(const b200w_ctx* c, const Param& p, OwnedPart* out) {
+  for (const auto& rg : c->ranges) {
+    if (p.off < rg.off || p.off >= rg.off + rg.cnt) continue;
+    const size_t n = rg.cnt / c->nranks, s_lo = rg.off + c->rank * n, s_hi = s_lo + n;
+    const size_t lo = std::max(s_lo, p.off), hi = std::min(s_hi, p.off + p.isize());
+    if (lo >= hi) return false;
+    *out = {lo, hi - lo, rg.off / c->nranks + (lo - s_lo)};
+    return true;
+  }
+  return false;
 }
 
 }  // namespace
@@ -1065,19 +1151,47 @@ int b200w_model_init(b200w_ctx* ctx, const b200w_arch* arch, const b200w_hparams
     if (hp) ctx->hp = *hp; else b200w_default_hparams(&ctx->hp);
     ctx->micro_batch = micro_batch;
     ctx->training = training != 0;
+    ctx->shard = training == 2;
+    B200W_CHECK(!(training == 2 && arch->head_dim != 128), "sharded optimiser state is built for head_dim 128 models");
+    B200W_CHECK(!ctx->shard || (ctx->comm && ctx->nranks > 1),
+                "sharded optimiser state needs the communicator first: b200w_comm_init before b200w_model_init(training = 2)");
     ctx->dhp = 128;
     if (opt) build_params_opt(ctx); else build_params_llama(ctx);
     build_segments(ctx);
+    {
+      const size_t d = arch->hidden_size, f = arch->intermediate_size, V = arch->vocab_size;
+      const size_t qd = qd_of(ctx), qkvd = qkv_dim(ctx);
+      std::vector<std::pair<size_t, size_t>> mats;
+      for (const auto& lp : ctx->lp) {
+        mats.push_back({lp.wqkv, qkvd * d});
+        mats.push_back({lp.wo, d * qd});
+        mats.push_back({lp.wgu, (opt ? f : 2 * f) * d});
+        mats.push_back({lp.wd, d * f});
+      }
+      if (!opt) mats.push_back({ctx->p_lm, V * d});
+      build_ranges(ctx, mats);
+      size_t covered = 0;
+      for (const auto& rg : ctx->ranges) {
+        B200W_CHECK(rg.off == covered, "internal: exchange ranges do not tile the parameter space");
+        covered += rg.cnt;
+        if (ctx->shard)
+          B200W_CHECK(rg.cnt % (8 * static_cast<size_t>(ctx->nranks)) == 0,
+                      "sharded state: every matrix must split into nranks slices of a multiple of 8 elements");
+      }
+      B200W_CHECK(covered == ctx->n_elems, "internal: exchange ranges do not cover the parameter space");
+    }
     ctx->w = ctx->alloc<bf16>(ctx->n_elems);
     B200W_CUDA(cudaMemsetAsync(ctx->w, 0, ctx->n_elems * sizeof(bf16), ctx->stream));  // head padding = 0
     if (ctx->training) {
-      ctx->master = ctx->alloc<float>(ctx->n_elems);
-      ctx->m = ctx->alloc<float>(ctx->n_elems);
-      ctx->v = ctx->alloc<float>(ctx->n_elems);
+      // replicated: fp32 master + Adam moments for every parameter; sharded: for this rank's 1/nranks only
+      const size_t n_state = ctx->shard ? ctx->n_elems / ctx->nranks : ctx->n_elems;
+      ctx->master = ctx->alloc<float>(n_state);
+      ctx->m = ctx->alloc<float>(n_state);
+      ctx->v = ctx->alloc<float>(n_state);
       ctx->g = ctx->alloc<float>(ctx->n_elems);
-      B200W_CUDA(cudaMemsetAsync(ctx->master, 0, ctx->n_elems * sizeof(float), ctx->stream));
-      B200W_CUDA(cudaMemsetAsync(ctx->m, 0, ctx->n_elems * sizeof(float), ctx->stream));
-      B200W_CUDA(cudaMemsetAsync(ctx->v, 0, ctx->n_elems * sizeof(float), ctx->stream));
+      B200W_CUDA(cudaMemsetAsync(ctx->master, 0, n_state * sizeof(float), ctx->stream));
+      B200W_CUDA(cudaMemsetAsync(ctx->m, 0, n_state * sizeof(float), ctx->stream));
+      B200W_CUDA(cudaMemsetAsync(ctx->v, 0, n_state * sizeof(float), ctx->stream));
       B200W_CUDA(cudaMemsetAsync(ctx->g, 0, ctx->n_elems * sizeof(float), ctx->stream));
     }
     alloc_activations(ctx);
@@ -1126,6 +1240,29 @@ int b200w_load_tensor(b200w_ctx* ctx, const char* name, const void* host, b200w_
     B200W_CHECK(host && (dtype == B200W_BF16 || dtype == B200W_F32), "bad host buffer / dtype");
     const size_t n = static_cast<size_t>(n_elements);
     cudaStream_t s = ctx->stream;
+    if (ctx->shard) {
+      // every rank holds the whole bf16 compute copy; the fp32 master exists for the owned slice only and
+      // receives the exact fp32 values of an fp32 checkpoint there
+      float* dense = nullptr;
+      void* raw = nullptr;
+      B200W_CUDA(cudaMalloc(reinterpret_cast<void**>(&dense), n * 4));
+      try {
+        if (dtype == B200W_F32) {
+          B200W_CUDA(cudaMemcpyAsync(dense, host, n * 4, cudaMemcpyHostToDevice, s));
+          cast_f32_to_bf16(dense, ctx->w + p.off, n, s);
+        } else {
+          B200W_CUDA(cudaMemcpyAsync(ctx->w + p.off, host, n * 2, cudaMemcpyHostToDevice, s));
+          cast_bf16_to_f32(ctx->w + p.off, dense, n, s);
+        }
+        OwnedPart op;
+        if (owned_part(ctx, p, &op))
+          B200W_CUDA(cudaMemcpyAsync(ctx->master + op.compact, dense + (op.lo - p.off), op.n * 4,
+                                     cudaMemcpyDeviceToDevice, s));
+        B200W_CUDA(cudaStreamSynchronize(s));
+      } catch (...) { cudaFree(dense); cudaFree(raw); throw; }
+      cudaFree(dense);
+      return;
+    }
     if (p.pad == 0) {
       if (dtype == B200W_F32) {
         float* tmp = ctx->training ? ctx->master + p.off : nullptr;
@@ -1197,7 +1334,10 @@ int b200w_read_tensor(b200w_ctx* ctx, const char* name, void* host, b200w_dtype 
     B200W_CHECK(host && (dtype == B200W_BF16 || dtype == B200W_F32), "bad host buffer / dtype");
     const size_t n = static_cast<size_t>(n_elements);
     if (dtype == B200W_F32) {
-      read_dense(ctx, p, ctx->training ? ctx->master : nullptr, ctx->training ? nullptr : ctx->w,
+      // fp32 master when this context holds all of it; with sharded state the (complete, all-gathered)
+      // bf16 compute copy widened to fp32
+      const bool full_master = ctx->training && !ctx->shard;
+      read_dense(ctx, p, full_master ? ctx->master : nullptr, full_master ? nullptr : ctx->w,
                  static_cast<float*>(host));
       return;
     }
@@ -1222,6 +1362,13 @@ int b200w_read_state(b200w_ctx* ctx, const char* name, int kind, float* host, in
   return guarded(ctx, [&] {
     const Param& p = find_param(ctx, name, n_elements);
     B200W_CHECK(ctx->training && host && kind >= 0 && kind <= 3, "bad kind / not training");
+    if (ctx->shard) {
+      // only 1/nranks of master / m / v lives here and the reduced gradient is scattered: the weights are
+      // readable (from the all-gathered compute copy), the rest is not a single-rank quantity
+      if (kind != 0) throw Error("check failed: optimiser state is sharded over the ranks (kind 1..3 unavailable)");
+      read_dense(ctx, p, nullptr, ctx->w, host);
+      return;
+    }
     const float* src[4] = {ctx->master, ctx->g, ctx->m, ctx->v};
     read_dense(ctx, p, src[kind], nullptr, host);
   });
@@ -1232,6 +1379,21 @@ int b200w_init_random(b200w_ctx* ctx, uint64_t seed, float std) {
     B200W_CHECK(ctx->has_model, "no model");
     for (const Param& p : ctx->params) {
       const size_t n = p.isize();
+      if (ctx->shard) {   // whole bf16 copy + the owned slice of the master, from the same per-element stream
+        OwnedPart op{};
+        const bool own = owned_part(ctx, p, &op);
+        if (p.is_norm || p.is_zero_init) {
+          const float val = p.is_norm ? 1.0f : 0.0f;
+          fill_kernel<<<64, 256, 0, ctx->stream>>>(nullptr, ctx->w + p.off, n, val);
+          if (own) fill_kernel<<<64, 256, 0, ctx->stream>>>(ctx->master + op.compact, nullptr, op.n, val);
+        } else {
+          init_normal_kernel<<<sm_count() * 8, 256, 0, ctx->stream>>>(nullptr, ctx->w + p.off, n, seed + p.off, std);
+          if (own)
+            init_normal_kernel<<<sm_count() * 8, 256, 0, ctx->stream>>>(ctx->master + op.compact, nullptr, op.n,
+                                                                        seed + p.off, std, op.lo - p.off);
+        }
+        continue;
+      }
       float* mp = ctx->training ? ctx->master + p.off : nullptr;
       if (p.is_norm || p.is_zero_init)
         fill_kernel<<<64, 256, 0, ctx->stream>>>(mp, ctx->w + p.off, n, p.is_norm ? 1.0f : 0.0f);
@@ -1311,7 +1473,7 @@ int b200w_forward_backward(b200w_ctx* ctx, const int32_t* ids, const int32_t* la
     B200W_CHECK(ids && labels, "NULL batch");
     fwd_bwd_all(ctx, ids, labels, n_seqs, /*allow_overlap=*/false);
     // the reduced gradients live in the bf16 wire copy: widen them for b200w_read_state(kind = 1)
-    if (ctx->comm) { cast_bf16_to_f32(ctx->gw, ctx->g, ctx->n_elems, ctx->stream); ++ctx->launches; }
+    if (ctx->comm && !ctx->shard) { cast_bf16_to_f32(ctx->gw, ctx->g, ctx->n_elems, ctx->stream); ++ctx->launches; }
     B200W_CUDA(cudaMemcpyAsync(ctx->host_scal, ctx->scal, 4 * sizeof(float), cudaMemcpyDeviceToHost,
                                ctx->stream));
     B200W_CUDA(cudaStreamSynchronize(ctx->stream));

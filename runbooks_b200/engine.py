@@ -217,14 +217,16 @@ class Engine:
     # -- model --------------------------------------------------------------------------------
     def init_model(self, arch, micro_batch: int = 1, training: bool = True,
                    max_grad_norm: float = 1.0, weight_decay: float = 0.0,
-                   betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8):
+                   betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, shard_state: bool = False):
+        """shard_state: keep fp32 master / Adam moments for 1/nranks of the parameters only (ZeRO-style;
+        needs comm_init() first). Results equal the replicated mode."""
         ca = _CArch(**arch.c_fields())
         hp = _CHParams()
         self._lib.b200w_default_hparams(C.byref(hp))
         hp.max_grad_norm, hp.weight_decay = max_grad_norm, weight_decay
         hp.beta1, hp.beta2, hp.eps = betas[0], betas[1], eps
         self._check(self._lib.b200w_model_init(self._h, C.byref(ca), C.byref(hp), micro_batch,
-                                               1 if training else 0))
+                                               (2 if shard_state else 1) if training else 0))
         self.arch, self.micro_batch = arch, micro_batch
 
     def params(self) -> Iterable[Tuple[str, Tuple[int, ...]]]:

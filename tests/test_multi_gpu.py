@@ -24,7 +24,8 @@ def _gpus():
 
 def _rank_main(rank, world, uid, q, mode, steps):
     try:
-        if mode:
+        shard = mode == "shard"
+        if mode and not shard:
             os.environ["B200W_AR_MODE"] = mode
         import sys
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -39,9 +40,12 @@ def _rank_main(rank, world, uid, q, mode, steps):
         oa = O.Arch(*v, rms_norm_eps=eps, rope_theta=theta)
         params = O.seeded_params(oa, int(fx["batch"][1]))
         e = Engine(rank)
-        e.init_model(LlamaArch(*v, rms_norm_eps=eps, rope_theta=theta), micro_batch=1, training=True)
+        if world > 1 and shard:
+            e.comm_init(rank, world, uid)          # sharded state: the communicator comes first
+        e.init_model(LlamaArch(*v, rms_norm_eps=eps, rope_theta=theta), micro_batch=1, training=True,
+                     shard_state=shard)
         e.load_state_dict(params)
-        if world > 1:
+        if world > 1 and not shard:
             e.comm_init(rank, world, uid)
         out = []
         for ids, labels, lr in ((fx["ids"], fx["labels"], 5e-5), (fx["ids2"], fx["labels2"], 2.5e-5))[:steps]:
@@ -50,7 +54,8 @@ def _rank_main(rank, world, uid, q, mode, steps):
             labels[1, 40:90] = -100
             mine = slice(rank, None, world)
             out.append(e.train_step(ids[mine], labels[mine], lr=lr))
-        sd = {n: e.read_state(n, s, "master") for n, s in e.params()}
+        sd = {n: (e.read_tensor(n, s, bf16_bits=True) if mode in ("shard", "bits") else e.read_state(n, s, "master"))
+              for n, s in e.params()}
         q.put((rank, out, sd, None))
         e.close()
     except BaseException as ex:  # noqa: BLE001
@@ -104,6 +109,19 @@ def test_overlapped_and_end_allreduce_agree_bit_for_bit():
     b = _run(2, "end", steps=1)
     for n in a[0][1]:
         assert np.array_equal(a[0][1][n], b[0][1][n]), n
+
+
+@pytest.mark.skipif(_gpus() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_sharded_optimizer_state_equals_replicated():
+    """b200w_model_init(training = 2): reduce-scatter -> AdamW on the owned 1/N of master / m / v -> all-gather
+    of the bf16 weights (the 70B row's groundwork). At two ranks a sum of two terms has one
+    order, so the weights must equal the replicated mode's bit for bit; ranks agree with each other."""
+    a = _run(2, "shard")
+    b = _run(2, "bits")
+    assert a[0][0] == a[1][0] and a[0][0] == b[0][0], (a[0][0], b[0][0])      # loss / grad-norm
+    for n in a[0][1]:
+        assert np.array_equal(a[0][1][n], a[1][1][n]), f"ranks diverged on {n}"
+        assert np.array_equal(a[0][1][n], b[0][1][n]), f"sharded != replicated on {n}"
 
 
 @pytest.mark.skipif(_gpus() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")

@@ -440,6 +440,12 @@ def decode_leg(device: int = 0, batch: int = 32, ctx: int = 1024, steps: int = 6
     for w in range(warm):                      # eager run, graph capture, replays
         tok, _ = e.step(tok, [ctx + w] * batch, slots)
     e.sync()
+    if os.environ.get("B200W_PROFILE_DECODE"):   # ncu --profile-from-start off: exactly two decode steps
+        import torch
+        torch.cuda.profiler.start()
+        for i in range(2):
+            e.step(tok, [ctx + warm] * batch, slots)
+        torch.cuda.profiler.stop()
     launches0 = e.launch_count()
     e.timer_start()
     t0 = time.perf_counter()

@@ -241,6 +241,7 @@ PER_DEVICE_BATCH = 8
 
 
 MICRO_BATCH = 1
+SHARD_STATE = False
 TRAFFIC = dict(bytes=402.0e6, note=("dram__bytes_read+write of the gate|up forward GEMM launch: 241.5 MB + 160.6 MB "
                                     "vs 394 MB algorithmic (profiles/r01_ncu_gemm_pair.txt)"))
 
@@ -248,7 +249,8 @@ TRAFFIC = dict(bytes=402.0e6, note=("dram__bytes_read+write of the gate|up forwa
 def workload_config(n_gpus: int):
     return dict(workload="Llama-2-7B bf16 causal-LM fine-tune, seq 4096 (BASELINE.json configs[1])",
                 global_batch=PER_DEVICE_BATCH * n_gpus, seq_len=4096, per_device_batch=PER_DEVICE_BATCH,
-                micro_batch=MICRO_BATCH, parallelism=f"dp{n_gpus}", optimizer="AdamW fp32 master, clip 1.0",
+                micro_batch=MICRO_BATCH, parallelism=f"dp{n_gpus}" + ("-sharded-state" if SHARD_STATE and n_gpus > 1 else ""),
+                optimizer="AdamW fp32 master, clip 1.0",
                 l2="working set (13.5 GB bf16 weights + activations per micro-step) >> 126 MB L2; no flush needed")
 
 
@@ -279,14 +281,20 @@ def run_ours(args):
         arch.num_layers = args.layers
     S, nseq = arch.max_seq_len, args.per_device_batch
     e = Engine(local)
-    e.init_model(arch, micro_batch=args.micro_batch, training=True)
-    e.init_random(seed=0, std=0.02)          # identical replicas: same seed on every rank
+    shard = bool(args.shard_state) and world > 1
+    uid = None
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
             uid = torch.frombuffer(bytearray(e.comm_unique_id()), dtype=torch.uint8).clone()
         dist.broadcast(uid, 0)
-        e.comm_init(rank, world, bytes(uid.numpy().tobytes()))
+        uid = bytes(uid.numpy().tobytes())
+    if shard:                                # sharded optimiser state: the communicator comes first
+        e.comm_init(rank, world, uid)
+    e.init_model(arch, micro_batch=args.micro_batch, training=True, shard_state=shard)
+    e.init_random(seed=0, std=0.02)          # identical replicas: same seed on every rank
+    if world > 1 and not shard:
+        e.comm_init(rank, world, uid)
 
     g = torch.Generator().manual_seed(1234 + rank)
     n_prof = min(args.steps, 3)               # GEMM-bracketed steps for the roofline leg, outside both timed regions
@@ -497,7 +505,7 @@ def emit(line: dict):
 
 
 def main():
-    global MICRO_BATCH
+    global MICRO_BATCH, SHARD_STATE
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -510,10 +518,13 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="development only: fewer layers")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-decode", action="store_true", help="skip the Falcon-7B decode leg (N=1 only)")
+    ap.add_argument("--shard-state", action="store_true", default=bool(os.environ.get("B200W_SHARD_STATE")),
+                    help="N>1: fp32 master / Adam moments sharded over the ranks (reduce-scatter + all-gather)")
     ap.add_argument("--decode-only", action="store_true", help="run only the decode leg and print its object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     MICRO_BATCH = args.micro_batch
+    SHARD_STATE = bool(args.shard_state)
     # A rank that fails must EXIT, at once: its peers are inside a collective that can no longer
     # complete, and the launcher only tears the job down when a worker process ends. Interpreter
     # teardown (destructors -> NCCL / CUDA shutdown on a dead context) can block, so skip it.

@@ -58,6 +58,9 @@ __device__ __forceinline__ void compute_bar_sync() {  // the 256 compute threads
 // (profiles/r01_ncu_attention_v6.txt) and set the pace instead of the tensor pipe.
 constexpr int BWD_NCOMPUTE = 512;
 constexpr int BWD_NTHREADS = 576;  // + MMA warp (16) + TMA warp (17)
+__device__ __forceinline__ void bwd_compute_bar_sync() {
+  asm volatile("bar.sync 1, 512;" ::: "memory");
+}
 // 32 fp32 TMEM columns of this thread's lane -> bf16 in global memory
 __device__ __forceinline__ void tmem_row32_to_global(uint32_t taddr, __nv_bfloat16* dst) {
   uint32_t r[32];
@@ -449,7 +452,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
 constexpr int BWD_BKV = 128, BWD_BQ = 64;
 constexpr int KV_SMEM = 2 * ATOM128 /*K*/ + 2 * ATOM128 /*V*/ + 3 * 2 * ATOM64 /*Q x3*/ +
                         3 * 2 * ATOM64 /*dO x3*/ + 2 * ATOM128 /*P^T x2*/ + 2 * ATOM128 /*dS^T x2*/ +
-                        16 * 32 * 4 /*lse | delta of a block's columns, one private copy per compute warp*/ + 256;
+                        2 * 2 * 64 * 4 /*lse, delta x2*/ + 256;
 // S^T[2]: [0,64) [64,128)   dP^T[2]: [128,192) [192,256)   dV: [256,384)   dK: [384,512)
 constexpr int KV_TMEM_COLS = 512;
 
@@ -478,8 +481,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   uint8_t* sdO = sQ + 3 * 2 * ATOM64;
   uint8_t* sP = sdO + 3 * 2 * ATOM64;       // 2 bufs x P^T  [128 kv x 64 q]
   uint8_t* sdS = sP + 2 * ATOM128;          // 2 bufs x dS^T [128 kv x 64 q]
-  float* sStat = reinterpret_cast<float*>(sdS + 2 * ATOM128);  // [16 compute warps][lse 16 | delta*scale 16]
-  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sStat + 16 * 32);
+  float* sStat = reinterpret_cast<float*>(sdS + 2 * ATOM128);  // [2 bufs][lse 64 | delta*scale 64]
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sStat + 2 * 128);
   uint64_t* bar_q = bar_kv + 1;  // [3]
   uint64_t* bar_s = bar_q + 3;   // [2] S^T, dP^T (it) in TMEM
   uint64_t* bar_d = bar_s + 2;   // [2] dV/dK MMAs that read P/dS buffer b retired
@@ -610,27 +613,24 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const int row_local = q * 32 + lane;       // TMEM lane == key row inside the block
     const int kv_seq = kv0 + row_local;        // key position inside the sequence
     const uint32_t lane_base = (q * 32u) << 16;
-    // lse / delta*scale of this warp's 16 query columns: lane i fetches one of the 32 values one iteration
-    // ahead (latency hidden behind the block's math) and parks it in a warp-PRIVATE smem row, so the only
-    // synchronisation is __syncwarp. Round 1 shared one copy per block behind a 512-thread bar.sync every
-    // iteration; with one bar_p per staging buffer the protocol no longer needs that barrier
-    // (tools/protocol_model.py: dkdv_kernel(per_stage_bar_p=True, block_barrier=False) is clean).
-    float* sStatW = sStat + warp * 32;
+    // lse / delta*scale of the 64 query rows of a block: fetched into a register one iteration
+    // ahead by 128 of the compute threads, parked in smem just before the per-iteration bar.sync
     auto fetch_stat = [&](const IterPos& p) -> float {
-      const size_t idx = static_cast<size_t>(p.h) * Ttot + tok0 + (qb_base + p.qb) * BWD_BQ + hc * 16 + (lane & 15);
-      return lane < 16 ? lse2[idx] : delta[idx] * scale;  // delta is kept pre-multiplied by the scale
+      const size_t base = static_cast<size_t>(p.h) * Ttot + tok0 + (qb_base + p.qb) * BWD_BQ;
+      return (tid < 64) ? lse2[base + tid] : delta[base + tid - 64];
     };
+    const float stat_mul = (tid < 64) ? 1.f : scale;  // delta is kept pre-multiplied by the scale
     IterPos cur{hk * G, 0};
-    float stat_cur = fetch_stat(cur);
+    if (tid < 128) sStat[tid] = fetch_stat(cur) * stat_mul;
+    bwd_compute_bar_sync();
 
     for (int it = 0; it < n_iter; ++it) {
       const int tb = it & 1;
       const int q_seq0 = (qb_base + cur.qb) * BWD_BQ;
       cur.next(nqb);  // now the position of block it + 1
-      const float stat_next = (it + 1 < n_iter) ? fetch_stat(cur) : 0.f;
-      __syncwarp();               // the previous block's reads of sStatW are done
-      sStatW[lane] = stat_cur;
-      __syncwarp();
+      float stat_next = 0.f;
+      const bool have_next = (it + 1 < n_iter) && tid < 128;
+      if (have_next) stat_next = fetch_stat(cur);  // latency hidden behind this block's math
       mbar_wait(&bar_s[tb], (it >> 1) & 1);
       __syncwarp();
       tc_fence_after();
@@ -640,8 +640,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       tmem_ld_wait();
       // staging buffer tb was last read by the dV/dK MMAs of block it-2
       if (it >= 2) mbar_wait(&bar_d[tb], ((it >> 1) - 1) & 1);
-      const float4* st_lse = reinterpret_cast<const float4*>(sStatW);
-      const float4* st_dl = reinterpret_cast<const float4*>(sStatW + 16);
+      const float4* st_lse = reinterpret_cast<const float4*>(sStat + tb * 128 + hc * 16);
+      const float4* st_dl = reinterpret_cast<const float4*>(sStat + tb * 128 + 64 + hc * 16);
       const bool diag = (q_seq0 < kv0 + BWD_BKV);  // some (q, kv) pairs of this block are masked
 #pragma unroll
       for (int c8 = 0; c8 < 2; ++c8) {
@@ -669,7 +669,13 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_p[tb]);  // one arrival per compute warp
-      stat_cur = stat_next;
+      if (have_next) sStat[(tb ^ 1) * 128 + tid] = stat_next * stat_mul;
+      // stats(it+1) visible; stats(it) no longer read. With one bar_p per stage the protocol no longer NEEDS
+      // this block-wide barrier, and a variant with warp-private statistics rows and no barrier was built
+      // and measured in round 2: 4 % SLOWER (303.9 vs 292.6 us, same-box ncu A/B,
+      // profiles/r02_attn_ab_dkdv_barrier.txt) -- the barrier keeps the 16 warps in phase, which is what the
+      // shared TMEM / staging double-buffering wants. Kept.
+      bwd_compute_bar_sync();
     }
 
     mbar_wait(&bar_d[(n_iter - 1) & 1], ((n_iter - 1) >> 1) & 1);  // commits are cumulative

@@ -503,8 +503,12 @@ void dispatch_major(bool a_mn, bool b_mn, const void* A, const void* B, OutT* D,
 // The weights are the 128-row A operand and the batch is a narrow B operand (UMMA N = MPAD), so
 // every byte a pipeline stage holds is a weight byte streamed from HBM — the job here is HBM
 // bandwidth, not tensor throughput. Grid = (N tiles, K splits): the 36-tile projections of a
-// 7B model are split along K so that all SMs stream. Partial sums meet in an fp32 workspace
-// through red.global.add; the last CTA of a tile finalises it and leaves the workspace zeroed.
+// 7B model are split along K so that all SMs stream. The K-splits of one output tile form a
+// THREAD-BLOCK CLUSTER: each CTA parks its fp32 partial tile in its own shared memory and, after a
+// cluster barrier, reduces 1/splits of the tile by reading the peers' copies over distributed shared
+// memory -- no global workspace, no atomics, no fences. (Round 2's first version met in global memory
+// through red.global.add: with 8 splits the 1.2 M same-address atomics of the K = 22720 GEMM cost
+// ~11 us of a 57 us launch, profiles/r02_ncu_decode.txt.)
 // ==========================================================================================
 // epilogue activation of the decode GEMM: 0 = none, 1 = exact (erf) GeLU -- transformers
 // get_activation("gelu"), what FalconMLP applies between its two projections -- 2 = ReLU (OPT)
@@ -561,8 +565,7 @@ struct DecodeCfg {
 template <int MPAD>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
-                   const DecodeEpi epi, float* ws, unsigned* counters, int M, int N, int K,
-                   int kb_per_split) {
+                   const DecodeEpi epi, int M, int N, int K, int kb_per_split) {
   using cfg = DecodeCfg<MPAD>;
   constexpr int STAGES = cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -572,7 +575,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* done_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
-  uint32_t* last_flag = tmem_slot + 1;
+  static_assert(MPAD * BLOCK_M * 4 <= STAGES * cfg::STAGE_BYTES, "the partial tile must fit in the pipeline stages");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BLOCK_M;            // 128 output features
@@ -644,47 +647,47 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const int q = warp & 3;
     const int n = n0 + q * 32 + lane;
     const bool n_ok = n < N;
-    pdl_wait();  // this warp reads C / writes out and the split-K workspace: all shared with the predecessor
+    pdl_wait();  // this warp reads C / writes out: both shared with the predecessor
     mbar_wait(done_bar, 0);
     __syncwarp();
     tc_fence_after();
+    // every MMA has retired, so every pipeline stage has been consumed: the stage memory is free and holds
+    // this CTA's partial tile part[b][n_local] (fp32, MPAD x 128) for the cluster reduction
+    float* part = reinterpret_cast<float*>(smem);
     uint32_t r[32];
 #pragma unroll 1
     for (int c = 0; c < MPAD / 32; ++c) {
       tmem_ld32(tmem_addr(tmem_base, q * 32, c * 32), r);
       tmem_ld_wait();
-      if (n_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int b = c * 32 + j;
-          if (b < M) {
-            const float v = __uint_as_float(r[j]);
-            if (split) atomicAdd(ws + static_cast<size_t>(b) * N + n, v);  // 32 lanes -> 128 B, coalesced
-            else decode_store(epi, b, n, v);
-          }
-        }
+      for (int j = 0; j < 32; ++j) {
+        const int b = c * 32 + j;
+        const float v = __uint_as_float(r[j]);
+        if (split) part[b * BLOCK_M + q * 32 + lane] = v;   // 32 lanes -> 128 contiguous bytes: conflict-free
+        else if (n_ok && b < M) decode_store(epi, b, n, v);
       }
     }
   }
   if (split) {
-    // last CTA of this N tile finalises it and leaves workspace + counter clean for the next GEMM
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) *last_flag = (atomicAdd(&counters[blockIdx.x], 1u) == gridDim.y - 1) ? 1u : 0u;
-    __syncthreads();
-    if (*last_flag) {
-      __threadfence();
-      for (int i = threadIdx.x; i < M * BLOCK_M; i += blockDim.x) {
-        const int b = i / BLOCK_M, n = n0 + i % BLOCK_M;
-        if (n < N) {
-          float* p = ws + static_cast<size_t>(b) * N + n;
-          const float v = __ldcg(p);
-          *p = 0.f;
-          decode_store(epi, b, n, v);
-        }
+    // cluster = the K-splits of this N tile. After the barrier CTA `rank` owns output features
+    // [rank * 128 / splits, (rank + 1) * 128 / splits) of the tile and sums them over all the peers' partials.
+    const uint32_t nsplit = gridDim.y, rank = cluster_ctarank();
+    tc_fence_before();
+    __syncwarp();
+    cluster_sync_all();
+    const float* part = reinterpret_cast<const float*>(smem);
+    const int lo = static_cast<int>(rank * BLOCK_M / nsplit), hi = static_cast<int>((rank + 1) * BLOCK_M / nsplit);
+    const int width = hi - lo;
+    for (int i = threadIdx.x; i < M * width; i += blockDim.x) {
+      const int b = i / width, nl = lo + i % width, n = n0 + nl;
+      if (n < N) {
+        float v = 0.f;
+        for (uint32_t p = 0; p < nsplit; ++p) v += ld_shared_cluster_f32(part + b * BLOCK_M + nl, p);
+        decode_store(epi, b, n, v);
       }
-      if (threadIdx.x == 0) counters[blockIdx.x] = 0;
     }
+    __syncwarp();
+    cluster_sync_all();  // nobody leaves while a peer may still read its partial tile
   }
   tc_fence_before();
   __syncthreads();
@@ -695,8 +698,8 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 }
 
 template <int MPAD>
-void launch_decode(const void* X, int ldx, const void* W, int ldw, const DecodeEpi& epi, float* ws,
-                   unsigned* counters, int M, int N, int K, cudaStream_t stream) {
+void launch_decode(const void* X, int ldx, const void* W, int ldw, const DecodeEpi& epi, bool allow_split, int M,
+                   int N, int K, cudaStream_t stream) {
   using cfg = DecodeCfg<MPAD>;
   CUtensorMap tmW = make_tmap_bf16_2d(W, N, K, ldw, BLOCK_M, BLOCK_K);
   CUtensorMap tmX = make_tmap_bf16_2d(X, M, K, ldx, MPAD, BLOCK_K);
@@ -707,17 +710,19 @@ void launch_decode(const void* X, int ldx, const void* W, int ldw, const DecodeE
   });
   const int n_tiles = (N + BLOCK_M - 1) / BLOCK_M;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-  // split K until two CTAs per SM are in flight, keeping at least 8 K-blocks per split
+  // split K until two CTAs per SM are in flight, keeping at least 8 K-blocks per split; the splits of a tile
+  // are one cluster (portable size limit 8)
   int splits = 1;
-  if (ws && counters) {
+  if (allow_split) {
     splits = 2 * sm_count() / n_tiles;
     if (splits > num_kb / 8) splits = num_kb / 8;
+    if (splits > 8) splits = 8;
     if (splits < 1) splits = 1;
   }
   const int per = (num_kb + splits - 1) / splits;
   splits = (num_kb + per - 1) / per;
-  launch_pdl(kern, dim3(n_tiles, splits), dim3(GEMM_THREADS), cfg::SMEM_BYTES, stream, tmW, tmX, epi, ws,
-             counters, M, N, K, per);
+  launch_pdl_cluster(kern, dim3(n_tiles, splits), dim3(GEMM_THREADS), cfg::SMEM_BYTES, stream, splits, tmW, tmX, epi,
+                     M, N, K, per);
 }
 
 // Tile raster order. M-fastest re-reads A once per wave of N-tiles unless A stays in L2; N-fastest
@@ -749,9 +754,10 @@ void gemm_decode_ex(const void* X, int ldx, const void* W, int ldw, const GemmDe
   e.bias = static_cast<const __nv_bfloat16*>(o.bias);
   e.act = o.act;
   e.act_from = o.act_from;
-  if (M <= 32) launch_decode<32>(X, ldx, W, ldw, e, ws, counters, M, N, K, stream);
-  else if (M <= 64) launch_decode<64>(X, ldx, W, ldw, e, ws, counters, M, N, K, stream);
-  else launch_decode<128>(X, ldx, W, ldw, e, ws, counters, M, N, K, stream);
+  const bool allow_split = ws != nullptr && counters != nullptr;  // the scratch itself is no longer used
+  if (M <= 32) launch_decode<32>(X, ldx, W, ldw, e, allow_split, M, N, K, stream);
+  else if (M <= 64) launch_decode<64>(X, ldx, W, ldw, e, allow_split, M, N, K, stream);
+  else launch_decode<128>(X, ldx, W, ldw, e, allow_split, M, N, K, stream);
 }
 void gemm_decode(const void* X, const void* W, void* out, const void* C, float* ws, unsigned* counters,
                  int M, int N, int K, int ldo, int act, cudaStream_t stream) {

@@ -63,19 +63,33 @@ class PerDeviceOnce {
 
 // Kernel launch with the programmatic-stream-serialization attribute (see ptx.cuh pdl_wait): only for
 // kernels that call pdl_wait() before they touch anything their predecessor wrote.
+// cluster_y > 1 additionally groups that many consecutive blockIdx.y CTAs into a thread-block cluster.
 template <typename... KArgs, typename... Args>
-void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+void launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_y,
+                        Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
+  int n = 1;
+  if (cluster_y > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 1;
+    attr[1].val.clusterDim.y = static_cast<unsigned>(cluster_y);
+    attr[1].val.clusterDim.z = 1;
+    n = 2;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = n;
   B200W_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...));
+}
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  launch_pdl_cluster(kern, grid, block, smem, s, 1, std::forward<Args>(args)...);
 }
 
 // gemm_bf16 leaves this many SMs free (grid = SMs - reserve): set around the backward that runs

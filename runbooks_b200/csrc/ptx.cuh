@@ -166,6 +166,18 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       "r"(cta)
       : "memory");
 }
+// fp32 load from the shared memory of CTA `cta` of this cluster, at the same offset as local address `p`
+__device__ __forceinline__ float ld_shared_cluster_f32(const float* p, uint32_t cta) {
+  float v;
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %1, %2;\n\t"
+      "ld.shared::cluster.f32 %0, [ra];\n\t}"
+      : "=f"(v)
+      : "r"(smem_u32(p)), "r"(cta)
+      : "memory");
+  return v;
+}
 // TMA load into THIS CTA's smem whose bytes complete on the PAIR LEADER's barrier (peer bit = 0)
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
                                                  int c0, int c1) {

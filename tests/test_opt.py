@@ -59,39 +59,49 @@ def test_opt_forward_logits_and_greedy():
     e.close()
 
 
+def _torch_bf16_gradient_distance(params, ids, labels, oa, ref):
+    """How far the TORCH path itself lands from its own fp32 gradients when parameters and activations are
+    bf16 -- what any bf16 implementation, HF's included, computes. For this ReLU model it is 8-9 % on most
+    tensors (measured): a bf16 perturbation of a pre-activation near zero flips the ReLU mask, and each flip
+    is a 100 % error on that element (SiLU models sit at ~1 %)."""
+    import torch
+    from oracle.llama_oracle import causal_lm_loss, trainer_num_items
+    Pb = {k: torch.tensor(v).bfloat16().requires_grad_(True) for k, v in params.items()}
+    lab = torch.tensor(labels)
+    loss, _ = causal_lm_loss(OO.forward(Pb, torch.tensor(ids), oa).float(), lab, trainer_num_items(lab))
+    loss.backward()
+    return {k: rel_err(p.grad.float().numpy(), ref[k]) for k, p in Pb.items()}
+
+
 def test_opt_gradients_match_hf():
-    """Every gradient tensor against the fp32 oracle on the FULL tensor (the oracle itself is pinned to HF's
-    gradients at 1e-5 on CPU, tests/test_oracle_golden.py) and against HF's strided samples. Matrices: 3e-2
-    relative Frobenius. 1-D tensors (biases, LayerNorm parameters) are sums over the 256 tokens of bf16-rounded
-    per-token gradients with heavy cancellation, so their error is judged against the tensor's largest entry."""
+    """Every gradient tensor, in full, against the fp32 oracle (itself pinned to HF's gradients at 1e-5 on CPU,
+    tests/test_oracle_golden.py). Bar: 3e-2 relative Frobenius, or 1.5 x the distance the torch path shows
+    between its own bf16 and fp32 runs on that tensor, whichever is larger (ReLU: see the helper)."""
     fx, oa, arch, params = _load()
     e = _engine(arch, params, 2)
     loss = e.forward_backward(fx["ids"], fx["labels"])
     assert abs(loss - float(fx["loss"])) < 1e-3 * float(fx["loss"])
     ref = OO.train_step(params, fx["ids"], fx["labels"], oa)["grads"]
+    floor = _torch_bf16_gradient_distance(params, fx["ids"], fx["labels"], oa, ref)
     rows = []
     for name, shape in e.params():
         g = e.read_state(name, shape, "grad")
-        r = ref[name]
         if name.endswith("k_proj.bias"):
             # mathematically zero (softmax is invariant to a per-query constant): both sides hold rounding noise
             assert np.linalg.norm(g) < 1e-3 * float(fx["gnorm"]), name
             continue
-        err = rel_err(g, r)
-        err_max = float(np.abs(g - r).max() / max(np.abs(r).max(), 1e-30))
-        err_hf = rel_err(g.reshape(-1)[::17], fx["grad/" + name])
-        rows.append((err, err_max, err_hf, name, g.ndim))
+        rows.append((rel_err(g, ref[name]), floor[name], name))
+        gn = float(np.linalg.norm(g.astype(np.float64)))
+        assert abs(gn - float(fx["gradnorm/" + name])) < 2e-2 * float(fx["gradnorm/" + name]), name   # norms: 2 %
     rows.sort(reverse=True)
-    for err, err_max, err_hf, name, nd in rows[:6]:
-        print(f"opt grad {name:60s} rel_err {err:.3e} max-norm err {err_max:.3e} vs HF samples {err_hf:.3e}")
-    for err, err_max, err_hf, name, nd in rows:
-        if nd == 2:
-            assert err < 3e-2, (name, err)
-        else:
-            assert err_max < 3e-2, (name, err, err_max)
+    for err, fl, name in rows[:5]:
+        print(f"opt grad {name:58s} rel_err {err:.3e} (torch bf16-vs-fp32 on the same tensor: {fl:.3e})")
+    for err, fl, name in rows:
+        assert err < max(3e-2, 1.5 * fl), (name, err, fl)
     # nn.Embedding(padding_idx): the pad row's gradient is the tied head's contribution only
-    g = e.read_state("model.decoder.embed_tokens.weight", params["model.decoder.embed_tokens.weight"].shape, "grad")
-    assert rel_err(g[oa.pad_token_id], ref["model.decoder.embed_tokens.weight"][oa.pad_token_id]) < 3e-2
+    tname = "model.decoder.embed_tokens.weight"
+    g = e.read_state(tname, params[tname].shape, "grad")
+    assert rel_err(g[oa.pad_token_id], ref[tname][oa.pad_token_id]) < max(3e-2, 1.5 * floor[tname])
     e.close()
 
 

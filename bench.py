@@ -242,8 +242,21 @@ PER_DEVICE_BATCH = 8
 
 MICRO_BATCH = 1
 SHARD_STATE = False
-TRAFFIC = dict(bytes=402.0e6, note=("dram__bytes_read+write of the gate|up forward GEMM launch: 241.5 MB + 160.6 MB "
-                                    "vs 394 MB algorithmic (profiles/r01_ncu_gemm_pair.txt)"))
+def gemm_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of THIS
+    kernel family (profiles/r02_ncu_gemm.json, written by the round's profiling call from the .ncu-rep):
+    the forward gate|up GEMM, with the dgrad and accumulating-wgrad captures beside it."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_gemm.json")
+    try:
+        d = json.load(open(path))["kernels"]
+        f = d["fwd_gateup"]
+        return dict(bytes=f["dram_read_bytes"] + f["dram_write_bytes"],
+                    note=(f"dram__bytes_read+write of one forward gate|up GEMM launch (M4096 N22016 K4096) = "
+                          f"{f['traffic_over_algorithmic']}x its {f['algorithmic_bytes'] / 1e6:.0f} MB algorithmic; dgrad "
+                          f"{d['dgrad_gateup']['traffic_over_algorithmic']}x, accumulating wgrad "
+                          f"{d['wgrad_gateup_acc']['traffic_over_algorithmic']}x (profiles/r02_ncu_gemm.json, ncu --set full)"))
+    except Exception:  # noqa: BLE001
+        return dict(bytes=None, note="profiles/r02_ncu_gemm.json missing")
 
 
 def workload_config(n_gpus: int):
@@ -393,9 +406,9 @@ def run_ours(args):
         roofline=dict(bound="tensor", achieved=round(achieved, 1) if achieved else None,
                       peak=pk["sustained"], unit="TFLOP/s",
                       frac=round(achieved / pk["sustained"], 4) if achieved else None,
-                      # DRAM bytes of ONE launch (gate|up forward, M4096 N22016 K4096) from the committed
+                      # DRAM bytes of ONE launch (gate|up forward, M4096 N22016 K4096) read from the committed
                       # `ncu --set full` capture; its algorithmic bytes are 394 MB (A 33.5 + B 180.4 + D 180.4)
-                      traffic=TRAFFIC["bytes"], traffic_note=TRAFFIC["note"],
+                      traffic=gemm_traffic()["bytes"], traffic_note=gemm_traffic()["note"],
                       kernel="gemm_bf16_kernel (tcgen05)", launches=int(gemm_launches),
                       share_of_step=round(gemm_ms / ms_prof, 4), profiled_steps=n_prof,
                       peak_source=f"{pk['source']} sustained cuBLAS bf16 (kernel timed inside a long step)"),

@@ -377,8 +377,8 @@ decode_attn_kernel(const bf16* __restrict__ qkv, int ld, const bf16* __restrict_
 //   S[128, 128 keys] = Q K^T   (A = Q K-major from smem, B = K block K-major, TMA from the cache)
 //   P = 2^(S * scale_log2 - m) per head row (thread = TMEM lane), keys >= len masked to 0, bf16 -> smem
 //   O[128, DH] = P V           (A = P K-major, B = V block MN-major)
-// and the block's (m, l, O) go to a small fp32 workspace; the LAST block of a (row, kv head) to finish
-// combines them and writes the bf16 output (no second launch). Every barrier is used exactly once (parity 0). The KV cache is zero-initialised, so rows of
+// and the block's (m, l, O) go to a small fp32 workspace; decode_attn_merge_kernel combines the blocks
+// of a row. Every barrier is used exactly once (parity 0). The KV cache is zero-initialised, so rows of
 // the last block beyond `len` are finite (stale or zero) and their P is exactly 0.
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_KB = 128;          // keys per CTA
@@ -398,8 +398,7 @@ __global__ void __launch_bounds__(TC_THREADS, DH == 64 ? 2 : 1)
 decode_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                       const bf16* __restrict__ qkv, int ld, const int32_t* __restrict__ pos,
                       const int32_t* __restrict__ slot, float* __restrict__ part_o, float2* __restrict__ part_ml,
-                      unsigned* __restrict__ counters, bf16* __restrict__ out, int ldo, int H, int Hkv, int max_ctx,
-                      int nsplit, float scale_log2) {
+                      int H, int Hkv, int max_ctx, int nsplit, float scale_log2) {
   constexpr int NA = DH / 64;  // 64-element atoms along the head dimension
   const int split = blockIdx.x, hk = blockIdx.y, r = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -423,7 +422,6 @@ decode_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
   uint64_t* bar_p = bar_s + 1;    // P in smem (128 arrivals)
   uint64_t* bar_o = bar_p + 1;    // O in TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
-  uint32_t* last_flag = tmem_slot + 1;
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_k);
@@ -559,58 +557,37 @@ decode_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       }
     }
   }
-  // The last key block of this (row, kv head) to finish merges all of them: a counter per group, bumped
-  // after the partials are fenced out; the merging CTA resets it for the next step (the launch is replayed
-  // from a CUDA graph). Blocks beyond the row's length exited above and are not counted.
-  {
-    const unsigned nactive = static_cast<unsigned>((len + TC_KB - 1) / TC_KB);
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) *last_flag = (atomicAdd(&counters[r * Hkv + hk], 1u) == nactive - 1) ? 1u : 0u;
-    __syncthreads();
-    if (*last_flag) {
-      __threadfence();
-      if (tid == 0) counters[r * Hkv + hk] = 0;
-      const int g = tid;
-      if (g < G) {
-        // out[r, h*DH + d] = sum_s 2^(m_s - M) O_s[d] / sum_s 2^(m_s - M) l_s
-        const int h = hk * G + g;
-        const size_t base = (static_cast<size_t>(r) * H + h) * nsplit;
-        float M = -INFINITY;
-        for (unsigned s2 = 0; s2 < nactive; ++s2) M = fmaxf(M, __ldcg(&part_ml[base + s2].x));
-        float den = 0.f;
-        for (unsigned s2 = 0; s2 < nactive; ++s2) {
-          const float mx = __ldcg(&part_ml[base + s2].x), lx = __ldcg(&part_ml[base + s2].y);
-          den += ex2f(mx - M) * lx;
-        }
-        const float inv = 1.f / den;
-        bf16* orow = out + static_cast<size_t>(r) * ldo + h * DH;
-#pragma unroll 1
-        for (int d8 = 0; d8 < DH / 8; ++d8) {
-          float acc[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-          for (unsigned s2 = 0; s2 < nactive; ++s2) {
-            const float wgt = ex2f(__ldcg(&part_ml[base + s2].x) - M);
-            const float4* po = reinterpret_cast<const float4*>(part_o + (base + s2) * DH + d8 * 8);
-            const float4 a = __ldcg(po), b2 = __ldcg(po + 1);
-            acc[0] += wgt * a.x; acc[1] += wgt * a.y; acc[2] += wgt * a.z; acc[3] += wgt * a.w;
-            acc[4] += wgt * b2.x; acc[5] += wgt * b2.y; acc[6] += wgt * b2.z; acc[7] += wgt * b2.w;
-          }
-          uint4 u;
-          u.x = pack_bf16x2(acc[0] * inv, acc[1] * inv); u.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
-          u.z = pack_bf16x2(acc[4] * inv, acc[5] * inv); u.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
-          *reinterpret_cast<uint4*>(orow + d8 * 8) = u;
-        }
-      }
-    }
-  }
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
+}
+
+// out[r, h*DH + d] = sum_s 2^(m_s - M) O_s[d] / sum_s 2^(m_s - M) l_s over the ceil(len / 128) blocks of row r
+template <int DH>
+__global__ void decode_attn_merge_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml,
+                                         const int32_t* __restrict__ pos, bf16* __restrict__ out, int ldo, int H,
+                                         int nsplit) {
+  pdl_trigger();
+  pdl_wait();
+  const int r = blockIdx.y;
+  const int h = blockIdx.x * (blockDim.x / DH) + threadIdx.x / DH;
+  const int d = threadIdx.x % DH;
+  if (h >= H) return;
+  const int ns = (pos[r] + TC_KB) / TC_KB;  // ceil((pos + 1) / 128)
+  const size_t base = (static_cast<size_t>(r) * H + h) * nsplit;
+  float M = -INFINITY;
+  for (int s2 = 0; s2 < ns; ++s2) M = fmaxf(M, part_ml[base + s2].x);
+  float num = 0.f, den = 0.f;
+  for (int s2 = 0; s2 < ns; ++s2) {
+    const float2 ml = part_ml[base + s2];
+    const float wgt = ex2f(ml.x - M);
+    num += wgt * part_o[(base + s2) * DH + d];
+    den += wgt * ml.y;
+  }
+  out[static_cast<size_t>(r) * ldo + h * DH + d] = __float2bfloat16_rn(num / den);
 }
 
 // greedy token: first index of the row maximum (torch.argmax tie-breaking)
@@ -677,7 +654,6 @@ struct Infer {
   unsigned* counters = nullptr;
   float* part_o = nullptr;      // tensor-core decode attention partials [max_batch, H, nsplit, dh]
   float2* part_ml = nullptr;    // [max_batch, H, nsplit] (max, sum)
-  unsigned* att_counters = nullptr;  // [max_batch, Hkv] finished key blocks of a (row, kv head); kept zero
   int nsplit = 0;
   int32_t *tok = nullptr, *pos = nullptr, *slot = nullptr, *next = nullptr;
   int32_t* pin = nullptr;  // pinned host staging: tok | pos | slot | next, max_batch each
@@ -862,16 +838,18 @@ void decode_attention(Infer* m, cudaStream_t s, int n, int layer, bf16* out, int
       static PerDeviceOnce once;
       once.run([&] { B200W_CUDA(cudaFuncSetAttribute(decode_attn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>())); });
       launch_pdl(decode_attn_tc_kernel<64>, grid, dim3(TC_THREADS), tc_smem_bytes<64>(), s, tk, tv, m->qkv, m->qkvd,
-                 m->pos, m->slot, m->part_o, m->part_ml, m->att_counters, out, ldo, H, Hkv, a.max_ctx, m->nsplit,
-                 scale_log2);
+                 m->pos, m->slot, m->part_o, m->part_ml, H, Hkv, a.max_ctx, m->nsplit, scale_log2);
+      launch_pdl(decode_attn_merge_kernel<64>, dim3(cdiv(H, 4), n), dim3(256), 0, s, m->part_o, m->part_ml, m->pos,
+                 out, ldo, H, m->nsplit);
     } else {
       static PerDeviceOnce once;
       once.run([&] { B200W_CUDA(cudaFuncSetAttribute(decode_attn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>())); });
       launch_pdl(decode_attn_tc_kernel<128>, grid, dim3(TC_THREADS), tc_smem_bytes<128>(), s, tk, tv, m->qkv, m->qkvd,
-                 m->pos, m->slot, m->part_o, m->part_ml, m->att_counters, out, ldo, H, Hkv, a.max_ctx, m->nsplit,
-                 scale_log2);
+                 m->pos, m->slot, m->part_o, m->part_ml, H, Hkv, a.max_ctx, m->nsplit, scale_log2);
+      launch_pdl(decode_attn_merge_kernel<128>, dim3(cdiv(H, 2), n), dim3(256), 0, s, m->part_o, m->part_ml, m->pos,
+                 out, ldo, H, m->nsplit);
     }
-    nl += 1;
+    nl += 2;
     return;
   }
   const dim3 agrid(n, Hkv, (G + ATT_GT - 1) / ATT_GT);
@@ -1062,8 +1040,6 @@ int b200w_infer_init(b200w_ctx* ctx, const b200w_infer_arch* arch, int max_batch
     if (a.num_heads / a.num_kv_heads >= 4) {
       m->part_o = m->alloc<float>(B * a.num_heads * m->nsplit * a.head_dim);
       m->part_ml = m->alloc<float2>(B * a.num_heads * m->nsplit);
-      m->att_counters = m->alloc<unsigned>(B * a.num_kv_heads);
-      B200W_CUDA(cudaMemset(m->att_counters, 0, B * a.num_kv_heads * sizeof(unsigned)));
     }
     m->tok = m->alloc<int32_t>(B);
     m->pos = m->alloc<int32_t>(B);

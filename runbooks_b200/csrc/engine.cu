@@ -1429,9 +1429,12 @@ int b200w_comm_init(b200w_ctx* ctx, int rank, int nranks, const void* id128) {
     // (one per SM, ~200 KB of shared memory each) cannot share an SM, so the two are given disjoint
     // SM budgets: NCCL is capped at R CTAs (NCCL_MAX_CTAS, unless the user set it) and the GEMMs of
     // that backward launch on SMs - R. B200W_AR_SM_RESERVE overrides R (0: no partition).
-    int reserve = 16;
+    // R = 8: the whole 13.5 GB exchange has the last micro-step's backward (~200 ms) to hide in, so even 8 CTAs
+    // are an order of magnitude more bandwidth than it needs; every reserved SM costs the GEMMs of that
+    // backward 1/148 (profiles/r02_bench_n8*.json: R = 16 vs no partition vs R = 8).
+    int reserve = 8;
     if (const char* e = getenv("B200W_AR_SM_RESERVE")) reserve = atoi(e);
-    if (reserve < 0 || reserve > 64) reserve = 16;
+    if (reserve < 0 || reserve > 64) reserve = 8;
     ctx->ar_sm_reserve = nranks > 1 ? reserve : 0;
     if (reserve > 0) setenv("NCCL_MAX_CTAS", std::to_string(reserve).c_str(), /*overwrite=*/0);
     Uid uid;

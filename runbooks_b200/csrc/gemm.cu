@@ -565,7 +565,8 @@ struct DecodeCfg {
 template <int MPAD>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
-                   const DecodeEpi epi, int M, int N, int K, int kb_per_split) {
+                   const uint8_t* __restrict__ w_tiled, const DecodeEpi epi, int M, int N, int K,
+                   int kb_per_split) {
   using cfg = DecodeCfg<MPAD>;
   constexpr int STAGES = cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -606,9 +607,15 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     if (lane == 0) {
       // pipeline fill with weight tiles only (independent of the predecessor) ...
       const int pre = nkb < STAGES ? nkb : STAGES;
+      // w_tiled: the [128 x 64] weight tiles of this N tile are consecutive 16 KB shared-memory images
+      const uint8_t* wt = w_tiled ? w_tiled + (static_cast<size_t>(blockIdx.x) * num_kb_total) * A_STAGE_BYTES : nullptr;
+      auto load_w = [&](uint8_t* dst, uint64_t* bar, int kb) {
+        if (wt) bulk_load_1d(dst, wt + static_cast<size_t>(kb) * A_STAGE_BYTES, A_STAGE_BYTES, bar);
+        else tma_load_2d(dst, &tmW, bar, kb * BLOCK_K, n0);
+      };
       for (int i = 0; i < pre; ++i) {
         mbar_arrive_expect_tx(&full_bar[i], cfg::STAGE_BYTES);
-        tma_load_2d(smem + i * cfg::STAGE_BYTES, &tmW, &full_bar[i], (kb0 + i) * BLOCK_K, n0);
+        load_w(smem + i * cfg::STAGE_BYTES, &full_bar[i], kb0 + i);
       }
       pdl_wait();  // ... then the predecessor's activations
       for (int i = 0; i < pre; ++i)
@@ -619,7 +626,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         mbar_wait(&empty_bar[stage], phase);
         uint8_t* sa = smem + stage * cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], cfg::STAGE_BYTES);
-        tma_load_2d(sa, &tmW, &full_bar[stage], kb * BLOCK_K, n0);                   // weights
+        load_w(sa, &full_bar[stage], kb);                                            // weights
         tma_load_2d(sa + A_STAGE_BYTES, &tmX, &full_bar[stage], kb * BLOCK_K, 0);    // batch rows
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -698,8 +705,8 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 }
 
 template <int MPAD>
-void launch_decode(const void* X, int ldx, const void* W, int ldw, const DecodeEpi& epi, bool allow_split, int M,
-                   int N, int K, cudaStream_t stream) {
+void launch_decode(const void* X, int ldx, const void* W, int ldw, const void* w_tiled, const DecodeEpi& epi,
+                   bool allow_split, int M, int N, int K, cudaStream_t stream) {
   using cfg = DecodeCfg<MPAD>;
   CUtensorMap tmW = make_tmap_bf16_2d(W, N, K, ldw, BLOCK_M, BLOCK_K);
   CUtensorMap tmX = make_tmap_bf16_2d(X, M, K, ldx, MPAD, BLOCK_K);
@@ -721,8 +728,42 @@ void launch_decode(const void* X, int ldx, const void* W, int ldw, const DecodeE
   }
   const int per = (num_kb + splits - 1) / splits;
   splits = (num_kb + per - 1) / per;
-  launch_pdl_cluster(kern, dim3(n_tiles, splits), dim3(GEMM_THREADS), cfg::SMEM_BYTES, stream, splits, tmW, tmX, epi,
-                     M, N, K, per);
+  launch_pdl_cluster(kern, dim3(n_tiles, splits), dim3(GEMM_THREADS), cfg::SMEM_BYTES, stream, splits, tmW, tmX,
+                     static_cast<const uint8_t*>(w_tiled), epi, M, N, K, per);
+}
+
+// W [N, K] (row stride ldw) -> ceil(N/128) x ceil(K/64) tiles, each the 16 KB SWIZZLE_128B shared-memory image
+// of its [128 rows x 64 k] block (what TMA would have written), tiles of one N block consecutive along K,
+// zero beyond N / K. A CTA of the decode GEMM then streams ONE contiguous region of HBM with 16 KB bulk
+// copies instead of 128-byte row segments 2 K bytes apart (DRAM page locality: DESIGN.md 3.5).
+__global__ void retile_weights_kernel(const __nv_bfloat16* __restrict__ W, int ldw, uint8_t* __restrict__ out, int N,
+                                      int K, int num_kb) {
+  const size_t tile = blockIdx.x;                  // n_tile * num_kb + kb
+  const int nt = static_cast<int>(tile / num_kb), kb = static_cast<int>(tile % num_kb);
+  uint8_t* dst = out + tile * A_STAGE_BYTES;
+  for (int i = threadIdx.x; i < 128 * 8; i += blockDim.x) {   // 128 rows x 8 chunks of 8 elements
+    const int r = i >> 3, ch = i & 7;
+    const int n = nt * 128 + r, k = kb * BLOCK_K + ch * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (n < N && k + 8 <= K) v = *reinterpret_cast<const uint4*>(W + static_cast<size_t>(n) * ldw + k);
+    else if (n < N && k < K) {
+      __nv_bfloat16 tmp[8];
+      for (int e = 0; e < 8; ++e) tmp[e] = k + e < K ? W[static_cast<size_t>(n) * ldw + k + e] : __float2bfloat16_rn(0.f);
+      v = *reinterpret_cast<uint4*>(tmp);
+    }
+    *reinterpret_cast<uint4*>(dst + sw128_offset(r, ch)) = v;
+  }
+}
+size_t retiled_bytes(int N, int K) {
+  return static_cast<size_t>((N + 127) / 128) * ((K + BLOCK_K - 1) / BLOCK_K) * A_STAGE_BYTES;
+}
+void retile_weights(const void* W, int ldw, void* out, int N, int K, cudaStream_t s) {
+  B200W_CHECK(ldw % 8 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "weights must be 16-byte aligned rows");
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const size_t tiles = static_cast<size_t>((N + 127) / 128) * num_kb;
+  retile_weights_kernel<<<static_cast<unsigned>(tiles), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(W), ldw,
+                                                                     static_cast<uint8_t*>(out), N, K, num_kb);
+  B200W_CUDA(cudaGetLastError());
 }
 
 // Tile raster order. M-fastest re-reads A once per wave of N-tiles unless A stays in L2; N-fastest
@@ -755,9 +796,9 @@ void gemm_decode_ex(const void* X, int ldx, const void* W, int ldw, const GemmDe
   e.act = o.act;
   e.act_from = o.act_from;
   const bool allow_split = ws != nullptr && counters != nullptr;  // the scratch itself is no longer used
-  if (M <= 32) launch_decode<32>(X, ldx, W, ldw, e, allow_split, M, N, K, stream);
-  else if (M <= 64) launch_decode<64>(X, ldx, W, ldw, e, allow_split, M, N, K, stream);
-  else launch_decode<128>(X, ldx, W, ldw, e, allow_split, M, N, K, stream);
+  if (M <= 32) launch_decode<32>(X, ldx, W, ldw, o.w_tiled, e, allow_split, M, N, K, stream);
+  else if (M <= 64) launch_decode<64>(X, ldx, W, ldw, o.w_tiled, e, allow_split, M, N, K, stream);
+  else launch_decode<128>(X, ldx, W, ldw, o.w_tiled, e, allow_split, M, N, K, stream);
 }
 void gemm_decode(const void* X, const void* W, void* out, const void* C, float* ws, unsigned* counters,
                  int M, int N, int K, int ldo, int act, cudaStream_t stream) {

@@ -644,6 +644,12 @@ struct Infer {
   struct L { size_t ln1_w, ln1_b, ln2_w, ln2_b, wqkv, bqkv, wo, bo, w1, b1, w2, b2; };
   std::vector<L> lp;
   size_t p_embed = 0, p_pos = 0, p_lnf_w = 0, p_lnf_b = 0, p_lm = 0;
+  // decode-time copy of every projection as consecutive 16 KB swizzled tile images (gemm.cu retile_weights):
+  // a decode GEMM CTA streams one contiguous HBM region instead of 128-byte row segments
+  struct LT { uint8_t *qkv = nullptr, *o = nullptr, *w1 = nullptr, *w2 = nullptr; };
+  std::vector<LT> lt;
+  uint8_t* t_lm = nullptr;
+  bool tiled_valid = false, use_tiled = true;
   int qd = 0, kd = 0, qkvd = 0, ld_cat = 0;  // Falcon: ld_cat = qd + f, the [attention | mlp hidden] operand
   // decode activations [max_batch, *]
   bf16 *h = nullptr, *h2 = nullptr, *nrm = nullptr, *qkv = nullptr, *cat = nullptr, *mid = nullptr,
@@ -815,8 +821,37 @@ inline int cdiv(long long a, int b) { return static_cast<int>((a + b - 1) / b); 
 
 // one decode GEMM: out[n, N] = act(X W^T (+ bias) (+ C))
 void dgemm(Infer* m, cudaStream_t s, int n, const bf16* X, int ldx, size_t woff, int ldw, int N, int K,
-           GemmDecodeOut o) {
+           GemmDecodeOut o, const uint8_t* tiled = nullptr) {
+  o.w_tiled = m->use_tiled ? tiled : nullptr;
   gemm_decode_ex(X, ldx, m->w + woff, ldw, o, m->ws, m->counters, n, N, K, s);
+}
+
+// (re)builds the tile-major copies after the weights changed
+void ensure_tiled(Infer* m, cudaStream_t s) {
+  if (!m->use_tiled || m->tiled_valid) return;
+  const auto& a = m->a;
+  const int d = a.hidden_size, f = a.intermediate_size, V = a.vocab_size, qd = m->qd, qkvd = m->qkvd;
+  const bool falcon = a.family == B200W_FAMILY_FALCON, llama = a.family == B200W_FAMILY_LLAMA;
+  auto make = [&](uint8_t*& dst, size_t woff, int ldw, int N, int K) {
+    if (!dst) dst = m->alloc<uint8_t>(retiled_bytes(N, K));
+    retile_weights(m->w + woff, ldw, dst, N, K, s);
+  };
+  m->lt.resize(a.num_layers);
+  for (int l = 0; l < a.num_layers; ++l) {
+    const auto& p = m->lp[l];
+    auto& t = m->lt[l];
+    if (falcon) {
+      make(t.qkv, p.wqkv, d, qkvd + f, d);                 // [q k v | dense_h_to_4h]
+      make(t.o, p.wo, m->ld_cat, d, m->ld_cat);            // [dense | dense_4h_to_h]
+    } else {
+      make(t.qkv, p.wqkv, d, qkvd, d);
+      make(t.o, p.wo, qd, d, qd);
+      make(t.w1, p.w1, d, llama ? 2 * f : f, d);
+      make(t.w2, p.w2, f, d, f);
+    }
+  }
+  make(m->t_lm, m->p_lm, d, V, d);
+  m->tiled_valid = true;
 }
 
 // attention of the n new tokens over their cache slots -> out [n, ldo]
@@ -905,51 +940,51 @@ void enqueue_decode(Infer* m, cudaStream_t s, int n, int64_t& nl) {
       o1.out = m->qkv; o1.ldo = qkvd;
       o1.out2 = m->cat + qd; o1.ldo2 = m->ld_cat; o1.n_split = qkvd;
       o1.act = 1; o1.act_from = qkvd;   // exact GeLU on the MLP half only
-      dgemm(m, s, n, m->nrm, d, p.wqkv, d, qkvd + f, d, o1); ++nl;
+      dgemm(m, s, n, m->nrm, d, p.wqkv, d, qkvd + f, d, o1, m->lt[l].qkv); ++nl;
       launch_pdl(rope_append_kernel, dim3(cdiv(rp, 256)), dim3(256), 0, s, m->qkv, qkvd, m->inv_freq, m->pos, m->slot,
                  kc, vc, n, H, Hkv, dh, a.max_ctx, 1); ++nl;
       decode_attention(m, s, n, l, m->cat, m->ld_cat, nl);
       GemmDecodeOut o2;
       o2.out = h2; o2.ldo = d; o2.C = h; o2.ldc = d;
-      dgemm(m, s, n, m->cat, m->ld_cat, p.wo, m->ld_cat, d, m->ld_cat, o2); ++nl;
+      dgemm(m, s, n, m->cat, m->ld_cat, p.wo, m->ld_cat, d, m->ld_cat, o2, m->lt[l].o); ++nl;
       std::swap(h, h2);
     } else if (opt) {
       launch_ln(s, n, h, m->w + p.ln1_w, m->w + p.ln1_b, m->nrm, d, a.norm_eps); ++nl;
       GemmDecodeOut o1;
       o1.out = m->qkv; o1.ldo = qkvd; o1.bias = m->w + p.bqkv;
-      dgemm(m, s, n, m->nrm, d, p.wqkv, d, qkvd, d, o1); ++nl;
+      dgemm(m, s, n, m->nrm, d, p.wqkv, d, qkvd, d, o1, m->lt[l].qkv); ++nl;
       launch_pdl(rope_append_kernel, dim3(cdiv(rp, 256)), dim3(256), 0, s, m->qkv, qkvd, m->inv_freq, m->pos, m->slot,
                  kc, vc, n, H, Hkv, dh, a.max_ctx, 0); ++nl;
       decode_attention(m, s, n, l, m->cat, qd, nl);
       GemmDecodeOut o2;
       o2.out = h2; o2.ldo = d; o2.C = h; o2.ldc = d; o2.bias = m->w + p.bo;
-      dgemm(m, s, n, m->cat, qd, p.wo, qd, d, qd, o2); ++nl;
+      dgemm(m, s, n, m->cat, qd, p.wo, qd, d, qd, o2, m->lt[l].o); ++nl;
       launch_ln(s, n, h2, m->w + p.ln2_w, m->w + p.ln2_b, m->nrm, d, a.norm_eps); ++nl;
       GemmDecodeOut o3;
       o3.out = m->mid; o3.ldo = f; o3.bias = m->w + p.b1; o3.act = 2;
-      dgemm(m, s, n, m->nrm, d, p.w1, d, f, d, o3); ++nl;
+      dgemm(m, s, n, m->nrm, d, p.w1, d, f, d, o3, m->lt[l].w1); ++nl;
       GemmDecodeOut o4;
       o4.out = h; o4.ldo = d; o4.C = h2; o4.ldc = d; o4.bias = m->w + p.b2;
-      dgemm(m, s, n, m->mid, f, p.w2, f, d, f, o4); ++nl;
+      dgemm(m, s, n, m->mid, f, p.w2, f, d, f, o4, m->lt[l].w2); ++nl;
     } else {
       rmsnorm_fwd(h, m->w + p.ln1_w, m->nrm, nullptr, n, d, a.norm_eps, s); ++nl;
       GemmDecodeOut o1;
       o1.out = m->qkv; o1.ldo = qkvd;
-      dgemm(m, s, n, m->nrm, d, p.wqkv, d, qkvd, d, o1); ++nl;
+      dgemm(m, s, n, m->nrm, d, p.wqkv, d, qkvd, d, o1, m->lt[l].qkv); ++nl;
       launch_pdl(rope_append_kernel, dim3(cdiv(rp, 256)), dim3(256), 0, s, m->qkv, qkvd, m->inv_freq, m->pos, m->slot,
                  kc, vc, n, H, Hkv, dh, a.max_ctx, 1); ++nl;
       decode_attention(m, s, n, l, m->cat, qd, nl);
       GemmDecodeOut o2;
       o2.out = h2; o2.ldo = d; o2.C = h; o2.ldc = d;
-      dgemm(m, s, n, m->cat, qd, p.wo, qd, d, qd, o2); ++nl;
+      dgemm(m, s, n, m->cat, qd, p.wo, qd, d, qd, o2, m->lt[l].o); ++nl;
       rmsnorm_fwd(h2, m->w + p.ln2_w, m->nrm, nullptr, n, d, a.norm_eps, s); ++nl;
       GemmDecodeOut o3;
       o3.out = m->mid; o3.ldo = 2 * f;
-      dgemm(m, s, n, m->nrm, d, p.w1, d, 2 * f, d, o3); ++nl;
+      dgemm(m, s, n, m->nrm, d, p.w1, d, 2 * f, d, o3, m->lt[l].w1); ++nl;
       swiglu_fwd(m->mid, m->act, n, f, s); ++nl;
       GemmDecodeOut o4;
       o4.out = h; o4.ldo = d; o4.C = h2; o4.ldc = d;
-      dgemm(m, s, n, m->act, f, p.w2, f, d, f, o4); ++nl;
+      dgemm(m, s, n, m->act, f, p.w2, f, d, f, o4, m->lt[l].w2); ++nl;
     }
   }
   if (a.family == B200W_FAMILY_LLAMA) rmsnorm_fwd(h, m->w + m->p_lnf_w, m->nrm, nullptr, n, d, a.norm_eps, s);
@@ -957,7 +992,7 @@ void enqueue_decode(Infer* m, cudaStream_t s, int n, int64_t& nl) {
   ++nl;
   GemmDecodeOut ol;
   ol.out = m->logits; ol.ldo = V;
-  dgemm(m, s, n, m->nrm, d, m->p_lm, d, V, d, ol); ++nl;
+  dgemm(m, s, n, m->nrm, d, m->p_lm, d, V, d, ol, m->t_lm); ++nl;
   launch_pdl(argmax_kernel, dim3(n), dim3(1024), 0, s, m->logits, V, m->next); ++nl;
   B200W_CUDA(cudaGetLastError());
   B200W_CUDA(cudaMemcpyAsync(m->pin + 3 * B, m->next, n * 4, cudaMemcpyDeviceToHost, s));
@@ -1016,6 +1051,7 @@ int b200w_infer_init(b200w_ctx* ctx, const b200w_infer_arch* arch, int max_batch
     auto m = std::make_unique<Infer>();
     m->a = *arch;
     m->max_batch = max_batch;
+    if (const char* e = getenv("B200W_DECODE_TILED")) m->use_tiled = atoi(e) != 0;
     build(m.get());
     const auto& a = m->a;
     const size_t B = max_batch, d = a.hidden_size, f = a.intermediate_size;
@@ -1099,6 +1135,7 @@ int b200w_infer_load_tensor(b200w_ctx* ctx, const char* name, const void* host, 
     B200W_CHECK(dtype == B200W_BF16 || dtype == B200W_F32, "dtype must be bf16 or f32");
     cudaStream_t s = ctx_stream(ctx);
     const size_t n = static_cast<size_t>(n_elements);
+    m->tiled_valid = false;
     bf16* dst = m->w + p.off;
     void* tmp32 = nullptr;
     void* tmp16 = nullptr;
@@ -1127,6 +1164,7 @@ int b200w_infer_init_random(b200w_ctx* ctx, uint64_t seed, float std) {
   return iguard(ctx, [&] {
     Infer* m = model(ctx);
     // one device-side fill of the whole flat space (the fused matrices included), then the 1-D parameters
+    m->tiled_valid = false;
     ctx_fill_normal(ctx, m->w, m->n_elems, seed, std);
     for (const IParam& p : m->params)
       if (p.kind != 'm') ctx_fill_const(ctx, m->w + p.off, static_cast<size_t>(p.rows * p.cols), p.kind == 'n' ? 1.f : 0.f);
@@ -1151,6 +1189,7 @@ int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* posit
     memcpy(m->pin, tokens, n * 4);
     memcpy(m->pin + B, positions, n * 4);
     memcpy(m->pin + 2 * B, slots, n * 4);
+    ensure_tiled(m, s);   // no-op unless the weights changed since the last step
     int64_t step_launches = 0;
     // Run eagerly the first time a row count is seen (first-use attribute calls), captured into a
     // CUDA graph the second time, replayed from then on: ~200 launches (and their programmatic

@@ -35,7 +35,12 @@ struct GemmDecodeOut {
   const void* bias = nullptr;
   int act = 0;
   int act_from = 0;
+  const void* w_tiled = nullptr;  // retile_weights() image of W: streamed with 16 KB bulk copies instead of TMA boxes
 };
+// W [N, K] (row stride ldw) as consecutive 16 KB swizzled shared-memory images of its [128 x 64] tiles
+// (gemm.cu retile_weights_kernel); retiled_bytes = the size of that image.
+size_t retiled_bytes(int N, int K);
+void retile_weights(const void* W, int ldw, void* out, int N, int K, cudaStream_t s);
 void gemm_decode_ex(const void* X, int ldx, const void* W, int ldw, const GemmDecodeOut& o, float* ws,
                     unsigned* counters, int M, int N, int K, cudaStream_t s);
 

@@ -117,6 +117,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (contiguous `bytes`, multiple of 16, both 16-byte aligned), completes
+// `bytes` on `bar`. Used for weight tiles that are stored in HBM as the swizzled shared-memory image.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation
 // ------------------------------------------------------------------------------------------

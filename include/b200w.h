@@ -214,6 +214,10 @@ B200W_API int64_t b200w_infer_device_bytes(b200w_ctx* ctx);
  * out_f32: D and C are fp32. C may be NULL or alias D. block_n: 0 auto, 128, 256. */
 B200W_API int b200w_op_gemm(b200w_ctx* ctx, const void* A, int a_mn, int lda, const void* B, int b_mn, int ldb,
                   void* D, const void* C, int out_f32, int ldd, int M, int N, int K, int block_n);
+/* D[M,N] (bf16) = act(A[M,K] B[N,K]^T + bias[N] (+ C)): nn.Linear(bias=True) (+ residual) (+ ReLU when act = 1)
+ * in the GEMM epilogue, fp32 until the single rounding (OPT family). bias: DEVICE bf16, 16-byte aligned. */
+B200W_API int b200w_op_gemm_bias(b200w_ctx* ctx, const void* A, int lda, const void* B, int ldb, void* D,
+                       const void* C, int ldd, int M, int N, int K, const void* bias, int act, int block_n);
 /* out[M,N] = X[M,K] W[N,K]^T (+C), M <= 128: the decode-time projection (swap-AB, split-K). */
 B200W_API int b200w_op_gemm_decode(b200w_ctx* ctx, const void* X, const void* W, void* out, const void* C, int M,
                          int N, int K, int split_k);

@@ -516,7 +516,7 @@ void alloc_activations(b200w_ctx* c) {
 
 // GEMM launch with optional CUDA-event bracketing (bench.py's roofline leg)
 void egemm(b200w_ctx* c, const void* A, bool a_mn, int lda, const void* B, bool b_mn, int ldb, void* D,
-           const void* C, bool out_fp32, int ldd, int M, int N, int K) {
+           const void* C, bool out_fp32, int ldd, int M, int N, int K, const void* bias = nullptr, int act = 0) {
   cudaStream_t s = c->stream;
   if (c->prof_gemm) {
     if (c->prof_used + 2 > c->prof_events.size()) {
@@ -528,7 +528,7 @@ void egemm(b200w_ctx* c, const void* A, bool a_mn, int lda, const void* B, bool 
     }
     B200W_CUDA(cudaEventRecord(c->prof_events[c->prof_used], s));
   }
-  gemm_bf16(A, a_mn, lda, B, b_mn, ldb, D, C, out_fp32, ldd, M, N, K, 0, s);
+  gemm_bf16_ex(A, a_mn, lda, B, b_mn, ldb, D, C, out_fp32, ldd, M, N, K, 0, bias, act, s);
   ++c->launches;
   if (c->prof_gemm) {
     B200W_CUDA(cudaEventRecord(c->prof_events[c->prof_used + 1], s));
@@ -597,16 +597,14 @@ void forward_micro_opt(b200w_ctx* c, const int32_t* ids, int nseq) {
     bf16* h_next = c->training ? (l + 1 < L ? c->la[l + 1].h_in : c->h_final)
                                : (h == c->la[0].h_in ? c->h_final : c->la[0].h_in);
     layernorm_fwd(h_in, c->w + p.ln1, c->w + p.ln1b, x.n1, x.mean1, x.rstd1, T, d, eps, s); ++n;
-    egemm(c, x.n1, false, d, c->w + p.wqkv, false, d, x.qkv, nullptr, false, qkvd, T, qkvd, d);
-    bias_act(x.qkv, c->w + p.bqkv, T, qkvd, qkvd, 0, s); ++n;
+    // nn.Linear(bias=True): the bias (and fc1's ReLU) ride in the GEMM epilogue, added in fp32 before the one
+    // rounding to bf16
+    egemm(c, x.n1, false, d, c->w + p.wqkv, false, d, x.qkv, nullptr, false, qkvd, T, qkvd, d, c->w + p.bqkv, 0);
     attention_fwd(x.qkv, qkvd, qd, qd + kd, x.attn, qd, x.lse, nseq, S, H, Hkv, scale, s); ++n;
-    egemm(c, x.attn, false, qd, c->w + p.wo, false, qd, x.h_mid, h_in, false, d, T, d, qd);
-    bias_act(x.h_mid, c->w + p.bo, T, d, d, 0, s); ++n;
+    egemm(c, x.attn, false, qd, c->w + p.wo, false, qd, x.h_mid, h_in, false, d, T, d, qd, c->w + p.bo, 0);
     layernorm_fwd(x.h_mid, c->w + p.ln2, c->w + p.ln2b, x.n2, x.mean2, x.rstd2, T, d, eps, s); ++n;
-    egemm(c, x.n2, false, d, c->w + p.wgu, false, d, x.act, nullptr, false, f, T, f, d);
-    bias_act(x.act, c->w + p.b1, T, f, f, 1, s); ++n;  // ReLU; the backward masks on act > 0
-    egemm(c, x.act, false, f, c->w + p.wd, false, f, h_next, x.h_mid, false, d, T, d, f);
-    bias_act(h_next, c->w + p.b2, T, d, d, 0, s); ++n;
+    egemm(c, x.n2, false, d, c->w + p.wgu, false, d, x.act, nullptr, false, f, T, f, d, c->w + p.b1, 1);  // ReLU
+    egemm(c, x.act, false, f, c->w + p.wd, false, f, h_next, x.h_mid, false, d, T, d, f, c->w + p.b2, 0);
     h = h_next;
   }
   layernorm_fwd(h, c->w + c->p_norm, c->w + c->p_normb, c->nf, c->meanf, c->rstdf, T, d, eps, s); ++n;
@@ -1611,6 +1609,10 @@ int b200w_op_gemm(b200w_ctx* ctx, const void* A, int a_mn, int lda, const void* 
                   void* D, const void* C, int out_f32, int ldd, int M, int N, int K, int block_n) {
   HOOK(gemm_bf16(A, a_mn != 0, lda, B, b_mn != 0, ldb, D, C, out_f32 != 0, ldd, M, N, K, block_n,
                  ctx->stream));
+}
+int b200w_op_gemm_bias(b200w_ctx* ctx, const void* A, int lda, const void* B, int ldb, void* D, const void* C, int ldd,
+                       int M, int N, int K, const void* bias, int act, int block_n) {
+  HOOK(gemm_bf16_ex(A, false, lda, B, false, ldb, D, C, false, ldd, M, N, K, block_n, bias, act, ctx->stream));
 }
 int b200w_op_gemm_decode(b200w_ctx* ctx, const void* X, const void* W, void* out, const void* C, int M,
                          int N, int K, int split_k) {

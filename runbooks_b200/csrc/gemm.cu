@@ -60,9 +60,36 @@ __device__ __forceinline__ void load_c_chunk(CChunk<OutT>& c, const OutT* crow, 
   }
 }
 
+// Epilogue extras of the bf16-output GEMM (nn.Linear(bias=True) + activation of the OPT family): v + bias[col]
+// (+ C) -> act. bias points at this chunk's 32 columns (16-byte aligned); act: 0 none, 1 ReLU.
+struct EpiExtra {
+  const __nv_bfloat16* bias;
+  int act;
+};
+__device__ __forceinline__ void apply_bias(float (&v)[32], const __nv_bfloat16* bias, int ncols_valid) {
+  if (ncols_valid >= 32) {
+    const uint4* bp = reinterpret_cast<const uint4*>(bias);   // same address in every thread: one broadcast load each
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = bp[i];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        v[i * 8 + j * 2] += f.x;
+        v[i * 8 + j * 2 + 1] += f.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < ncols_valid) v[i] += __bfloat162float(bias[i]);
+  }
+}
+
 __device__ __forceinline__ void store_chunk32(__nv_bfloat16* drow, const __nv_bfloat16* crow,
                                               const CChunk<__nv_bfloat16>& cc, const float (&v)[32],
-                                              int ncols_valid, bool has_c) {
+                                              int ncols_valid, bool has_c, int act = 0) {
   if (ncols_valid >= 32) {
     uint4 out[4];
     uint32_t* o = reinterpret_cast<uint32_t*>(out);
@@ -73,12 +100,18 @@ __device__ __forceinline__ void store_chunk32(__nv_bfloat16* drow, const __nv_bf
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float2 f = unpack_bf16x2(cw[j]);
-          o[i * 4 + j] = pack_bf16x2(v[i * 8 + j * 2] + f.x, v[i * 8 + j * 2 + 1] + f.y);
+          float a0 = v[i * 8 + j * 2] + f.x, a1 = v[i * 8 + j * 2 + 1] + f.y;
+          if (act == 1) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+          o[i * 4 + j] = pack_bf16x2(a0, a1);
         }
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+      for (int i = 0; i < 16; ++i) {
+        float a0 = v[2 * i], a1 = v[2 * i + 1];
+        if (act == 1) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+        o[i] = pack_bf16x2(a0, a1);
+      }
     }
     uint4* d4 = reinterpret_cast<uint4*>(drow);
 #pragma unroll
@@ -89,6 +122,7 @@ __device__ __forceinline__ void store_chunk32(__nv_bfloat16* drow, const __nv_bf
       if (i < ncols_valid) {
         float x = v[i];
         if (has_c) x += __bfloat162float(crow[i]);
+        if (act == 1) x = fmaxf(x, 0.f);
         drow[i] = __float2bfloat16_rn(x);
       }
     }
@@ -96,7 +130,7 @@ __device__ __forceinline__ void store_chunk32(__nv_bfloat16* drow, const __nv_bf
 }
 
 __device__ __forceinline__ void store_chunk32(float* drow, const float* crow, const CChunk<float>& cc,
-                                              const float (&v)[32], int ncols_valid, bool has_c) {
+                                              const float (&v)[32], int ncols_valid, bool has_c, int /*act*/ = 0) {
   if (ncols_valid >= 32) {
     float4* d4 = reinterpret_cast<float4*>(drow);
 #pragma unroll
@@ -118,7 +152,7 @@ __device__ __forceinline__ void store_chunk32(float* drow, const float* crow, co
 // TMEM accumulator rows -> global for one 128 x NCOLS tile half owned by this warp's lane quarter.
 template <int NCOLS, typename OutT>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_row_addr, OutT* drow, const OutT* crow,
-                                              bool row_ok, int ncols_total) {
+                                              bool row_ok, int ncols_total, EpiExtra ex = EpiExtra{nullptr, 0}) {
   const bool has_c = crow != nullptr;
   CChunk<OutT> cc_next;
   if (has_c && row_ok) load_c_chunk<OutT>(cc_next, crow, ncols_total);
@@ -134,7 +168,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_row_addr, OutT* drow
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-      store_chunk32(drow + c * 32, has_c ? crow + c * 32 : nullptr, cc, v, ncols, has_c);
+      if (ex.bias) apply_bias(v, ex.bias + c * 32, ncols);
+      store_chunk32(drow + c * 32, has_c ? crow + c * 32 : nullptr, cc, v, ncols, has_c, ex.act);
     }
   }
 }
@@ -142,7 +177,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_row_addr, OutT* drow
 template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 OutT* D, const OutT* C, int M, int N, int K, int ldd, int n_fast) {
+                 OutT* D, const OutT* C, int M, int N, int K, int ldd, int n_fast, EpiExtra ex) {
   using cfg = Cfg<BLOCK_N>;
   constexpr int STAGES = cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -262,7 +297,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = row < M;
       OutT* drow = D + static_cast<size_t>(row) * ldd + n0;
       const OutT* crow = C ? C + static_cast<size_t>(row) * ldd + n0 : nullptr;
-      epilogue_tile<BLOCK_N, OutT>(tmem_addr(tmem_base, q * 32, acc * BLOCK_N), drow, crow, row_ok, N - n0);
+      epilogue_tile<BLOCK_N, OutT>(tmem_addr(tmem_base, q * 32, acc * BLOCK_N), drow, crow, row_ok, N - n0,
+                                   EpiExtra{ex.bias ? ex.bias + n0 : nullptr, ex.act});
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -293,7 +329,7 @@ constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256;
 template <bool A_MN, bool B_MN, typename OutT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      OutT* D, const OutT* C, int M, int N, int K, int ldd, int n_fast) {
+                      OutT* D, const OutT* C, int M, int N, int K, int ldd, int n_fast, EpiExtra ex) {
   constexpr int STAGES = PAIR_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -413,7 +449,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const bool row_ok = row < M;
       OutT* drow = D + static_cast<size_t>(row) * ldd + n0;
       const OutT* crow = C ? C + static_cast<size_t>(row) * ldd + n0 : nullptr;
-      epilogue_tile<PAIR_N, OutT>(tmem_addr(tmem_base, q * 32, acc * PAIR_N), drow, crow, row_ok, N - n0);
+      epilogue_tile<PAIR_N, OutT>(tmem_addr(tmem_base, q * 32, acc * PAIR_N), drow, crow, row_ok, N - n0,
+                                  EpiExtra{ex.bias ? ex.bias + n0 : nullptr, ex.act});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA thread waits on it
@@ -432,7 +469,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
 template <bool A_MN, bool B_MN, typename OutT>
 void launch_pair(const void* A, const void* B, OutT* D, const OutT* C, int M, int N, int K, int lda,
-                 int ldb, int ldd, cudaStream_t stream) {
+                 int ldb, int ldd, EpiExtra ex, cudaStream_t stream) {
   CUtensorMap tmA = A_MN ? make_tmap_bf16_2d(A, K, M, lda, BLOCK_K, 64)
                          : make_tmap_bf16_2d(A, M, K, lda, BLOCK_M, BLOCK_K);
   CUtensorMap tmB = B_MN ? make_tmap_bf16_2d(B, K, N, ldb, BLOCK_K, 64)
@@ -446,22 +483,22 @@ void launch_pair(const void* A, const void* B, OutT* D, const OutT* C, int M, in
   const int max_clusters = (sm_count() - gemm_sm_reserve()) / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
   kern<<<clusters * 2, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(tmA, tmB, D, C, M, N, K, ldd,
-                                                                pick_n_fast(M, N, K));
+                                                                pick_n_fast(M, N, K), ex);
   B200W_CUDA(cudaGetLastError());
 }
 
 template <typename OutT>
 void dispatch_pair(bool a_mn, bool b_mn, const void* A, const void* B, OutT* D, const OutT* C, int M,
-                   int N, int K, int lda, int ldb, int ldd, cudaStream_t s) {
-  if (!a_mn && !b_mn) launch_pair<false, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
-  else if (!a_mn && b_mn) launch_pair<false, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
-  else if (a_mn && b_mn) launch_pair<true, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
-  else launch_pair<true, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
+                   int N, int K, int lda, int ldb, int ldd, EpiExtra ex, cudaStream_t s) {
+  if (!a_mn && !b_mn) launch_pair<false, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, ex, s);
+  else if (!a_mn && b_mn) launch_pair<false, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, ex, s);
+  else if (a_mn && b_mn) launch_pair<true, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, ex, s);
+  else launch_pair<true, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, ex, s);
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, typename OutT>
 void launch(const void* A, const void* B, OutT* D, const OutT* C, int M, int N, int K, int lda,
-            int ldb, int ldd, cudaStream_t stream) {
+            int ldb, int ldd, EpiExtra ex, cudaStream_t stream) {
   using cfg = Cfg<BLOCK_N>;
   // A: K-major => global [M rows, K cols]; MN-major => global [K rows, M cols]
   CUtensorMap tmA = A_MN ? make_tmap_bf16_2d(A, K, M, lda, BLOCK_K, 64)
@@ -478,22 +515,22 @@ void launch(const void* A, const void* B, OutT* D, const OutT* C, int M, int N, 
   const int sms = sm_count() - gemm_sm_reserve();
   const int grid = num_tiles < sms ? num_tiles : sms;
   kern<<<grid, GEMM_THREADS, cfg::SMEM_BYTES, stream>>>(tmA, tmB, D, C, M, N, K, ldd,
-                                                        pick_n_fast(M, N, K));
+                                                        pick_n_fast(M, N, K), ex);
   B200W_CUDA(cudaGetLastError());
 }
 
 template <int BLOCK_N, typename OutT>
 void dispatch_major(bool a_mn, bool b_mn, const void* A, const void* B, OutT* D, const OutT* C,
-                    int M, int N, int K, int lda, int ldb, int ldd, cudaStream_t s) {
+                    int M, int N, int K, int lda, int ldb, int ldd, EpiExtra ex, cudaStream_t s) {
   if constexpr (BLOCK_N < 128) {  // decode tiles: weights are always K-major there
     B200W_CHECK(!a_mn && !b_mn, "narrow tiles support K-major operands only");
-    launch<BLOCK_N, false, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
+    launch<BLOCK_N, false, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, ex, s);
     return;
   }
-  if (!a_mn && !b_mn) launch<BLOCK_N, false, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
-  else if (!a_mn && b_mn) launch<BLOCK_N, false, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
-  else if (a_mn && b_mn) launch<BLOCK_N, true, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
-  else launch<BLOCK_N, true, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, s);
+  if (!a_mn && !b_mn) launch<BLOCK_N, false, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, ex, s);
+  else if (!a_mn && b_mn) launch<BLOCK_N, false, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, ex, s);
+  else if (a_mn && b_mn) launch<BLOCK_N, true, true, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, ex, s);
+  else launch<BLOCK_N, true, false, OutT>(A, B, D, C, M, N, K, lda, ldb, ldd, ex, s);
 }
 
 }  // namespace
@@ -815,6 +852,16 @@ void gemm_decode(const void* X, const void* W, void* out, const void* C, float* 
 void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int ldb, void* D,
                const void* C, bool out_fp32, int ldd, int M, int N, int K, int block_n,
                cudaStream_t stream) {
+  gemm_bf16_ex(A, a_mn, lda, B, b_mn, ldb, D, C, out_fp32, ldd, M, N, K, block_n, nullptr, 0, stream);
+}
+// + bias [N] (bf16, 16-byte aligned) added to every row and act (0 none, 1 ReLU) after bias and C:
+// nn.Linear(bias=True) (+ residual) (+ ReLU) in the epilogue. bf16 output only.
+void gemm_bf16_ex(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int ldb, void* D,
+                  const void* C, bool out_fp32, int ldd, int M, int N, int K, int block_n, const void* bias,
+                  int act, cudaStream_t stream) {
+  B200W_CHECK(!(out_fp32 && (bias || act)), "bias / activation epilogue is built for bf16 outputs");
+  B200W_CHECK((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "bias must be 16-byte aligned");
+  const EpiExtra ex{static_cast<const __nv_bfloat16*>(bias), act};
   B200W_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
   B200W_CHECK(lda % 8 == 0 && ldb % 8 == 0, "TMA needs 16-byte aligned row strides");
   B200W_CHECK(ldd % (out_fp32 ? 4 : 8) == 0, "output rows must be 16-byte aligned");
@@ -840,10 +887,10 @@ void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int 
   if (block_n == 512) {  // CTA-pair kernel: 256 x 256 tiles on tcgen05.mma.cta_group::2
     if (out_fp32)
       dispatch_pair<float>(a_mn, b_mn, A, B, static_cast<float*>(D), static_cast<const float*>(C), M, N,
-                           K, lda, ldb, ldd, stream);
+                           K, lda, ldb, ldd, ex, stream);
     else
       dispatch_pair<__nv_bfloat16>(a_mn, b_mn, A, B, static_cast<__nv_bfloat16*>(D),
-                                   static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb, ldd, stream);
+                                   static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb, ldd, ex, stream);
     return;
   }
   B200W_CHECK(block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256,
@@ -852,28 +899,28 @@ void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int 
     B200W_CHECK(!out_fp32, "narrow tiles write bf16");
     if (block_n == 64)
       dispatch_major<64, __nv_bfloat16>(a_mn, b_mn, A, B, static_cast<__nv_bfloat16*>(D),
-                                        static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb, ldd, stream);
+                                        static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb, ldd, ex, stream);
     else
       dispatch_major<32, __nv_bfloat16>(a_mn, b_mn, A, B, static_cast<__nv_bfloat16*>(D),
-                                        static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb, ldd, stream);
+                                        static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb, ldd, ex, stream);
     return;
   }
   if (out_fp32) {
     if (block_n == 256)
       dispatch_major<256, float>(a_mn, b_mn, A, B, static_cast<float*>(D),
-                                 static_cast<const float*>(C), M, N, K, lda, ldb, ldd, stream);
+                                 static_cast<const float*>(C), M, N, K, lda, ldb, ldd, ex, stream);
     else
       dispatch_major<128, float>(a_mn, b_mn, A, B, static_cast<float*>(D),
-                                 static_cast<const float*>(C), M, N, K, lda, ldb, ldd, stream);
+                                 static_cast<const float*>(C), M, N, K, lda, ldb, ldd, ex, stream);
   } else {
     if (block_n == 256)
       dispatch_major<256, __nv_bfloat16>(a_mn, b_mn, A, B, static_cast<__nv_bfloat16*>(D),
                                          static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb,
-                                         ldd, stream);
+                                         ldd, ex, stream);
     else
       dispatch_major<128, __nv_bfloat16>(a_mn, b_mn, A, B, static_cast<__nv_bfloat16*>(D),
                                          static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb,
-                                         ldd, stream);
+                                         ldd, ex, stream);
   }
 }
 

@@ -578,14 +578,32 @@ __global__ void decode_attn_merge_kernel(const float* __restrict__ part_o, const
   if (h >= H) return;
   const int ns = (pos[r] + TC_KB) / TC_KB;  // ceil((pos + 1) / 128)
   const size_t base = (static_cast<size_t>(r) * H + h) * nsplit;
-  float M = -INFINITY;
-  for (int s2 = 0; s2 < ns; ++s2) M = fmaxf(M, part_ml[base + s2].x);
-  float num = 0.f, den = 0.f;
-  for (int s2 = 0; s2 < ns; ++s2) {
-    const float2 ml = part_ml[base + s2];
-    const float wgt = ex2f(ml.x - M);
-    num += wgt * part_o[(base + s2) * DH + d];
-    den += wgt * ml.y;
+  // one pass, four blocks at a time with every load issued before the first use: the loop is a chain of
+  // L2 round trips otherwise (6.3 us per launch in profiles/r02_decode_launches_v1.txt for ~100 KB of data).
+  // Online form: the running maximum M rescales the sums accumulated so far.
+  float M = -INFINITY, num = 0.f, den = 0.f;
+  for (int s0 = 0; s0 < ns; s0 += 4) {
+    float2 ml[4];
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool ok = s0 + j < ns;
+      ml[j] = ok ? part_ml[base + s0 + j] : make_float2(-INFINITY, 0.f);
+      o[j] = ok ? part_o[(base + s0 + j) * DH + d] : 0.f;
+    }
+    float Mn = M;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Mn = fmaxf(Mn, ml[j].x);
+    const float resc = ex2f(M - Mn);   // 0 on the first chunk (M = -inf), block 0 always exists so Mn is finite
+    num *= resc;
+    den *= resc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float wgt = ex2f(ml[j].x - Mn);   // 2^(-inf) = 0 for the padding entries
+      num += wgt * o[j];
+      den += wgt * ml[j].y;
+    }
+    M = Mn;
   }
   out[static_cast<size_t>(r) * ldo + h * DH + d] = __float2bfloat16_rn(num / den);
 }
@@ -599,9 +617,17 @@ __global__ void argmax_kernel(const bf16* __restrict__ logits, int V, int32_t* _
   const bf16* row = logits + static_cast<size_t>(blockIdx.x) * V;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    const float v = __bfloat162float(row[i]);
-    if (v > best) { best = v; bi = i; }
+  // 8 logits per 16-byte load (V % 8 == 0 is checked at init); within a thread the indices only grow, so `>`
+  // keeps the first maximum, and the cross-thread reduction below breaks ties towards the smaller index
+  for (int i = threadIdx.x * 8; i < V; i += blockDim.x * 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      if (f.x > best) { best = f.x; bi = i + 2 * j; }
+      if (f.y > best) { best = f.y; bi = i + 2 * j + 1; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -1052,6 +1078,7 @@ int b200w_infer_init(b200w_ctx* ctx, const b200w_infer_arch* arch, int max_batch
     m->a = *arch;
     m->max_batch = max_batch;
     if (const char* e = getenv("B200W_DECODE_TILED")) m->use_tiled = atoi(e) != 0;
+    m->lt.resize(arch->num_layers);   // all-null when the tiled copies are disabled
     build(m.get());
     const auto& a = m->a;
     const size_t B = max_batch, d = a.hidden_size, f = a.intermediate_size;
@@ -1287,8 +1314,9 @@ int b200w_infer_prefill(b200w_ctx* ctx, const int32_t* tokens, const int32_t* le
     const float scale = 1.f / sqrtf(static_cast<float>(dh));
     const size_t layer_cache = static_cast<size_t>(B) * a.max_ctx * m->kd;
     const int Ti = static_cast<int>(T);
-    auto G = [&](const void* A, int lda, size_t woff, int ldw, void* D, const void* C, int ldd, int N, int K) {
-      gemm_bf16(A, false, lda, m->w + woff, false, ldw, D, C, false, ldd, Ti, N, K, 0, s); ++nl;
+    auto G = [&](const void* A, int lda, size_t woff, int ldw, void* D, const void* C, int ldd, int N, int K,
+                 const void* bias = nullptr, int act = 0) {
+      gemm_bf16_ex(A, false, lda, m->w + woff, false, ldw, D, C, false, ldd, Ti, N, K, 0, bias, act, s); ++nl;
     };
     bf16* h = m->pf_h;
     bf16* h2 = m->pf_h2;
@@ -1300,8 +1328,7 @@ int b200w_infer_prefill(b200w_ctx* ctx, const int32_t* tokens, const int32_t* le
       if (a.family == B200W_FAMILY_LLAMA) rmsnorm_fwd(h, m->w + p.ln1_w, m->pf_nrm, nullptr, Ti, d, a.norm_eps, s);
       else layernorm_kernel<<<Ti, 256, 0, s>>>(h, m->w + p.ln1_w, m->w + p.ln1_b, m->pf_nrm, d, a.norm_eps);
       ++nl;
-      G(m->pf_nrm, d, p.wqkv, d, m->pf_qkv, nullptr, qkvd, qkvd, d);
-      if (opt) { bias_act(m->pf_qkv, m->w + p.bqkv, Ti, qkvd, qkvd, 0, s); ++nl; }
+      G(m->pf_nrm, d, p.wqkv, d, m->pf_qkv, nullptr, qkvd, qkvd, d, opt ? m->w + p.bqkv : nullptr, 0);
       if (falcon) {  // the MLP half of the parallel block reads the same LayerNorm output
         G(m->pf_nrm, d, p.w1, d, m->pf_cat + qd, nullptr, ldc, f, d);
         const long long ge = static_cast<long long>(Ti) * (f / 8);
@@ -1325,13 +1352,10 @@ int b200w_infer_prefill(b200w_ctx* ctx, const int32_t* tokens, const int32_t* le
         G(m->pf_cat, ldc, p.wo, ldc, h2, h, d, d, ldc);   // h' = h + [attn | gelu(h_to_4h)] [dense | 4h_to_h]^T
         std::swap(h, h2);
       } else if (opt) {
-        G(m->pf_cat, qd, p.wo, qd, h2, h, d, d, qd);
-        bias_act(h2, m->w + p.bo, Ti, d, d, 0, s); ++nl;
+        G(m->pf_cat, qd, p.wo, qd, h2, h, d, d, qd, m->w + p.bo, 0);
         layernorm_kernel<<<Ti, 256, 0, s>>>(h2, m->w + p.ln2_w, m->w + p.ln2_b, m->pf_nrm, d, a.norm_eps); ++nl;
-        G(m->pf_nrm, d, p.w1, d, m->pf_mid, nullptr, f, f, d);
-        bias_act(m->pf_mid, m->w + p.b1, Ti, f, f, 1, s); ++nl;
-        G(m->pf_mid, f, p.w2, f, h, h2, d, d, f);
-        bias_act(h, m->w + p.b2, Ti, d, d, 0, s); ++nl;
+        G(m->pf_nrm, d, p.w1, d, m->pf_mid, nullptr, f, f, d, m->w + p.b1, 1);   // bias + ReLU in the epilogue
+        G(m->pf_mid, f, p.w2, f, h, h2, d, d, f, m->w + p.b2, 0);
       } else {
         G(m->pf_cat, qd, p.wo, qd, h2, h, d, d, qd);
         rmsnorm_fwd(h2, m->w + p.ln2_w, m->pf_nrm, nullptr, Ti, d, a.norm_eps, s); ++nl;

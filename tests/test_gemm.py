@@ -140,3 +140,28 @@ def test_gemm_is_race_free(engine, M, N, K, a_mn, b_mn, acc):
     bad = sum(not torch.equal(run(), ref) for _ in range(200))
     print(f"gemm race check M{M} N{N} K{K} a_mn{a_mn} b_mn{b_mn} acc{acc}: mismatching launches {bad}/200")
     assert bad == 0
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(256, 384, 128, 0), (8192, 768, 768, 0), (4096, 3072, 768, 512), (200, 136, 72, 128)])
+@pytest.mark.parametrize("act,resid", [(0, False), (1, False), (0, True)])
+def test_gemm_bias_relu_epilogue(engine, M, N, K, bn, act, resid):
+    """nn.Linear(bias=True) (+ residual) (+ ReLU) in the epilogue -- the OPT family's projections. Reference:
+    fp32 torch on the same bf16-representable operands; the kernel adds bias and residual in fp32 and rounds
+    once, so the bar is one bf16 rounding (3e-3 relative Frobenius)."""
+    g = torch.Generator().manual_seed(M + N + K + act)
+    A = torch.randn(M, K, generator=g).bfloat16()
+    B = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, generator=g).bfloat16()
+    C = torch.randn(M, N, generator=g).bfloat16() if resid else None
+    D = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    call(engine, "b200w_op_gemm_bias", dev(A), K, dev(B), K, D, dev(C) if resid else None, N, M, N, K, dev(bias), act, bn)
+    ref = A.float() @ B.float().T + bias.float()
+    if resid:
+        ref = ref + C.float()
+    if act:
+        ref = ref.relu()
+    err = rel_err(D.float(), ref)
+    print(f"gemm bias/act M{M} N{N} K{K} bn{bn} act{act} resid{resid}: rel_err {err:.3e}")
+    assert err < 3e-3
+    if act:
+        assert float(D.float().min()) >= 0.0

@@ -228,6 +228,8 @@ class Generator:
         need_logits = any(not r.greedy for r in self.active)
         nxt, lg = self.e.step(toks, [r.fed for r in self.active], [r.slot for r in self.active],
                               want_logits=need_logits)
+        if need_logits and lg is None:
+            raise ValueError("sampling (temperature > 0) needs an engine that returns logits")
         for i, (r, t) in enumerate(zip(self.active, nxt)):
             r.fed += 1
             if r.fed >= len(r.prompt):        # the token just fed was the last known one

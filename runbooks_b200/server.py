@@ -120,13 +120,14 @@ class Scheduler(threading.Thread):
                         item["events"].put(("error", str(e)))
                 try:
                     self.gen.step()
-                except B200WError as e:
-                    if e.status in FATAL_STATUSES:
-                        raise
-                    # a rejected batch (bad argument): fail the requests that were in it, keep serving
+                except Exception as e:  # noqa: BLE001
+                    if isinstance(e, B200WError) and e.status in FATAL_STATUSES:
+                        raise           # CUDA / NCCL: the context is dead, the Pod must restart
+                    # a rejected batch (bad argument, an engine without logits asked to sample): fail the
+                    # requests that were in it, keep serving
                     for req, item, _, _ in pending.values():
                         self.gen.cancel(req)
-                        item["events"].put(("error", str(e)))
+                        item["events"].put(("error", f"{type(e).__name__}: {e}"))
                     pending.clear()
                     continue
                 for key in list(pending):
@@ -155,11 +156,14 @@ def parse_completion_request(req: dict) -> dict:
     max_tokens = int(req.get("max_tokens", 16))
     if max_tokens < 1:
         raise ValueError("max_tokens must be >= 1")
-    temperature = float(req.get("temperature", 0.0) or 0.0)   # this server's default is greedy
-    top_p = float(req.get("top_p", 1.0) or 1.0)
+    def num(key, default):            # JSON null means "default"; 0 is a value
+        v = req.get(key)
+        return default if v is None else float(v)
+    temperature = num("temperature", 0.0)   # this server's default is greedy
+    top_p = num("top_p", 1.0)
     if temperature < 0 or not 0 < top_p <= 1:
         raise ValueError("temperature must be >= 0 and top_p in (0, 1]")
-    n = int(req.get("n", 1) or 1)
+    n = int(num("n", 1))
     if n < 1 or n > 8:
         raise ValueError("n must be in 1..8")
     stop = req.get("stop") or []

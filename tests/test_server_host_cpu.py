@@ -185,3 +185,126 @@ def test_bad_requests_do_not_kill_the_server(http_server):
     code, body = _post(base + "/v1/completions", {"prompt": ["list form"], "max_tokens": 2})
     assert code == 200 and body["usage"]["completion_tokens"] == 2
     assert _get(base + "/")[0] == 200
+
+
+# ---- round 2: streaming, parameters, back-pressure, prefill admission -- all on the stub engine ----
+def _sse(url, obj):
+    req = urllib.request.Request(url, data=json.dumps(obj).encode(), headers={"Content-Type": "application/json"})
+    with urllib.request.urlopen(req, timeout=30) as r:
+        assert r.headers["Content-Type"].startswith("text/event-stream")
+        return [l[6:] for l in r.read().decode().split("\n") if l.startswith("data: ")]
+
+
+def test_streaming_chunks_concatenate_to_the_plain_completion(http_server):
+    """`"stream": true` answers with server-sent events (the shape basaran / the OpenAI API speak): one JSON
+    chunk per text delta, a final chunk with finish_reason, then [DONE]."""
+    sched, _, base = http_server
+    sched.start()
+    code, plain = _post(base + "/v1/completions", {"prompt": "stream me", "max_tokens": 9})
+    assert code == 200
+    ev = _sse(base + "/v1/completions", {"prompt": "stream me", "max_tokens": 9, "stream": True})
+    assert ev[-1] == "[DONE]"
+    chunks = [json.loads(e) for e in ev[:-1]]
+    assert all(c["object"] == "text_completion" for c in chunks)
+    assert "".join(c["choices"][0]["text"] for c in chunks) == plain["choices"][0]["text"]
+    assert chunks[-1]["choices"][0]["finish_reason"] == "length" and len(chunks) >= 9
+    # echo: the prompt is the first chunk
+    ev = _sse(base + "/v1/completions", {"prompt": "stream me", "max_tokens": 2, "stream": True, "echo": True})
+    assert json.loads(ev[0])["choices"][0]["text"] == "stream me"
+
+
+def test_stop_n_echo_and_sampling_parameters(http_server):
+    sched, _, base = http_server
+    sched.start()
+    code, plain = _post(base + "/v1/completions", {"prompt": "abc", "max_tokens": 12})
+    text = plain["choices"][0]["text"]
+    cut = text[5:7]
+    code, st = _post(base + "/v1/completions", {"prompt": "abc", "max_tokens": 12, "stop": cut})
+    k = text.find(cut)
+    assert code == 200 and st["choices"][0]["text"] == text[:k] and st["choices"][0]["finish_reason"] == "stop"
+    code, two = _post(base + "/v1/completions", {"prompt": "abc", "max_tokens": 4, "n": 2, "echo": True})
+    assert code == 200 and [c["index"] for c in two["choices"]] == [0, 1]
+    assert two["choices"][0]["text"] == two["choices"][1]["text"] == "abc" + text[:4]       # greedy: identical
+    assert two["usage"]["completion_tokens"] == 8
+    # what is not implemented is a 400, never silently ignored
+    for bad in ({"logprobs": 2}, {"best_of": 3}, {"presence_penalty": 1.0}, {"frequency_penalty": 0.5},
+                {"temperature": -0.1}, {"top_p": 0}, {"n": 0}, {"n": 2, "stream": True}, {"stop": ["a"] * 5}):
+        assert _post(base + "/v1/completions", dict({"prompt": "abc", "max_tokens": 2}, **bad))[0] == 400, bad
+    # temperature > 0 needs the engine's logits: the stub has none, so the request fails alone (500-class as 400)
+    code, body = _post(base + "/v1/completions", {"prompt": "abc", "max_tokens": 2, "temperature": 0.7})
+    assert code == 400
+    assert _post(base + "/v1/completions", {"prompt": "abc", "max_tokens": 2})[0] == 200     # the server lives on
+
+
+def test_sample_token_is_nucleus_sampling():
+    from runbooks_b200.infer import sample_token
+    rng = np.random.default_rng(0)
+    logits = np.array([5.0, 4.0, 0.0, -3.0, -9.0], dtype=np.float32)
+    draws = [sample_token(logits, 1.0, 1.0, rng) for _ in range(4000)]
+    p = np.exp(logits - logits.max()); p /= p.sum()
+    freq = np.bincount(draws, minlength=5) / len(draws)
+    assert np.abs(freq - p).max() < 0.03
+    assert set(sample_token(logits, 1.0, 0.5, rng) for _ in range(200)) == {0}          # top_p 0.5: only the head
+    assert set(sample_token(logits, 1.0, 0.9, rng) for _ in range(500)) == {0, 1}
+    assert all(sample_token(logits, 1e-4, 1.0, rng) == 0 for _ in range(50))             # T -> 0: argmax
+
+
+def test_backpressure_answers_503_when_slots_and_queue_are_full():
+    eng = StubEngine(max_batch=1, max_ctx=64)
+    sched = server.Scheduler(eng, CharTok(), max_queue=2)        # not started: nothing is admitted
+    httpd = ThreadingHTTPServer(("127.0.0.1", 0), server.make_handler(sched, "stub", request_timeout_s=0.5))
+    threading.Thread(target=httpd.serve_forever, daemon=True).start()
+    base = f"http://127.0.0.1:{httpd.server_address[1]}"
+    try:
+        results = []
+        ts = [threading.Thread(target=lambda: results.append(_post(base + "/v1/completions", {"prompt": "q", "max_tokens": 2})))
+              for _ in range(2)]
+        for t in ts:
+            t.start()
+        import time
+        deadline = time.time() + 10
+        while sched.q.qsize() < 2 and time.time() < deadline:
+            time.sleep(0.01)
+        code, body = _post(base + "/v1/completions", {"prompt": "one too many", "max_tokens": 2})
+        assert code == 503 and "busy" in body["error"]
+        for t in ts:
+            t.join(10)
+        assert sorted(r[0] for r in results) == [504, 504]       # never scheduled: the request timeout answers
+    finally:
+        httpd.shutdown()
+
+
+def test_generator_prefills_at_admission_when_the_engine_can():
+    """An engine with `prefill` ingests the whole prompt in one call (b200w_infer_prefill) and continues with
+    decode steps at position len(prompt); the token stream must equal the token-by-token path's."""
+    class PrefillStub(StubEngine):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.prefills = []
+
+        def prefill(self, prompts, slots, want_logits=False):
+            self.prefills.append([len(p) for p in prompts])
+            outs = []
+            for p, s in zip(prompts, slots):
+                self.cache[s] = []
+                nxt = None
+                for i, t in enumerate(p):                       # same hash model, whole prompt at once
+                    nxt, _ = StubEngine.step(self, [t], [i], [s])
+                outs.append(int(nxt[0]))
+            self.batch_sizes = [b for b in self.batch_sizes if b != 1 or True]
+            return np.array(outs, dtype=np.int32), None
+
+    rng = np.random.default_rng(1)
+    prompts = [list(map(int, rng.integers(0, VOCAB - 1, size=n))) for n in (1, 7, 3, 12)]
+    eng = PrefillStub(max_batch=2)
+    g = Generator(eng)
+    outs = []
+    for p in prompts:                                            # two slots: admit, run to completion in pairs
+        while not g.free:
+            g.step()
+        outs.append(g.add(p, 5))
+    while g.active:
+        g.step()
+    assert eng.prefills == [[7], [3], [12]]                      # the 1-token prompt goes through the decode path
+    for r, p in zip(outs, prompts):
+        assert r.out == reference(p, 5)

@@ -180,9 +180,13 @@ class Generator:
         self.free = list(range(engine.max_batch))
         self.active: List[_Req] = []
         self.use_prefill = use_prefill and hasattr(engine, "prefill")
+        self._deferred: List[_Req] = []
 
     def add(self, prompt: List[int], max_tokens: int, temperature: float = 0.0, top_p: float = 1.0,
-            seed: Optional[int] = None) -> _Req:
+            seed: Optional[int] = None, defer_prefill: bool = False) -> _Req:
+        """defer_prefill: only register the request; flush_prefill() then ingests every deferred prompt of the
+        same padded length in ONE prefill call (what the scheduler does when several requests are admitted in
+        the same round)."""
         if not prompt:
             raise ValueError("empty prompt")
         V = self.e.serve_arch.vocab_size
@@ -197,11 +201,26 @@ class Generator:
                  np.random.default_rng(seed) if temperature > 0 else None)
         self.active.append(r)
         if self.use_prefill and len(prompt) > 1:
-            nxt, lg = self.e.prefill([r.prompt], [r.slot], want_logits=not r.greedy)
-            r.fed = len(r.prompt)
-            self._emit(r, int(nxt[0]) if r.greedy else sample_token(lg[0], r.temperature, r.top_p, r.rng))
-            self._retire()
+            self._deferred.append(r)
+            if not defer_prefill:
+                self.flush_prefill()
         return r
+
+    def flush_prefill(self):
+        """One prefill call per group of deferred prompts that pad to the same multiple of 128 tokens."""
+        pend, self._deferred = self._deferred, []
+        groups: Dict[int, List[_Req]] = {}
+        for r in pend:
+            groups.setdefault((len(r.prompt) + 127) // 128, []).append(r)
+        for _, rs in sorted(groups.items()):
+            need_logits = any(not r.greedy for r in rs)
+            nxt, lg = self.e.prefill([r.prompt for r in rs], [r.slot for r in rs], want_logits=need_logits)
+            if need_logits and lg is None:
+                raise ValueError("sampling (temperature > 0) needs an engine that returns logits")
+            for i, r in enumerate(rs):
+                r.fed = len(r.prompt)
+                self._emit(r, int(nxt[i]) if r.greedy else sample_token(lg[i], r.temperature, r.top_p, r.rng))
+        self._retire()
 
     def _emit(self, r: _Req, t: int):
         r.out.append(t)

@@ -94,8 +94,10 @@ class Scheduler(threading.Thread):
         pending = {}
         try:
             while True:
-                # admit as many queued requests as there are free slots
+                # admit as many queued requests as there are free slots; their prompts are then ingested together
+                # (one prefill call per padded length) before the next decode step
                 block = not self.gen.active
+                admitted = []
                 while self.gen.free:
                     try:
                         item = self.q.get(timeout=0.5 if block else 0)
@@ -108,16 +110,25 @@ class Scheduler(threading.Thread):
                         ids = self.tok.encode(item["prompt"])
                         if self.tok.bos_id is not None:
                             ids = [self.tok.bos_id] + ids
-                        req = self.gen.add(ids, item["max_tokens"], item["temperature"], item["top_p"], item["seed"])
-                        state = {"sent": 0}
-                        if not self._progress(req, item, len(ids), state):
-                            pending[id(req)] = (req, item, len(ids), state)
-                    except B200WError as e:
-                        if e.status in FATAL_STATUSES:
-                            raise
-                        item["events"].put(("error", str(e)))
+                        req = self.gen.add(ids, item["max_tokens"], item["temperature"], item["top_p"], item["seed"],
+                                           defer_prefill=True)
+                        admitted.append((req, item, len(ids)))
                     except Exception as e:  # noqa: BLE001 — per-request failure, the server lives on
                         item["events"].put(("error", str(e)))
+                if admitted:
+                    try:
+                        self.gen.flush_prefill()
+                    except Exception as e:  # noqa: BLE001
+                        if isinstance(e, B200WError) and e.status in FATAL_STATUSES:
+                            raise
+                        for req, item, _ in admitted:
+                            self.gen.cancel(req)
+                            item["events"].put(("error", f"{type(e).__name__}: {e}"))
+                        admitted = []
+                    for req, item, n_ids in admitted:
+                        state = {"sent": 0}
+                        if not self._progress(req, item, n_ids, state):
+                            pending[id(req)] = (req, item, n_ids, state)
                 try:
                     self.gen.step()
                 except Exception as e:  # noqa: BLE001

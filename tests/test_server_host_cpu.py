@@ -308,3 +308,34 @@ def test_generator_prefills_at_admission_when_the_engine_can():
     assert eng.prefills == [[7], [3], [12]]                      # the 1-token prompt goes through the decode path
     for r, p in zip(outs, prompts):
         assert r.out == reference(p, 5)
+
+
+def test_scheduler_prefills_a_round_of_admissions_in_one_call():
+    """Requests admitted in the same scheduler round are ingested by ONE prefill call per padded length."""
+    class PrefillStub(StubEngine):
+        prefills = []
+
+        def prefill(self, prompts, slots, want_logits=False):
+            PrefillStub.prefills.append(sorted(len(p) for p in prompts))
+            outs = []
+            for p, s in zip(prompts, slots):
+                self.cache[s] = []
+                for i, t in enumerate(p):
+                    nxt, _ = StubEngine.step(self, [t], [i], [s])
+                outs.append(int(nxt[0]))
+            return np.array(outs, dtype=np.int32), None
+
+    PrefillStub.prefills = []
+    eng = PrefillStub(max_batch=4, max_ctx=400)
+    sched = server.Scheduler(eng, CharTok())
+    items = [sched.submit("a" * n, 3) for n in (10, 50, 200, 120)]       # 11, 51, 201, 121 ids with <s>
+    sched.start()
+    tok = CharTok()
+    for it, n in zip(items, (10, 50, 200, 120)):
+        kind, val = it["events"].get(timeout=20)
+        while kind == "delta":
+            kind, val = it["events"].get(timeout=20)
+        assert kind == "done", val
+        alone = Generator(StubEngine(max_batch=1, max_ctx=400)).generate([[tok.bos_id] + tok.encode("a" * n)], 3)[0]
+        assert val["text"] == tok.decode(alone)
+    assert PrefillStub.prefills == [[11, 51, 121], [201]]                # <= 128 tokens together, the 201 alone

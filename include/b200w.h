@@ -45,7 +45,8 @@ typedef enum { B200W_BF16 = 0, B200W_F32 = 1, B200W_I32 = 2 } b200w_dtype;
 /* Model families. The fine-tune engine builds LLAMA and OPT, the Server engine all three. */
 #define B200W_FAMILY_LLAMA 0  /* HF models/llama/modeling_llama.py: RMSNorm, rotate_half RoPE, SwiGLU,
                                  untied lm_head, no biases; head_dim must be 128 for training      */
-#define B200W_FAMILY_FALCON 1 /* HF models/falcon/modeling_falcon.py, falcon-7b layout (Server only) */
+#define B200W_FAMILY_FALCON 1 /* HF models/falcon/modeling_falcon.py, falcon-7b layout: multi_query, parallel_attn,
+                                 one LayerNorm per block, exact GeLU, no biases, tied head                    */
 #define B200W_FAMILY_OPT 2    /* HF models/opt/modeling_opt.py, opt-125m layout: learned positions
                                  (+2), pre-LayerNorm with bias, biased projections, ReLU MLP, tied
                                  lm_head; head_dim 64 or 128 (64 is stored zero-padded to 128 on the
@@ -64,7 +65,7 @@ typedef struct {
   int32_t max_seq_len;  /* sequences are packed to exactly this many tokens (multiple of 128)      */
   float rms_norm_eps;   /* RMSNorm eps (Llama) / LayerNorm eps (OPT: 1e-5)                          */
   float rope_theta;     /* Llama only                                                                */
-  int32_t family;       /* B200W_FAMILY_LLAMA or B200W_FAMILY_OPT                                    */
+  int32_t family;       /* B200W_FAMILY_LLAMA, B200W_FAMILY_OPT or B200W_FAMILY_FALCON               */
   int32_t pad_token_id; /* nn.Embedding(padding_idx=config.pad_token_id): that row gets no gradient
                            from the lookup (modeling_llama.py:358-361, modeling_opt.py:289); -1: none */
   int32_t max_positions; /* OPT: max_position_embeddings (the table holds 2 more rows); else 0      */
@@ -238,6 +239,10 @@ B200W_API int b200w_op_layernorm_bwd(b200w_ctx* ctx, const void* dy, const void*
 B200W_API int b200w_op_bias_act(b200w_ctx* ctx, void* x, const void* bias, int T, int N, int ld, int act);
 /* dz = dy where act > 0 else 0 (act = saved post-ReLU activation); n elements, multiple of 8 */
 B200W_API int b200w_op_relu_bwd(b200w_ctx* ctx, const void* dy, const void* act, void* dz, int64_t n);
+/* exact (erf) GeLU (Falcon MLP): y = gelu(x); dx = dy * gelu'(x) from the saved pre-activation x. n elements,
+ * multiple of 8; dx may alias dy */
+B200W_API int b200w_op_gelu_fwd(b200w_ctx* ctx, const void* x, void* y, int64_t n);
+B200W_API int b200w_op_gelu_bwd(b200w_ctx* ctx, const void* dy, const void* x, void* dx, int64_t n);
 /* db[c] += sum_t dy[t, c] (fp32) */
 B200W_API int b200w_op_colsum(b200w_ctx* ctx, const void* dy, float* db, int T, int N, int ld);
 B200W_API int b200w_op_rmsnorm_fwd(b200w_ctx* ctx, const void* x, const void* w, void* y, float* rstd, int T,

@@ -8,7 +8,9 @@ examples/falcon-7b-instruct/server.yaml serves):
   FalconRotaryEmbedding / apply_rotary_pos_emb : rotate_half, theta 10000
   FalconMLP (:528-543)                   dense_4h_to_h(gelu(dense_h_to_4h(x))), exact (erf) GeLU
   lm_head tied to word_embeddings
-Pinned against FalconForCausalLM outputs in tests/golden/falcon_tiny.npz (oracle/make_golden.py).
+Pinned against FalconForCausalLM outputs in tests/golden/falcon_tiny.npz, and the fine-tune step (train_step:
+HF Trainer loss normaliser, clip, AdamW with the Trainer's decay groups) against two real optimiser steps in
+tests/golden/falcon_tiny_train.npz (oracle/make_golden.py run_falcon / run_falcon_train).
 """
 from __future__ import annotations
 
@@ -19,7 +21,9 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .llama_oracle import apply_rope, bf16_round, causal_attention, rope_cos_sin
+from .llama_oracle import (adamw_update, apply_rope, bf16_round, causal_attention, causal_lm_loss, clip_grad_norm,
+                           rope_cos_sin, trainer_num_items)
+from .llama_oracle import decays as _decays_by_name
 
 
 @dataclass
@@ -95,6 +99,36 @@ def forward(params: Dict[str, torch.Tensor], ids: torch.Tensor, a: FalconArch) -
     h = F.layer_norm(h, (d,), params["transformer.ln_f.weight"], params["transformer.ln_f.bias"],
                      a.layer_norm_epsilon)
     return F.linear(h, params["transformer.word_embeddings.weight"])
+
+
+def decays(name: str) -> bool:
+    """Trainer.get_decay_parameter_names (trainer.py:1280-1290) excludes nn.LayerNorm parameters by module TYPE
+    as well as by name: Falcon's final `ln_f` is an nn.LayerNorm whose name matches none of the patterns (the
+    golden's no_decay list holds it; found by the two-step pin, 8.6e-4 on ln_f.weight)."""
+    return _decays_by_name(name) and not name.startswith("transformer.ln_f.")
+
+
+def train_step(params_np, ids, labels, a: FalconArch, lr=5e-5, max_grad_norm=1.0, state=None, step=1,
+               weight_decay=0.0):
+    """fwd, HF causal-LM loss, bwd (the tied table receives lookup + head gradients through autograd; Falcon's
+    nn.Embedding has no padding_idx, modeling_falcon.py:680), global-norm clip, AdamW. Same return layout as
+    llama_oracle.train_step."""
+    P = {k: torch.tensor(v, dtype=torch.float32, requires_grad=True) for k, v in params_np.items()}
+    logits = forward(P, torch.as_tensor(ids, dtype=torch.int64), a)
+    lab = torch.as_tensor(labels, dtype=torch.int64)
+    loss, nll = causal_lm_loss(logits, lab, trainer_num_items(lab))
+    loss.backward()
+    grads = {k: p.grad.detach() for k, p in P.items()}
+    gnorm, coef = clip_grad_norm(grads, max_grad_norm)
+    new_p, new_m, new_v = {}, {}, {}
+    for k, p in P.items():
+        m0 = torch.zeros_like(p) if state is None else torch.as_tensor(state["m"][k])
+        v0 = torch.zeros_like(p) if state is None else torch.as_tensor(state["v"][k])
+        pn, mn, vn = adamw_update(p.detach(), grads[k] * coef, m0, v0, step, lr,
+                                  wd=weight_decay if decays(k) else 0.0)
+        new_p[k], new_m[k], new_v[k] = pn.numpy(), mn.numpy(), vn.numpy()
+    return dict(loss=float(loss.detach()), gnorm=gnorm, logits=logits.detach().numpy(), nll=nll.detach().numpy(),
+                grads={k: g.numpy() for k, g in grads.items()}, params=new_p, m=new_m, v=new_v)
 
 
 def greedy(params_np, prompt_ids, n_new: int, a: FalconArch):

@@ -379,7 +379,85 @@ def run_opt():
           f"loss2 {out2.loss.item():.6f}; generated[0] = {gen[0].tolist()}")
 
 
+def run_falcon_train():
+    """Tiny falcon-7b-layout model through two real optimiser steps (FalconForCausalLM + torch AdamW with the
+    Trainer's decay groups): multi-query attention backward (4 query heads share one key/value head), the
+    parallel block's shared LayerNorm gradient, exact GeLU, the tied head."""
+    from transformers import FalconConfig, FalconForCausalLM
+    from transformers.trainer_pt_utils import get_parameter_names
+    from oracle import falcon_oracle as FO
+
+    a = FO.FalconArch(vocab_size=512, hidden_size=256, num_layers=2, num_heads=4, head_dim=64)
+    params = FO.seeded_params(a, 41, std=0.06)
+    cfg = FalconConfig(vocab_size=a.vocab_size, hidden_size=a.hidden_size, num_hidden_layers=a.num_layers,
+                       num_attention_heads=a.num_heads, multi_query=True, parallel_attn=True, bias=False,
+                       new_decoder_architecture=False, alibi=False, layer_norm_epsilon=1e-5,
+                       max_position_embeddings=256, tie_word_embeddings=True, hidden_dropout=0.0,
+                       attention_dropout=0.0, pad_token_id=3)
+    cfg._attn_implementation = "sdpa"
+    torch.manual_seed(0)
+    model = FalconForCausalLM(cfg).float()
+    sd = {k: torch.tensor(v) for k, v in params.items()}
+    sd["lm_head.weight"] = sd["transformer.word_embeddings.weight"]
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("rotary" in m or "inv_freq" in m for m in missing), (missing, unexpected)
+    assert model.lm_head.weight.data_ptr() == model.transformer.word_embeddings.weight.data_ptr(), "head must be tied"
+    rng = np.random.default_rng(42)
+    B, S, WD = 2, 128, 0.5
+
+    def batch():
+        ids = rng.integers(0, a.vocab_size, size=(B, S)).astype(np.int64)
+        ids[0, 33] = ids[1, 5] = 3                   # config.pad_token_id: Falcon's embedding has no padding_idx
+        labels = ids.copy()
+        labels[0, :11] = -100
+        labels[1, 50:61] = -100
+        return ids, labels
+
+    def n_items(lab):
+        return torch.tensor(int((lab != -100).sum()))
+
+    named = dict(model.named_parameters())
+    # Trainer.get_decay_parameter_names (trainer.py:1280-1290)
+    decay = [n for n in get_parameter_names(model, [torch.nn.LayerNorm], ["bias", "layernorm", "rmsnorm", "norm"])]
+    groups = [{"params": [p for n, p in named.items() if n in decay], "weight_decay": WD},
+              {"params": [p for n, p in named.items() if n not in decay], "weight_decay": 0.0}]
+    opt = torch.optim.AdamW(groups, lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    ids, labels = batch()
+    model.train()
+    out = model(input_ids=torch.tensor(ids), labels=torch.tensor(labels), num_items_in_batch=n_items(labels))
+    out.loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in named.items()}
+    gnorm = float(torch.nn.utils.clip_grad_norm_(list(named.values()), 1.0))
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    ids2, labels2 = batch()
+    out2 = model(input_ids=torch.tensor(ids2), labels=torch.tensor(labels2), num_items_in_batch=n_items(labels2))
+    out2.loss.backward()
+    gnorm2 = float(torch.nn.utils.clip_grad_norm_(list(named.values()), 1.0))
+    for g in opt.param_groups:
+        g["lr"] = 5e-4
+    opt.step()
+    fx = dict(arch=np.array([a.vocab_size, a.hidden_size, a.num_layers, a.num_heads, a.head_dim]), seed=np.int64(41),
+              std=np.float64(0.06), weight_decay=np.float64(WD), lrs=np.array([1e-3, 5e-4]),
+              ids=ids, labels=labels, ids2=ids2, labels2=labels2, loss=np.float32(out.loss.item()),
+              gnorm=np.float32(gnorm), loss2=np.float32(out2.loss.item()), gnorm2=np.float32(gnorm2),
+              logits=out.logits.detach().numpy().astype(np.float32),
+              no_decay=np.array(sorted(n for n in named if n not in decay)))
+    for k in named:
+        fx["gradnorm/" + k] = np.float32(grads[k].norm().item())
+        fx["grad/" + k] = grads[k].flatten()[::17].numpy().copy()
+        fx["param2/" + k] = named[k].detach().flatten()[::17].numpy().copy()
+    fx["pad_row_grad"] = grads["transformer.word_embeddings.weight"][3].numpy().copy()
+    path = os.path.join(OUT, "falcon_tiny_train.npz")
+    np.savez_compressed(path, **fx)
+    print(f"falcon_tiny_train -> {path} ({os.path.getsize(path) / 1024:.0f} KiB): loss {out.loss.item():.6f} "
+          f"gnorm {gnorm:.6f} loss2 {out2.loss.item():.6f} gnorm2 {gnorm2:.6f}; no_decay {len(fx['no_decay'])}")
+
+
 if __name__ == "__main__":
+    if "--falcon-train-only" in sys.argv:
+        run_falcon_train()
+        sys.exit(0)
     if "--opt-only" in sys.argv:
         run_opt()
         sys.exit(0)
@@ -387,11 +465,13 @@ if __name__ == "__main__":
         run_opt()
         run_trainer_case()
         run_falcon_7b_width()
+        run_falcon_train()
         sys.exit(0)
     run_ops()
     run_falcon()
     run_opt()
     run_trainer_case()
     run_falcon_7b_width()
+    run_falcon_train()
     for name, (a, B, seed) in CASES.items():
         run_case(name, a, B, seed)

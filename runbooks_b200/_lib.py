@@ -95,6 +95,8 @@ PROTOTYPES = {
     "b200w_op_layernorm_bwd": (C.c_int, [c_ctx, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]),
     "b200w_op_bias_act": (C.c_int, [c_ctx, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "b200w_op_relu_bwd": (C.c_int, [c_ctx, vp, vp, vp, C.c_int64]),
+    "b200w_op_gelu_fwd": (C.c_int, [c_ctx, vp, vp, C.c_int64]),
+    "b200w_op_gelu_bwd": (C.c_int, [c_ctx, vp, vp, vp, C.c_int64]),
     "b200w_op_colsum": (C.c_int, [c_ctx, vp, vp, C.c_int, C.c_int, C.c_int]),
     "b200w_op_rmsnorm_fwd": (C.c_int, [c_ctx, vp, vp, vp, vp, C.c_int, C.c_int, C.c_float]),
     "b200w_op_rmsnorm_bwd": (C.c_int, [c_ctx, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]),

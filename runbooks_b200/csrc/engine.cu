@@ -298,6 +298,8 @@ struct b200w_ctx {
 namespace {
 
 bool is_opt(const b200w_arch& a) { return a.family == B200W_FAMILY_OPT; }
+bool is_falcon(const b200w_arch& a) { return a.family == B200W_FAMILY_FALCON; }
+bool has_layernorm(const b200w_arch& a) { return is_opt(a) || is_falcon(a); }
 int qd_of(const b200w_ctx* c) { return c->arch.num_heads * c->dhp; }
 int kd_of(const b200w_ctx* c) { return c->arch.num_kv_heads * c->dhp; }
 int qkv_dim(const b200w_ctx* c) { return qd_of(c) + 2 * kd_of(c); }
@@ -450,9 +452,38 @@ void build_params_opt(b200w_ctx* c) {
   c->p_lm = c->p_embed;  // tied
 }
 
+// Falcon-7B layout (HF models/falcon/modeling_falcon.py, multi_query + parallel_attn, bias=False;
+// checkpoint keys of FalconForCausalLM). query_key_value rows are [H q heads | 1 k head | 1 v head],
+// every 64-wide head padded to 128 like OPT's; lm_head is tied to word_embeddings.
+void build_params_falcon(b200w_ctx* c) {
+  const b200w_arch& a = c->arch;
+  const int d = a.hidden_size, f = a.intermediate_size, L = a.num_layers;
+  const int qd = a.num_heads * a.head_dim, qkv = (a.num_heads + 2 * a.num_kv_heads) * a.head_dim;
+  c->lp.assign(L, {});
+  const std::string tr = "transformer.";
+  add_param(c, tr + "word_embeddings.weight", a.vocab_size, d, 'm', &c->p_embed);
+  for (int l = 0; l < L; ++l) {
+    const std::string pre = tr + "h." + std::to_string(l) + ".";
+    add_param(c, pre + "input_layernorm.weight", 1, d, 'n', &c->lp[l].ln1);
+    add_param(c, pre + "input_layernorm.bias", 1, d, 'b', &c->lp[l].ln1b);
+  }
+  add_param(c, tr + "ln_f.weight", 1, d, 'n', &c->p_norm);
+  add_param(c, tr + "ln_f.bias", 1, d, 'b', &c->p_normb);
+  c->n_zero_prefix = c->n_elems;
+  for (int l = 0; l < L; ++l) {
+    const std::string pre = tr + "h." + std::to_string(l) + ".";
+    auto& p = c->lp[l];
+    add_param(c, pre + "self_attention.query_key_value.weight", qkv, d, 'm', &p.wqkv, 1);
+    add_param(c, pre + "self_attention.dense.weight", d, qd, 'm', &p.wo, 2);
+    add_param(c, pre + "mlp.dense_h_to_4h.weight", f, d, 'm', &p.wgu);
+    add_param(c, pre + "mlp.dense_4h_to_h.weight", d, f, 'm', &p.wd);
+  }
+  c->p_lm = c->p_embed;  // tied
+}
+
 void alloc_activations(b200w_ctx* c) {
   const b200w_arch& a = c->arch;
-  const bool opt = is_opt(a);
+  const bool opt = is_opt(a), falcon = is_falcon(a), ln = has_layernorm(a);
   const size_t T = static_cast<size_t>(c->micro_batch) * a.max_seq_len;
   const size_t d = a.hidden_size, f = a.intermediate_size, qd = qd_of(c), qkvd = qkv_dim(c),
                H = a.num_heads;
@@ -468,11 +499,11 @@ void alloc_activations(b200w_ctx* c) {
       x.attn = c->alloc<bf16>(T * qd);
       x.h_mid = c->alloc<bf16>(T * d);
       x.n2 = c->alloc<bf16>(T * d);
-      x.gu = opt ? nullptr : c->alloc<bf16>(T * 2 * f);
+      x.gu = opt ? nullptr : c->alloc<bf16>(T * (falcon ? 1 : 2) * f);  // Falcon: the pre-GeLU activation
       x.act = c->alloc<bf16>(T * f);
       x.rstd1 = c->alloc<float>(T);
       x.rstd2 = c->alloc<float>(T);
-      x.mean1 = opt ? c->alloc<float>(T) : nullptr;
+      x.mean1 = ln ? c->alloc<float>(T) : nullptr;
       x.mean2 = opt ? c->alloc<float>(T) : nullptr;
       x.lse = c->alloc<float>(H * T);
     } else {
@@ -482,7 +513,7 @@ void alloc_activations(b200w_ctx* c) {
   c->h_final = c->alloc<bf16>(T * d);
   c->nf = c->alloc<bf16>(T * d);
   c->rstdf = c->alloc<float>(T);
-  if (opt) c->meanf = c->alloc<float>(T);
+  if (ln) c->meanf = c->alloc<float>(T);
   c->logits = c->alloc<bf16>(T * a.vocab_size);
   c->nll = c->alloc<float>(T);
   c->targets = c->alloc<int32_t>(T);
@@ -495,20 +526,20 @@ void alloc_activations(b200w_ctx* c) {
     c->dh_b = c->alloc<bf16>(T * d);
     c->dn = c->alloc<bf16>(T * d);
     c->dact = c->alloc<bf16>(T * f);
-    if (!opt) c->dgu = c->alloc<bf16>(T * 2 * f);
+    if (!ln) c->dgu = c->alloc<bf16>(T * 2 * f);
     c->dattn = c->alloc<bf16>(T * qd);
     c->dqkv = c->alloc<bf16>(T * qkvd);
     c->delta = c->alloc<float>(H * T);
     // norm backward partials [blocks, d] (RMSNorm) or [blocks, 2 d] (LayerNorm); bias column sums
     // [colsum_blocks, widest projection]
-    size_t part = static_cast<size_t>(rmsnorm_bwd_blocks(static_cast<int>(T))) * d * (opt ? 2 : 1);
+    size_t part = static_cast<size_t>(rmsnorm_bwd_blocks(static_cast<int>(T))) * d * (ln ? 2 : 1);
     if (opt) {
       const size_t widest = std::max<size_t>({qkvd, f, d});
       part = std::max(part, static_cast<size_t>(colsum_blocks(static_cast<int>(T))) * widest);
     }
     c->dw_partial = c->alloc<float>(part);
   }
-  if (!opt) {
+  if (!opt) {  // the table is over the real head_dim; padded heads rotate their first head_dim columns
     c->rope_tab = c->alloc<float2>(static_cast<size_t>(a.max_seq_len) * (a.head_dim / 2));
     rope_table(c->rope_tab, a.max_seq_len, a.head_dim, a.rope_theta, c->stream);
   }
@@ -613,8 +644,47 @@ void forward_micro_opt(b200w_ctx* c, const int32_t* ids, int nseq) {
   if (c->training && h != c->h_final) throw Error("internal: residual stream bookkeeping");
 }
 
+// ---- Falcon family (HF models/falcon/modeling_falcon.py FalconDecoderLayer.forward :580-650 with
+// parallel_attn and one input_layernorm): ln = LN(h); h' = h + dense(attn(ln)) + 4h_to_h(gelu(h_to_4h(ln))).
+// Multi-query attention: H query heads share one key/value head (the GQA path with Hkv = 1).
+void forward_micro_falcon(b200w_ctx* c, const int32_t* ids, int nseq) {
+  const b200w_arch& a = c->arch;
+  const int S = a.max_seq_len, T = nseq * S, d = a.hidden_size, f = a.intermediate_size;
+  const int H = a.num_heads, Hkv = a.num_kv_heads;
+  const int qd = qd_of(c), kd = kd_of(c), qkvd = qkv_dim(c);
+  const float scale = 1.f / sqrtf(static_cast<float>(a.head_dim));
+  const float eps = a.rms_norm_eps;
+  cudaStream_t s = c->stream;
+  int64_t& n = c->launches;
+  const int L = a.num_layers;
+
+  bf16* h = c->la[0].h_in;
+  embed_fwd(ids, c->w + c->p_embed, nullptr, h, T, d, a.vocab_size, S, 0, s); ++n;
+  for (int l = 0; l < L; ++l) {
+    auto& x = c->la[l];
+    const auto& p = c->lp[l];
+    bf16* h_in = c->training ? x.h_in : h;
+    bf16* h_next = c->training ? (l + 1 < L ? c->la[l + 1].h_in : c->h_final)
+                               : (h == c->la[0].h_in ? c->h_final : c->la[0].h_in);
+    layernorm_fwd(h_in, c->w + p.ln1, c->w + p.ln1b, x.n1, x.mean1, x.rstd1, T, d, eps, s); ++n;
+    egemm(c, x.n1, false, d, c->w + p.wqkv, false, d, x.qkv, nullptr, false, qkvd, T, qkvd, d);
+    rope_apply(x.qkv, qkvd, c->rope_tab, T, S, H + Hkv, a.head_dim, false, s, c->dhp); ++n;
+    attention_fwd(x.qkv, qkvd, qd, qd + kd, x.attn, qd, x.lse, nseq, S, H, Hkv, scale, s); ++n;
+    egemm(c, x.attn, false, qd, c->w + p.wo, false, qd, x.h_mid, h_in, false, d, T, d, qd);
+    egemm(c, x.n1, false, d, c->w + p.wgu, false, d, x.gu, nullptr, false, f, T, f, d);
+    gelu_fwd(x.gu, x.act, static_cast<size_t>(T) * f, s); ++n;
+    egemm(c, x.act, false, f, c->w + p.wd, false, f, h_next, x.h_mid, false, d, T, d, f);
+    h = h_next;
+  }
+  layernorm_fwd(h, c->w + c->p_norm, c->w + c->p_normb, c->nf, c->meanf, c->rstdf, T, d, eps, s); ++n;
+  egemm(c, c->nf, false, d, c->w + c->p_lm, false, d, c->logits, nullptr, false, a.vocab_size, T,
+        a.vocab_size, d);
+  if (c->training && h != c->h_final) throw Error("internal: residual stream bookkeeping");
+}
+
 void forward_micro(b200w_ctx* c, const int32_t* ids, int nseq) {
   if (is_opt(c->arch)) forward_micro_opt(c, ids, nseq);
+  else if (is_falcon(c->arch)) forward_micro_falcon(c, ids, nseq);
   else forward_micro_llama(c, ids, nseq);
 }
 
@@ -802,11 +872,63 @@ void backward_micro_opt(b200w_ctx* c, const int32_t* ids, int nseq, bool first, 
   ar(0, c->n_zero_prefix);
 }
 
+// Falcon backward. Both branches read the same LayerNorm output, so its gradient is the sum of the MLP
+// branch's (written first) and the attention branch's (accumulated by the qkv dgrad GEMM's C operand).
+void backward_micro_falcon(b200w_ctx* c, const int32_t* ids, int nseq, bool first, bool overlap_ar) {
+  const b200w_arch& a = c->arch;
+  const int S = a.max_seq_len, T = nseq * S, d = a.hidden_size, f = a.intermediate_size;
+  const int H = a.num_heads, Hkv = a.num_kv_heads, V = a.vocab_size;
+  const int qd = qd_of(c), kd = kd_of(c), qkvd = qkv_dim(c);
+  const float scale = 1.f / sqrtf(static_cast<float>(a.head_dim));
+  cudaStream_t s = c->stream;
+  int64_t& n = c->launches;
+  const int L = a.num_layers;
+  float* g = c->g;
+  float* part = c->dw_partial;
+  auto acc = [&](size_t off) -> const void* { return first ? nullptr : g + off; };
+  auto ar = [&](size_t off, size_t count) { if (overlap_ar) allreduce_range(c, off, count); };
+
+  egemm(c, c->logits, false, V, c->w + c->p_lm, true, d, c->dn, nullptr, false, d, T, d, V);
+  egemm(c, c->logits, true, V, c->nf, true, d, g + c->p_embed, g + c->p_embed, true, d, V, d, T);
+  bf16* dh_cur = c->dh_a;
+  bf16* dh_alt = c->dh_b;
+  layernorm_bwd(c->dn, c->h_final, c->w + c->p_norm, c->meanf, c->rstdf, nullptr, dh_cur, g + c->p_norm,
+                g + c->p_normb, part, T, d, s); n += 3;
+  for (int l = L - 1; l >= 0; --l) {
+    auto& x = c->la[l];
+    const auto& p = c->lp[l];
+    // MLP branch: h' += gelu(ln W1^T) W2^T
+    egemm(c, dh_cur, false, d, c->w + p.wd, true, f, c->dact, nullptr, false, f, T, f, d);
+    egemm(c, dh_cur, true, d, x.act, true, f, g + p.wd, acc(p.wd), true, f, d, f, T);
+    ar(p.wd, static_cast<size_t>(d) * f);
+    gelu_bwd(c->dact, x.gu, c->dact, static_cast<size_t>(T) * f, s); ++n;
+    egemm(c, c->dact, false, f, c->w + p.wgu, true, d, c->dn, nullptr, false, d, T, d, f);
+    egemm(c, c->dact, true, f, x.n1, true, d, g + p.wgu, acc(p.wgu), true, d, f, d, T);
+    ar(p.wgu, static_cast<size_t>(f) * d);
+    // attention branch: h' += attn Wo^T
+    egemm(c, dh_cur, false, d, c->w + p.wo, true, qd, c->dattn, nullptr, false, qd, T, qd, d);
+    egemm(c, dh_cur, true, d, x.attn, true, qd, g + p.wo, acc(p.wo), true, qd, d, qd, T);
+    ar(p.wo, static_cast<size_t>(d) * qd);
+    attention_bwd(x.qkv, qkvd, qd, qd + kd, x.attn, c->dattn, qd, x.lse, c->delta, c->dqkv, nseq, S, H,
+                  Hkv, scale, s); n += 3;
+    rope_apply(c->dqkv, qkvd, c->rope_tab, T, S, H + Hkv, a.head_dim, true, s, c->dhp); ++n;
+    egemm(c, c->dqkv, false, qkvd, c->w + p.wqkv, true, d, c->dn, c->dn, false, d, T, d, qkvd);
+    egemm(c, c->dqkv, true, qkvd, x.n1, true, d, g + p.wqkv, acc(p.wqkv), true, d, qkvd, d, T);
+    ar(p.wqkv, static_cast<size_t>(qkvd) * d);
+    layernorm_bwd(c->dn, x.h_in, c->w + p.ln1, x.mean1, x.rstd1, dh_cur, dh_alt, g + p.ln1, g + p.ln1b, part,
+                  T, d, s); n += 3;
+    std::swap(dh_cur, dh_alt);
+  }
+  embed_bwd(ids, dh_cur, g + c->p_embed, nullptr, T, d, V, a.pad_token_id, S, 0, s); ++n;
+  ar(0, c->n_zero_prefix);
+}
+
 void backward_micro(b200w_ctx* c, const int32_t* ids, int nseq, bool first, bool overlap_ar) {
   // while the all-reduce runs under the backward, the persistent GEMMs leave NCCL its SMs
   if (overlap_ar) gemm_set_sm_reserve(c->ar_sm_reserve);
   try {
     if (is_opt(c->arch)) backward_micro_opt(c, ids, nseq, first, overlap_ar);
+    else if (is_falcon(c->arch)) backward_micro_falcon(c, ids, nseq, first, overlap_ar);
     else backward_micro_llama(c, ids, nseq, first, overlap_ar);
   } catch (...) {
     gemm_set_sm_reserve(0);
@@ -1126,10 +1248,14 @@ int b200w_model_init(b200w_ctx* ctx, const b200w_arch* arch, const b200w_hparams
   return guarded(ctx, [&] {
     B200W_CHECK(arch != nullptr, "arch is NULL");
     B200W_CHECK(!ctx->has_model, "model already initialised");
-    B200W_CHECK(arch->family == B200W_FAMILY_LLAMA || arch->family == B200W_FAMILY_OPT,
-                "the fine-tune engine builds the Llama and OPT families");
-    const bool opt = arch->family == B200W_FAMILY_OPT;
-    if (opt) {
+    B200W_CHECK(arch->family == B200W_FAMILY_LLAMA || arch->family == B200W_FAMILY_OPT ||
+                    arch->family == B200W_FAMILY_FALCON,
+                "the fine-tune engine builds the Llama, OPT and Falcon families");
+    const bool opt = arch->family == B200W_FAMILY_OPT, falcon = arch->family == B200W_FAMILY_FALCON;
+    if (falcon) {
+      B200W_CHECK(arch->head_dim == 64 || arch->head_dim == 128, "Falcon: head_dim must be 64 or 128");
+      B200W_CHECK(arch->hidden_size == arch->num_heads * arch->head_dim, "Falcon: hidden_size = heads x head_dim");
+    } else if (opt) {
       B200W_CHECK(arch->head_dim == 64 || arch->head_dim == 128, "OPT: head_dim must be 64 or 128");
       B200W_CHECK(arch->num_kv_heads == arch->num_heads, "OPT has no grouped-query attention");
       B200W_CHECK(arch->hidden_size == arch->num_heads * arch->head_dim, "OPT: hidden_size = heads x head_dim");
@@ -1154,7 +1280,7 @@ int b200w_model_init(b200w_ctx* ctx, const b200w_arch* arch, const b200w_hparams
     B200W_CHECK(!ctx->shard || (ctx->comm && ctx->nranks > 1),
                 "sharded optimiser state needs the communicator first: b200w_comm_init before b200w_model_init(training = 2)");
     ctx->dhp = 128;
-    if (opt) build_params_opt(ctx); else build_params_llama(ctx);
+    if (opt) build_params_opt(ctx); else if (falcon) build_params_falcon(ctx); else build_params_llama(ctx);
     build_segments(ctx);
     {
       const size_t d = arch->hidden_size, f = arch->intermediate_size, V = arch->vocab_size;
@@ -1163,10 +1289,10 @@ int b200w_model_init(b200w_ctx* ctx, const b200w_arch* arch, const b200w_hparams
       for (const auto& lp : ctx->lp) {
         mats.push_back({lp.wqkv, qkvd * d});
         mats.push_back({lp.wo, d * qd});
-        mats.push_back({lp.wgu, (opt ? f : 2 * f) * d});
+        mats.push_back({lp.wgu, (opt || falcon ? f : 2 * f) * d});
         mats.push_back({lp.wd, d * f});
       }
-      if (!opt) mats.push_back({ctx->p_lm, V * d});
+      if (!opt && !falcon) mats.push_back({ctx->p_lm, V * d});
       build_ranges(ctx, mats);
       size_t covered = 0;
       for (const auto& rg : ctx->ranges) {
@@ -1667,6 +1793,12 @@ int b200w_op_bias_act(b200w_ctx* ctx, void* x, const void* bias, int T, int N, i
 }
 int b200w_op_relu_bwd(b200w_ctx* ctx, const void* dy, const void* act, void* dz, int64_t n) {
   HOOK(relu_bwd(dy, act, dz, static_cast<size_t>(n), ctx->stream));
+}
+int b200w_op_gelu_fwd(b200w_ctx* ctx, const void* x, void* y, int64_t n) {
+  HOOK(gelu_fwd(x, y, static_cast<size_t>(n), ctx->stream));
+}
+int b200w_op_gelu_bwd(b200w_ctx* ctx, const void* dy, const void* x, void* dx, int64_t n) {
+  HOOK(gelu_bwd(dy, x, dx, static_cast<size_t>(n), ctx->stream));
 }
 int b200w_op_colsum(b200w_ctx* ctx, const void* dy, float* db, int T, int N, int ld) {
   return guarded(ctx, [&] {

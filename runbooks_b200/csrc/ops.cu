@@ -248,7 +248,7 @@ __global__ void rmsnorm_dw_reduce_kernel(const float* __restrict__ dw_partial, f
 // apply_rotary_pos_emb; inv_freq = theta^(-2i/dh))
 // ------------------------------------------------------------------------------------------
 __global__ void rope_apply_kernel(bf16* buf, int ld, const float2* __restrict__ tab, int T, int S,
-                                  int nheads, int dh, float sgn) {
+                                  int nheads, int dh, int head_stride, float sgn) {
   const int half = dh / 2;
   const int per_head = half / 8;  // threads per (token, head)
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -258,7 +258,7 @@ __global__ void rope_apply_kernel(bf16* buf, int ld, const float2* __restrict__ 
   const int h = static_cast<int>((idx / per_head) % nheads);
   const int t = static_cast<int>(idx / (static_cast<long long>(per_head) * nheads));
   const int pos = t % S;
-  bf16* p = buf + static_cast<size_t>(t) * ld + h * dh + i0;
+  bf16* p = buf + static_cast<size_t>(t) * ld + h * head_stride + i0;
   float x1[8], x2[8], o1[8], o2[8];
   load8(p, x1);
   load8(p + half, x2);
@@ -718,6 +718,33 @@ __global__ void relu_bwd_kernel(const bf16* dy, const bf16* __restrict__ act, bf
     store8(dz + i * 8, g);
   }
 }
+// exact (erf) GeLU, nn.GELU() default -- what FalconMLP applies (HF modeling_falcon.py:528-543).
+// forward: y = x Phi(x); backward from the saved PRE-activation: dx = dy (Phi(x) + x phi(x)).
+__global__ void gelu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, size_t n8) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float v[8];
+    load8(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+    store8(y + i * 8, v);
+  }
+}
+__global__ void gelu_bwd_kernel(const bf16* dy, const bf16* __restrict__ x, bf16* dx, size_t n8) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float g[8], v[8];
+    load8(dy + i * 8, g);
+    load8(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float cdf = 0.5f * (1.f + erff(v[j] * 0.70710678118654752f));
+      const float pdf = 0.39894228040143268f * expf(-0.5f * v[j] * v[j]);
+      g[j] *= cdf + v[j] * pdf;
+    }
+    store8(dx + i * 8, g);
+  }
+}
 // column sums of dy [T, N] (row stride ld) -> part[gridDim.y][N]; block = 32 column groups of 8 x
 // 8 row lanes, rows strided by 8 * gridDim.y. Summed into db by rmsnorm_dw_reduce_kernel.
 __global__ void __launch_bounds__(256)
@@ -821,11 +848,13 @@ void rope_table(float2* tab, int S, int dh, float theta, cudaStream_t s) {
   B200W_CUDA(cudaStreamSynchronize(s));  // h goes out of scope
 }
 void rope_apply(void* buf, int ld, const float2* tab, int T, int S, int nheads, int dh,
-                bool inverse, cudaStream_t s) {
-  B200W_CHECK(dh % 16 == 0 && ld % 8 == 0, "head_dim must be a multiple of 16");
+                bool inverse, cudaStream_t s, int head_stride) {
+  if (head_stride == 0) head_stride = dh;
+  B200W_CHECK(dh % 16 == 0 && ld % 8 == 0 && head_stride % 8 == 0 && head_stride >= dh,
+              "head_dim must be a multiple of 16");
   const long long total = static_cast<long long>(T) * nheads * (dh / 16);
   rope_apply_kernel<<<blocks_for(total, 256), 256, 0, s>>>(static_cast<bf16*>(buf), ld, tab, T, S,
-                                                           nheads, dh, inverse ? -1.f : 1.f);
+                                                           nheads, dh, head_stride, inverse ? -1.f : 1.f);
   B200W_CUDA(cudaGetLastError());
 }
 
@@ -930,6 +959,17 @@ void relu_bwd(const void* dy, const void* act, void* dz, size_t n, cudaStream_t 
   B200W_CHECK(n % 8 == 0, "element count must be a multiple of 8");
   relu_bwd_kernel<<<sm_count() * 8, 256, 0, s>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(act),
                                                  static_cast<bf16*>(dz), n / 8);
+  B200W_CUDA(cudaGetLastError());
+}
+void gelu_fwd(const void* x, void* y, size_t n, cudaStream_t s) {
+  B200W_CHECK(n % 8 == 0, "element count must be a multiple of 8");
+  gelu_fwd_kernel<<<sm_count() * 8, 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), n / 8);
+  B200W_CUDA(cudaGetLastError());
+}
+void gelu_bwd(const void* dy, const void* x, void* dx, size_t n, cudaStream_t s) {
+  B200W_CHECK(n % 8 == 0, "element count must be a multiple of 8");
+  gelu_bwd_kernel<<<sm_count() * 8, 256, 0, s>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x),
+                                                 static_cast<bf16*>(dx), n / 8);
   B200W_CUDA(cudaGetLastError());
 }
 int colsum_blocks(int T) { return T >= 256 ? 32 : (T + 7) / 8; }

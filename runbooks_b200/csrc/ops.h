@@ -83,8 +83,9 @@ void rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd
 void rope_table(float2* tab, int S, int dh, float theta, cudaStream_t s);
 // in-place rotation of `nheads` consecutive heads starting at column 0 of buf [T, ld];
 // position = t % S. inverse=true applies the transpose (backward pass).
+// head_stride: distance between heads in elements (0 = dh; > dh when 64-wide heads are stored padded).
 void rope_apply(void* buf, int ld, const float2* tab, int T, int S, int nheads, int dh,
-                bool inverse, cudaStream_t s);
+                bool inverse, cudaStream_t s, int head_stride = 0);
 
 // gu: [T, 2f] (gate | up); h: [T, f] = silu(gate) * up
 void swiglu_fwd(const void* gu, void* h, int T, int f, cudaStream_t s);
@@ -124,6 +125,9 @@ void layernorm_bwd(const void* dy, const void* x, const void* w, const float* me
 void bias_act(void* x, const void* bias, int T, int N, int ld, int act, cudaStream_t s);
 // dz = dy * (act > 0): backward of ReLU from the saved post-activation; dz may alias dy
 void relu_bwd(const void* dy, const void* act, void* dz, size_t n, cudaStream_t s);
+// exact (erf) GeLU: y = gelu(x); dx = dy * gelu'(x) from the saved pre-activation (dx may alias dy)
+void gelu_fwd(const void* x, void* y, size_t n, cudaStream_t s);
+void gelu_bwd(const void* dy, const void* x, void* dx, size_t n, cudaStream_t s);
 // db[c] += sum_t dy[t, c] (fp32, deterministic). part: fp32 scratch [colsum_blocks(T), N]
 int colsum_blocks(int T);
 void colsum_add(const void* dy, float* db, float* part, int T, int N, int ld, cudaStream_t s);

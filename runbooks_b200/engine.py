@@ -162,14 +162,83 @@ class OptArch:
                     family=self.family, pad_token_id=self.pad_token_id, max_positions=self.max_positions)
 
 
+@dataclass
+class FalconArch:
+    """tiiuae/falcon-7b family (HF models/falcon/modeling_falcon.py; the reference serves it from
+    examples/falcon-7b-instruct/): multi-query attention (H query heads, one key/value head), parallel
+    attention + MLP after one LayerNorm, rotate_half RoPE, exact GeLU, no biases, tied lm_head."""
+    vocab_size: int
+    hidden_size: int
+    intermediate_size: int     # ffn_hidden_size (4 x hidden_size)
+    num_layers: int
+    num_heads: int
+    max_seq_len: int = 2048
+    layer_norm_eps: float = 1e-5
+    rope_theta: float = 10000.0
+    pad_token_id: int = -1
+    num_kv_heads: int = 1
+    family = FAMILY_FALCON
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_heads
+
+    @classmethod
+    def falcon_7b(cls, seq_len: int = 2048) -> "FalconArch":
+        return cls(65024, 4544, 18176, 32, 71, seq_len)
+
+    @classmethod
+    def from_hf_config(cls, cfg: dict, seq_len: Optional[int] = None) -> "FalconArch":
+        if cfg.get("model_type") != "falcon":
+            raise ValueError(f"unsupported model_type {cfg.get('model_type')!r}")
+        d, heads = cfg["hidden_size"], cfg["num_attention_heads"]
+        _reject(cfg.get("alibi", False), "alibi positions")
+        _reject(cfg.get("bias", False), "bias=true")
+        _reject(cfg.get("new_decoder_architecture", False), "new_decoder_architecture (falcon-40b layout)")
+        _reject(not cfg.get("parallel_attn", True), "parallel_attn=false")
+        _reject(not cfg.get("multi_query", True), "multi_query=false")
+        _reject(cfg.get("activation", "gelu") != "gelu", f"activation {cfg.get('activation')!r}")
+        _reject(not cfg.get("tie_word_embeddings", True), "untied lm_head for a Falcon checkpoint")
+        _reject((cfg.get("rope_scaling") or {}).get("rope_type", "default") != "default", "rope scaling")
+        _reject((d // heads) not in (64, 128), "head_dim other than 64 / 128")
+        rope = cfg.get("rope_parameters") or {}
+        _reject(rope.get("rope_type", "default") != "default", "rope scaling")
+        maxpos = cfg.get("max_position_embeddings", 2048)
+        # FalconModel builds nn.Embedding(vocab, d) WITHOUT padding_idx (modeling_falcon.py:680): the pad row
+        # gets its lookup gradient like every other row, whatever config.pad_token_id says
+        return cls(cfg["vocab_size"], d, cfg.get("ffn_hidden_size") or 4 * d, cfg["num_hidden_layers"], heads,
+                   min(seq_len or maxpos, maxpos), cfg.get("layer_norm_epsilon", 1e-5),
+                   float(rope.get("rope_theta", cfg.get("rope_theta", 10000.0))), -1)
+
+    def to_hf_config(self) -> dict:
+        return {
+            "architectures": ["FalconForCausalLM"], "model_type": "falcon", "vocab_size": self.vocab_size,
+            "hidden_size": self.hidden_size, "ffn_hidden_size": self.intermediate_size,
+            "num_hidden_layers": self.num_layers, "num_attention_heads": self.num_heads, "multi_query": True,
+            "parallel_attn": True, "new_decoder_architecture": False, "bias": False, "alibi": False,
+            "activation": "gelu", "layer_norm_epsilon": self.layer_norm_eps, "rope_theta": self.rope_theta,
+            "max_position_embeddings": self.max_seq_len, "tie_word_embeddings": True, "hidden_dropout": 0.0,
+            "attention_dropout": 0.0, "bos_token_id": 11, "eos_token_id": 11, "torch_dtype": "bfloat16",
+        }
+
+    def c_fields(self) -> dict:
+        return dict(vocab_size=self.vocab_size, hidden_size=self.hidden_size,
+                    intermediate_size=self.intermediate_size, num_layers=self.num_layers,
+                    num_heads=self.num_heads, num_kv_heads=self.num_kv_heads, head_dim=self.head_dim,
+                    max_seq_len=self.max_seq_len, rms_norm_eps=self.layer_norm_eps, rope_theta=self.rope_theta,
+                    family=self.family, pad_token_id=self.pad_token_id, max_positions=0)
+
+
 def arch_from_hf_config(cfg: dict, seq_len: Optional[int] = None):
-    """config.json -> LlamaArch | OptArch; anything else (or any unimplemented variant) raises."""
+    """config.json -> LlamaArch | OptArch | FalconArch; anything else (or any unimplemented variant) raises."""
     mt = cfg.get("model_type", "llama")
     if mt == "llama":
         return LlamaArch.from_hf_config(cfg, seq_len)
     if mt == "opt":
         return OptArch.from_hf_config(cfg, seq_len)
-    raise ValueError(f"unsupported model_type {mt!r}: the fine-tune engine builds llama and opt")
+    if mt == "falcon":
+        return FalconArch.from_hf_config(cfg, seq_len)
+    raise ValueError(f"unsupported model_type {mt!r}: the fine-tune engine builds llama, opt and falcon")
 
 
 def _as_i32(a) -> np.ndarray:

@@ -196,6 +196,19 @@ def test_unimplemented_checkpoint_variants_fail_instead_of_training_something_el
     assert isinstance(o, OptArch) and (o.head_dim, o.pad_token_id, o.max_seq_len) == (64, 1, 2048)
     with pytest.raises(ValueError):
         arch_from_hf_config({"model_type": "mistral"})
+    from runbooks_b200.engine import FalconArch
+    fbase = {"model_type": "falcon", "vocab_size": 65024, "hidden_size": 4544, "num_hidden_layers": 32,
+             "num_attention_heads": 71, "multi_query": True, "parallel_attn": True, "bias": False, "alibi": False,
+             "new_decoder_architecture": False, "pad_token_id": 11}
+    fa = arch_from_hf_config(fbase, 1024)
+    assert isinstance(fa, FalconArch) and (fa.head_dim, fa.num_kv_heads, fa.intermediate_size, fa.max_seq_len) == (64, 1, 18176, 1024)
+    assert fa.pad_token_id == -1          # FalconModel's nn.Embedding has no padding_idx, whatever the config says
+    assert fa == FalconArch.falcon_7b(1024)
+    for bad in ({"alibi": True}, {"bias": True}, {"new_decoder_architecture": True}, {"parallel_attn": False},
+                {"multi_query": False}, {"activation": "relu"}, {"tie_word_embeddings": False},
+                {"rope_parameters": {"rope_type": "linear", "factor": 2.0}}):
+        with pytest.raises(ValueError):
+            arch_from_hf_config(dict(fbase, **bad))
     # tensors the engine would silently drop
     assert contract.is_ignorable_tensor("lm_head.weight", {"model_type": "opt"})
     assert contract.is_ignorable_tensor("model.layers.0.self_attn.rotary_emb.inv_freq", {"model_type": "llama"})

@@ -107,6 +107,27 @@ def test_bias_relu_and_their_backward(engine):
     assert rel_err(db, 2 * x.float()[:, :N].sum(0)) < 1e-5
 
 
+def test_gelu_and_its_backward(engine):
+    """Exact (erf) GeLU, what FalconMLP applies (nn.GELU()): forward within one bf16 rounding of torch's fp32
+    value, backward from the saved pre-activation against autograd."""
+    n = 300 * 1024
+    x = (2.5 * torch.randn(n, generator=G(7))).bfloat16()
+    y = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    call(engine, "b200w_op_gelu_fwd", dev(x), y, n)
+    ref = torch.nn.functional.gelu(x.float())
+    assert torch.equal(y.cpu(), ref.bfloat16()) or (y.cpu().float() - ref).abs().max() <= 2 ** -8 * ref.abs().max()
+    assert rel_err(y, ref) < 3e-3
+    dy = torch.randn(n, generator=G(8)).bfloat16()
+    xr = x.float().requires_grad_(True)
+    torch.nn.functional.gelu(xr).backward(dy.float())
+    dx = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    call(engine, "b200w_op_gelu_bwd", dev(dy), dev(x), dx, n)
+    assert rel_err(dx, xr.grad) < 3e-3
+    dyd = dev(dy)
+    call(engine, "b200w_op_gelu_bwd", dyd, dev(x), dyd, n)          # in place, as the engine calls it
+    assert torch.equal(dyd.cpu(), dx.cpu())
+
+
 @pytest.mark.parametrize("T,d", [(37, 256), (130, 4096), (5, 8192), (64, 520)])
 def test_rmsnorm_fwd_bwd(engine, T, d):
     x = torch.randn(T, d, generator=G(3)).bfloat16()

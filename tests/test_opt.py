@@ -70,7 +70,9 @@ def _torch_bf16_gradient_distance(params, ids, labels, oa, ref):
     lab = torch.tensor(labels)
     loss, _ = causal_lm_loss(OO.forward(Pb, torch.tensor(ids), oa).float(), lab, trainer_num_items(lab))
     loss.backward()
-    return {k: rel_err(p.grad.float().numpy(), ref[k]) for k, p in Pb.items()}
+    dist = {k: rel_err(p.grad.float().numpy(), ref[k]) for k, p in Pb.items()}
+    norm = {k: abs(float(p.grad.float().norm()) / max(float(np.linalg.norm(ref[k])), 1e-30) - 1.0) for k, p in Pb.items()}
+    return dist, norm
 
 
 def test_opt_gradients_match_hf():
@@ -82,7 +84,7 @@ def test_opt_gradients_match_hf():
     loss = e.forward_backward(fx["ids"], fx["labels"])
     assert abs(loss - float(fx["loss"])) < 1e-3 * float(fx["loss"])
     ref = OO.train_step(params, fx["ids"], fx["labels"], oa)["grads"]
-    floor = _torch_bf16_gradient_distance(params, fx["ids"], fx["labels"], oa, ref)
+    floor, norm_floor = _torch_bf16_gradient_distance(params, fx["ids"], fx["labels"], oa, ref)
     rows = []
     for name, shape in e.params():
         g = e.read_state(name, shape, "grad")
@@ -92,7 +94,9 @@ def test_opt_gradients_match_hf():
             continue
         rows.append((rel_err(g, ref[name]), floor[name], name))
         gn = float(np.linalg.norm(g.astype(np.float64)))
-        assert abs(gn - float(fx["gradnorm/" + name])) < 2e-2 * float(fx["gradnorm/" + name]), name   # norms: 2 %
+        # norms: 2 %, or 1.5 x what the torch bf16 path shows on that tensor (up to 2.5 % here: the mask flips again)
+        gold = float(fx["gradnorm/" + name])
+        assert abs(gn - gold) < max(2e-2, 1.5 * norm_floor[name]) * gold, (name, gn, gold, norm_floor[name])
     rows.sort(reverse=True)
     for err, fl, name in rows[:5]:
         print(f"opt grad {name:58s} rel_err {err:.3e} (torch bf16-vs-fp32 on the same tensor: {fl:.3e})")

@@ -212,3 +212,33 @@ def test_opt_restatement_details_matter():
     g_pad = OO.train_step(params, fx["ids"], fx["labels"], a)["grads"]["model.decoder.embed_tokens.weight"]
     g_plain = OO.train_step(params, fx["ids"], fx["labels"], plain)["grads"]["model.decoder.embed_tokens.weight"]
     assert np.abs(g_pad - g_plain).max() > 1e-4 * np.abs(g_pad).max()
+
+
+def test_falcon_two_train_steps_match_hf():
+    """oracle/falcon_oracle.py train_step against two real optimiser steps of FalconForCausalLM + AdamW with the
+    Trainer's decay groups (weight decay 0.5 so that a wrong group shows: `ln_f` is excluded by module type,
+    not by name)."""
+    from oracle import falcon_oracle as FO
+    fx = np.load("tests/golden/falcon_tiny_train.npz")
+    V, d, L, H, dh = (int(x) for x in fx["arch"])
+    a = FO.FalconArch(vocab_size=V, hidden_size=d, num_layers=L, num_heads=H, head_dim=dh)
+    params = FO.seeded_params(a, int(fx["seed"]), std=float(fx["std"]))
+    assert sorted(k for k in params if not FO.decays(k)) == sorted(str(x) for x in fx["no_decay"])
+    lr1, lr2 = (float(x) for x in fx["lrs"])
+    wd = float(fx["weight_decay"])
+    r1 = FO.train_step(params, fx["ids"], fx["labels"], a, lr=lr1, step=1, weight_decay=wd)
+    assert abs(r1["loss"] - float(fx["loss"])) < 2e-5 * abs(float(fx["loss"]))
+    assert abs(r1["gnorm"] - float(fx["gnorm"])) < 2e-5 * float(fx["gnorm"])
+    np.testing.assert_allclose(r1["logits"], fx["logits"], rtol=0, atol=2e-5 * np.abs(fx["logits"]).max())
+    for k in params:
+        g = r1["grads"][k]
+        assert abs(np.linalg.norm(g) - float(fx["gradnorm/" + k])) < 1e-5 * float(fx["gradnorm/" + k]), k
+        np.testing.assert_allclose(g.flatten()[::17], fx["grad/" + k], rtol=0, atol=1e-5 * float(fx["gradnorm/" + k]), err_msg=k)
+    np.testing.assert_allclose(r1["grads"]["transformer.word_embeddings.weight"][3], fx["pad_row_grad"], rtol=0,
+                               atol=1e-5 * np.abs(fx["pad_row_grad"]).max())
+    assert np.abs(fx["pad_row_grad"]).max() > 0
+    r2 = FO.train_step(r1["params"], fx["ids2"], fx["labels2"], a, lr=lr2, state=r1, step=2, weight_decay=wd)
+    assert abs(r2["loss"] - float(fx["loss2"])) < 2e-5 * abs(float(fx["loss2"]))
+    assert abs(r2["gnorm"] - float(fx["gnorm2"])) < 2e-5 * float(fx["gnorm2"])
+    for k in params:
+        np.testing.assert_allclose(r2["params"][k].flatten()[::17], fx["param2/" + k], rtol=0, atol=2e-5, err_msg=k)

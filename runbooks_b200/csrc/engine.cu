@@ -547,7 +547,8 @@ void alloc_activations(b200w_ctx* c) {
 
 // GEMM launch with optional CUDA-event bracketing (bench.py's roofline leg)
 void egemm(b200w_ctx* c, const void* A, bool a_mn, int lda, const void* B, bool b_mn, int ldb, void* D,
-           const void* C, bool out_fp32, int ldd, int M, int N, int K, const void* bias = nullptr, int act = 0) {
+           const void* C, bool out_fp32, int ldd, int M, int N, int K, const void* bias = nullptr, int act = 0,
+           void* d2_bf16 = nullptr) {
   cudaStream_t s = c->stream;
   if (c->prof_gemm) {
     if (c->prof_used + 2 > c->prof_events.size()) {
@@ -559,7 +560,7 @@ void egemm(b200w_ctx* c, const void* A, bool a_mn, int lda, const void* B, bool 
     }
     B200W_CUDA(cudaEventRecord(c->prof_events[c->prof_used], s));
   }
-  gemm_bf16_ex(A, a_mn, lda, B, b_mn, ldb, D, C, out_fp32, ldd, M, N, K, 0, bias, act, s);
+  gemm_bf16_ex(A, a_mn, lda, B, b_mn, ldb, D, C, out_fp32, ldd, M, N, K, 0, bias, act, s, d2_bf16);
   ++c->launches;
   if (c->prof_gemm) {
     B200W_CUDA(cudaEventRecord(c->prof_events[c->prof_used + 1], s));
@@ -728,9 +729,10 @@ void ensure_wire(b200w_ctx* c) {
 // Sharded optimiser state: the collective is a reduce-scatter -- rank r receives the sum of slice r of
 // the range, in place, which is all its share of the optimiser needs (SURVEY.md 8e, config #5:
 // reduce_scatter -> local AdamW on the shard -> all_gather, the wire bytes of one all-reduce).
-void exchange_one(b200w_ctx* c, size_t off, size_t count) {
+// precast: the wgrad GEMM that produced this range already wrote its bf16 wire copy (EpiExtra::d2).
+void exchange_one(b200w_ctx* c, size_t off, size_t count, bool precast = false) {
   const ArMode mode = ar_mode();
-  cast_f32_to_bf16(c->g + off, c->gw + off, count, c->stream); ++c->launches;
+  if (!precast) { cast_f32_to_bf16(c->g + off, c->gw + off, count, c->stream); ++c->launches; }
   if (mode == ArMode::Sync) B200W_CUDA(cudaStreamSynchronize(c->stream));
   B200W_CUDA(cudaEventRecord(c->ev_grad, c->stream));
   B200W_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_grad, 0));
@@ -748,13 +750,13 @@ void exchange_one(b200w_ctx* c, size_t off, size_t count) {
     B200W_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
   }
 }
-void allreduce_range(b200w_ctx* c, size_t off, size_t count) {
+void allreduce_range(b200w_ctx* c, size_t off, size_t count, bool precast = false) {
   if (count == 0) return;
-  if (!c->shard) return exchange_one(c, off, count);
+  if (!c->shard) return exchange_one(c, off, count, precast);
   // sharded: slices are defined per exchange range, so a request is served range by range
   bool any = false;
   for (const auto& r : c->ranges)
-    if (r.off >= off && r.off + r.cnt <= off + count) { exchange_one(c, r.off, r.cnt); any = true; }
+    if (r.off >= off && r.off + r.cnt <= off + count) { exchange_one(c, r.off, r.cnt, precast); any = true; }
   if (!any) throw Error("internal: gradient exchange request does not match the exchange ranges");
 }
 
@@ -772,11 +774,14 @@ void backward_micro_llama(b200w_ctx* c, const int32_t* ids, int nseq, bool first
   float* g = c->g;
   auto acc = [&](size_t off) -> const void* { return first ? nullptr : g + off; };
   auto ar = [&](size_t off, size_t count) { if (overlap_ar) allreduce_range(c, off, count); };
+  // matrices whose exchange follows their wgrad at once: the GEMM epilogue writes the bf16 wire copy itself
+  auto wire = [&](size_t off) -> void* { return overlap_ar ? c->gw + off : nullptr; };
+  auto arw = [&](size_t off, size_t count) { if (overlap_ar) allreduce_range(c, off, count, true); };
 
   // lm_head: dnf = dlogits W ; dW += dlogits^T nf
   egemm(c, c->logits, false, V, c->w + c->p_lm, true, d, c->dn, nullptr, false, d, T, d, V);
-  egemm(c, c->logits, true, V, c->nf, true, d, g + c->p_lm, acc(c->p_lm), true, d, V, d, T);
-  ar(c->p_lm, static_cast<size_t>(V) * d);
+  egemm(c, c->logits, true, V, c->nf, true, d, g + c->p_lm, acc(c->p_lm), true, d, V, d, T, nullptr, 0, wire(c->p_lm));
+  arw(c->p_lm, static_cast<size_t>(V) * d);
   bf16* dh_cur = c->dh_a;
   bf16* dh_alt = c->dh_b;
   rmsnorm_bwd(c->dn, c->h_final, c->w + c->p_norm, c->rstdf, nullptr, dh_cur, g + c->p_norm, c->dw_partial, T, d, s); n += 2;
@@ -787,25 +792,25 @@ void backward_micro_llama(b200w_ctx* c, const int32_t* ids, int nseq, bool first
     const size_t o_q = p.wqkv, o_o = p.wo, o_gu = p.wgu, o_d = p.wd;
     // h_next = h_mid + act Wd^T
     egemm(c, dh_cur, false, d, c->w + o_d, true, f, c->dact, nullptr, false, f, T, f, d);
-    egemm(c, dh_cur, true, d, x.act, true, f, g + o_d, acc(o_d), true, f, d, f, T);
-    ar(o_d, static_cast<size_t>(d) * f);
+    egemm(c, dh_cur, true, d, x.act, true, f, g + o_d, acc(o_d), true, f, d, f, T, nullptr, 0, wire(o_d));
+    arw(o_d, static_cast<size_t>(d) * f);
     swiglu_bwd(c->dact, x.gu, c->dgu, T, f, s); ++n;
     egemm(c, c->dgu, false, 2 * f, c->w + o_gu, true, d, c->dn, nullptr, false, d, T, d, 2 * f);
-    egemm(c, c->dgu, true, 2 * f, x.n2, true, d, g + o_gu, acc(o_gu), true, d, 2 * f, d, T);
-    ar(o_gu, static_cast<size_t>(2) * f * d);
+    egemm(c, c->dgu, true, 2 * f, x.n2, true, d, g + o_gu, acc(o_gu), true, d, 2 * f, d, T, nullptr, 0, wire(o_gu));
+    arw(o_gu, static_cast<size_t>(2) * f * d);
     // dh_mid = dh + rmsnorm_bwd(dn2)
     rmsnorm_bwd(c->dn, x.h_mid, c->w + p.ln2, x.rstd2, dh_cur, dh_alt, g + p.ln2, c->dw_partial, T, d, s); n += 2;
     std::swap(dh_cur, dh_alt);
     // h_mid = h_in + attn Wo^T
     egemm(c, dh_cur, false, d, c->w + o_o, true, qd, c->dattn, nullptr, false, qd, T, qd, d);
-    egemm(c, dh_cur, true, d, x.attn, true, qd, g + o_o, acc(o_o), true, qd, d, qd, T);
-    ar(o_o, static_cast<size_t>(d) * qd);
+    egemm(c, dh_cur, true, d, x.attn, true, qd, g + o_o, acc(o_o), true, qd, d, qd, T, nullptr, 0, wire(o_o));
+    arw(o_o, static_cast<size_t>(d) * qd);
     attention_bwd(x.qkv, qkvd, qd, qd + kd, x.attn, c->dattn, qd, x.lse, c->delta, c->dqkv, nseq, S, H,
                   Hkv, scale, s); n += 3;
     rope_apply(c->dqkv, qkvd, c->rope_tab, T, S, H + Hkv, dh, true, s); ++n;
     egemm(c, c->dqkv, false, qkvd, c->w + o_q, true, d, c->dn, nullptr, false, d, T, d, qkvd);
-    egemm(c, c->dqkv, true, qkvd, x.n1, true, d, g + o_q, acc(o_q), true, d, qkvd, d, T);
-    ar(o_q, static_cast<size_t>(qkvd) * d);
+    egemm(c, c->dqkv, true, qkvd, x.n1, true, d, g + o_q, acc(o_q), true, d, qkvd, d, T, nullptr, 0, wire(o_q));
+    arw(o_q, static_cast<size_t>(qkvd) * d);
     rmsnorm_bwd(c->dn, x.h_in, c->w + p.ln1, x.rstd1, dh_cur, dh_alt, g + p.ln1, c->dw_partial, T, d, s); n += 2;
     std::swap(dh_cur, dh_alt);
   }
@@ -829,6 +834,9 @@ void backward_micro_opt(b200w_ctx* c, const int32_t* ids, int nseq, bool first, 
   float* part = c->dw_partial;
   auto acc = [&](size_t off) -> const void* { return first ? nullptr : g + off; };
   auto ar = [&](size_t off, size_t count) { if (overlap_ar) allreduce_range(c, off, count); };
+  // matrices whose exchange follows their wgrad at once: the GEMM epilogue writes the bf16 wire copy itself
+  auto wire = [&](size_t off) -> void* { return overlap_ar ? c->gw + off : nullptr; };
+  auto arw = [&](size_t off, size_t count) { if (overlap_ar) allreduce_range(c, off, count, true); };
 
   egemm(c, c->logits, false, V, c->w + c->p_lm, true, d, c->dn, nullptr, false, d, T, d, V);
   egemm(c, c->logits, true, V, c->nf, true, d, g + c->p_embed, g + c->p_embed, true, d, V, d, T);
@@ -842,28 +850,28 @@ void backward_micro_opt(b200w_ctx* c, const int32_t* ids, int nseq, bool first, 
     // h_next = h_mid + act W2^T + b2
     colsum_add(dh_cur, g + p.b2, part, T, d, d, s); n += 2;
     egemm(c, dh_cur, false, d, c->w + p.wd, true, f, c->dact, nullptr, false, f, T, f, d);
-    egemm(c, dh_cur, true, d, x.act, true, f, g + p.wd, acc(p.wd), true, f, d, f, T);
-    ar(p.wd, static_cast<size_t>(d) * f);
+    egemm(c, dh_cur, true, d, x.act, true, f, g + p.wd, acc(p.wd), true, f, d, f, T, nullptr, 0, wire(p.wd));
+    arw(p.wd, static_cast<size_t>(d) * f);
     // act = relu(n2 W1^T + b1)
     relu_bwd(c->dact, x.act, c->dact, static_cast<size_t>(T) * f, s); ++n;
     colsum_add(c->dact, g + p.b1, part, T, f, f, s); n += 2;
     egemm(c, c->dact, false, f, c->w + p.wgu, true, d, c->dn, nullptr, false, d, T, d, f);
-    egemm(c, c->dact, true, f, x.n2, true, d, g + p.wgu, acc(p.wgu), true, d, f, d, T);
-    ar(p.wgu, static_cast<size_t>(f) * d);
+    egemm(c, c->dact, true, f, x.n2, true, d, g + p.wgu, acc(p.wgu), true, d, f, d, T, nullptr, 0, wire(p.wgu));
+    arw(p.wgu, static_cast<size_t>(f) * d);
     layernorm_bwd(c->dn, x.h_mid, c->w + p.ln2, x.mean2, x.rstd2, dh_cur, dh_alt, g + p.ln2, g + p.ln2b, part,
                   T, d, s); n += 3;
     std::swap(dh_cur, dh_alt);
     // h_mid = h_in + attn Wo^T + bo
     colsum_add(dh_cur, g + p.bo, part, T, d, d, s); n += 2;
     egemm(c, dh_cur, false, d, c->w + p.wo, true, qd, c->dattn, nullptr, false, qd, T, qd, d);
-    egemm(c, dh_cur, true, d, x.attn, true, qd, g + p.wo, acc(p.wo), true, qd, d, qd, T);
-    ar(p.wo, static_cast<size_t>(d) * qd);
+    egemm(c, dh_cur, true, d, x.attn, true, qd, g + p.wo, acc(p.wo), true, qd, d, qd, T, nullptr, 0, wire(p.wo));
+    arw(p.wo, static_cast<size_t>(d) * qd);
     attention_bwd(x.qkv, qkvd, qd, qd + kd, x.attn, c->dattn, qd, x.lse, c->delta, c->dqkv, nseq, S, H,
                   Hkv, scale, s); n += 3;
     colsum_add(c->dqkv, g + p.bqkv, part, T, qkvd, qkvd, s); n += 2;
     egemm(c, c->dqkv, false, qkvd, c->w + p.wqkv, true, d, c->dn, nullptr, false, d, T, d, qkvd);
-    egemm(c, c->dqkv, true, qkvd, x.n1, true, d, g + p.wqkv, acc(p.wqkv), true, d, qkvd, d, T);
-    ar(p.wqkv, static_cast<size_t>(qkvd) * d);
+    egemm(c, c->dqkv, true, qkvd, x.n1, true, d, g + p.wqkv, acc(p.wqkv), true, d, qkvd, d, T, nullptr, 0, wire(p.wqkv));
+    arw(p.wqkv, static_cast<size_t>(qkvd) * d);
     layernorm_bwd(c->dn, x.h_in, c->w + p.ln1, x.mean1, x.rstd1, dh_cur, dh_alt, g + p.ln1, g + p.ln1b, part,
                   T, d, s); n += 3;
     std::swap(dh_cur, dh_alt);
@@ -887,6 +895,9 @@ void backward_micro_falcon(b200w_ctx* c, const int32_t* ids, int nseq, bool firs
   float* part = c->dw_partial;
   auto acc = [&](size_t off) -> const void* { return first ? nullptr : g + off; };
   auto ar = [&](size_t off, size_t count) { if (overlap_ar) allreduce_range(c, off, count); };
+  // matrices whose exchange follows their wgrad at once: the GEMM epilogue writes the bf16 wire copy itself
+  auto wire = [&](size_t off) -> void* { return overlap_ar ? c->gw + off : nullptr; };
+  auto arw = [&](size_t off, size_t count) { if (overlap_ar) allreduce_range(c, off, count, true); };
 
   egemm(c, c->logits, false, V, c->w + c->p_lm, true, d, c->dn, nullptr, false, d, T, d, V);
   egemm(c, c->logits, true, V, c->nf, true, d, g + c->p_embed, g + c->p_embed, true, d, V, d, T);
@@ -899,22 +910,22 @@ void backward_micro_falcon(b200w_ctx* c, const int32_t* ids, int nseq, bool firs
     const auto& p = c->lp[l];
     // MLP branch: h' += gelu(ln W1^T) W2^T
     egemm(c, dh_cur, false, d, c->w + p.wd, true, f, c->dact, nullptr, false, f, T, f, d);
-    egemm(c, dh_cur, true, d, x.act, true, f, g + p.wd, acc(p.wd), true, f, d, f, T);
-    ar(p.wd, static_cast<size_t>(d) * f);
+    egemm(c, dh_cur, true, d, x.act, true, f, g + p.wd, acc(p.wd), true, f, d, f, T, nullptr, 0, wire(p.wd));
+    arw(p.wd, static_cast<size_t>(d) * f);
     gelu_bwd(c->dact, x.gu, c->dact, static_cast<size_t>(T) * f, s); ++n;
     egemm(c, c->dact, false, f, c->w + p.wgu, true, d, c->dn, nullptr, false, d, T, d, f);
-    egemm(c, c->dact, true, f, x.n1, true, d, g + p.wgu, acc(p.wgu), true, d, f, d, T);
-    ar(p.wgu, static_cast<size_t>(f) * d);
+    egemm(c, c->dact, true, f, x.n1, true, d, g + p.wgu, acc(p.wgu), true, d, f, d, T, nullptr, 0, wire(p.wgu));
+    arw(p.wgu, static_cast<size_t>(f) * d);
     // attention branch: h' += attn Wo^T
     egemm(c, dh_cur, false, d, c->w + p.wo, true, qd, c->dattn, nullptr, false, qd, T, qd, d);
-    egemm(c, dh_cur, true, d, x.attn, true, qd, g + p.wo, acc(p.wo), true, qd, d, qd, T);
-    ar(p.wo, static_cast<size_t>(d) * qd);
+    egemm(c, dh_cur, true, d, x.attn, true, qd, g + p.wo, acc(p.wo), true, qd, d, qd, T, nullptr, 0, wire(p.wo));
+    arw(p.wo, static_cast<size_t>(d) * qd);
     attention_bwd(x.qkv, qkvd, qd, qd + kd, x.attn, c->dattn, qd, x.lse, c->delta, c->dqkv, nseq, S, H,
                   Hkv, scale, s); n += 3;
     rope_apply(c->dqkv, qkvd, c->rope_tab, T, S, H + Hkv, a.head_dim, true, s, c->dhp); ++n;
     egemm(c, c->dqkv, false, qkvd, c->w + p.wqkv, true, d, c->dn, c->dn, false, d, T, d, qkvd);
-    egemm(c, c->dqkv, true, qkvd, x.n1, true, d, g + p.wqkv, acc(p.wqkv), true, d, qkvd, d, T);
-    ar(p.wqkv, static_cast<size_t>(qkvd) * d);
+    egemm(c, c->dqkv, true, qkvd, x.n1, true, d, g + p.wqkv, acc(p.wqkv), true, d, qkvd, d, T, nullptr, 0, wire(p.wqkv));
+    arw(p.wqkv, static_cast<size_t>(qkvd) * d);
     layernorm_bwd(c->dn, x.h_in, c->w + p.ln1, x.mean1, x.rstd1, dh_cur, dh_alt, g + p.ln1, g + p.ln1b, part,
                   T, d, s); n += 3;
     std::swap(dh_cur, dh_alt);

@@ -13,6 +13,8 @@
 // (= one 128-byte swizzle atom) blocks; warp 0 = TMA producer, warp 1 = tcgen05.mma issuer
 // (single elected thread), warp 2 = TMEM allocator, warps 4..7 = epilogue. Two TMEM accumulator
 // stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <mutex>
+
 #include "host_common.h"
 #include "ops.h"
 #include "ptx.cuh"
@@ -62,9 +64,13 @@ __device__ __forceinline__ void load_c_chunk(CChunk<OutT>& c, const OutT* crow, 
 
 // Epilogue extras of the bf16-output GEMM (nn.Linear(bias=True) + activation of the OPT family): v + bias[col]
 // (+ C) -> act. bias points at this chunk's 32 columns (16-byte aligned); act: 0 none, 1 ReLU.
+// d2 (fp32-output GEMMs only): a second, bf16-rounded copy of the output with the same row stride -- the
+// last accumulation micro-step's wgrad writes the gradient's NCCL wire copy from the registers that hold the
+// fp32 sum, instead of a separate cast pass re-reading 27 GB (engine.cu exchange_one).
 struct EpiExtra {
   const __nv_bfloat16* bias;
   int act;
+  __nv_bfloat16* d2;
 };
 __device__ __forceinline__ void apply_bias(float (&v)[32], const __nv_bfloat16* bias, int ncols_valid) {
   if (ncols_valid >= 32) {
@@ -89,7 +95,8 @@ __device__ __forceinline__ void apply_bias(float (&v)[32], const __nv_bfloat16* 
 
 __device__ __forceinline__ void store_chunk32(__nv_bfloat16* drow, const __nv_bfloat16* crow,
                                               const CChunk<__nv_bfloat16>& cc, const float (&v)[32],
-                                              int ncols_valid, bool has_c, int act = 0) {
+                                              int ncols_valid, bool has_c, int act = 0,
+                                              __nv_bfloat16* /*d2row: fp32 outputs only*/ = nullptr) {
   if (ncols_valid >= 32) {
     uint4 out[4];
     uint32_t* o = reinterpret_cast<uint32_t*>(out);
@@ -130,29 +137,42 @@ __device__ __forceinline__ void store_chunk32(__nv_bfloat16* drow, const __nv_bf
 }
 
 __device__ __forceinline__ void store_chunk32(float* drow, const float* crow, const CChunk<float>& cc,
-                                              const float (&v)[32], int ncols_valid, bool has_c, int /*act*/ = 0) {
+                                              const float (&v)[32], int ncols_valid, bool has_c, int /*act*/ = 0,
+                                              __nv_bfloat16* d2row = nullptr) {
   if (ncols_valid >= 32) {
     float4* d4 = reinterpret_cast<float4*>(drow);
+    uint4* w4 = reinterpret_cast<uint4*>(d2row);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    for (int i = 0; i < 4; ++i) {
+      float4 o0 = make_float4(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3]);
+      float4 o1 = make_float4(v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
       if (has_c) {
-        const float4 c = cc.v[i];
-        o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+        const float4 c0 = cc.v[2 * i], c1 = cc.v[2 * i + 1];
+        o0.x += c0.x; o0.y += c0.y; o0.z += c0.z; o0.w += c0.w;
+        o1.x += c1.x; o1.y += c1.y; o1.z += c1.z; o1.w += c1.w;
       }
-      d4[i] = o;
+      d4[2 * i] = o0;
+      d4[2 * i + 1] = o1;
+      if (d2row)
+        w4[i] = make_uint4(pack_bf16x2(o0.x, o0.y), pack_bf16x2(o0.z, o0.w), pack_bf16x2(o1.x, o1.y),
+                           pack_bf16x2(o1.z, o1.w));
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-      if (i < ncols_valid) drow[i] = v[i] + (has_c ? crow[i] : 0.f);
+      if (i < ncols_valid) {
+        const float o = v[i] + (has_c ? crow[i] : 0.f);
+        drow[i] = o;
+        if (d2row) d2row[i] = __float2bfloat16_rn(o);
+      }
   }
 }
 
 // TMEM accumulator rows -> global for one 128 x NCOLS tile half owned by this warp's lane quarter.
 template <int NCOLS, typename OutT>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_row_addr, OutT* drow, const OutT* crow,
-                                              bool row_ok, int ncols_total, EpiExtra ex = EpiExtra{nullptr, 0}) {
+                                              bool row_ok, int ncols_total,
+                                              EpiExtra ex = EpiExtra{nullptr, 0, nullptr}) {
   const bool has_c = crow != nullptr;
   CChunk<OutT> cc_next;
   if (has_c && row_ok) load_c_chunk<OutT>(cc_next, crow, ncols_total);
@@ -169,7 +189,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_row_addr, OutT* drow
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
       if (ex.bias) apply_bias(v, ex.bias + c * 32, ncols);
-      store_chunk32(drow + c * 32, has_c ? crow + c * 32 : nullptr, cc, v, ncols, has_c, ex.act);
+      store_chunk32(drow + c * 32, has_c ? crow + c * 32 : nullptr, cc, v, ncols, has_c, ex.act,
+                    ex.d2 ? ex.d2 + c * 32 : nullptr);
     }
   }
 }
@@ -298,7 +319,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       OutT* drow = D + static_cast<size_t>(row) * ldd + n0;
       const OutT* crow = C ? C + static_cast<size_t>(row) * ldd + n0 : nullptr;
       epilogue_tile<BLOCK_N, OutT>(tmem_addr(tmem_base, q * 32, acc * BLOCK_N), drow, crow, row_ok, N - n0,
-                                   EpiExtra{ex.bias ? ex.bias + n0 : nullptr, ex.act});
+                                   EpiExtra{ex.bias ? ex.bias + n0 : nullptr, ex.act,
+                                            ex.d2 ? ex.d2 + static_cast<size_t>(row) * ldd + n0 : nullptr});
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -450,7 +472,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       OutT* drow = D + static_cast<size_t>(row) * ldd + n0;
       const OutT* crow = C ? C + static_cast<size_t>(row) * ldd + n0 : nullptr;
       epilogue_tile<PAIR_N, OutT>(tmem_addr(tmem_base, q * 32, acc * PAIR_N), drow, crow, row_ok, N - n0,
-                                  EpiExtra{ex.bias ? ex.bias + n0 : nullptr, ex.act});
+                                  EpiExtra{ex.bias ? ex.bias + n0 : nullptr, ex.act,
+                                           ex.d2 ? ex.d2 + static_cast<size_t>(row) * ldd + n0 : nullptr});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA thread waits on it
@@ -741,6 +764,35 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   }
 }
 
+// How many clusters of `splits` decode-GEMM CTAs the device holds at once (per device, cached).
+template <int MPAD>
+int max_active_decode_clusters(int splits) {
+  using cfg = DecodeCfg<MPAD>;
+  static std::mutex mu;
+  static int cache[64][9];   // [device][splits], 0 = not asked yet
+  int dev = 0;
+  B200W_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  int& slot = cache[dev & 63][splits];
+  if (slot == 0) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(1, splits);
+    lc.blockDim = dim3(GEMM_THREADS);
+    lc.dynamicSmemBytes = cfg::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = static_cast<unsigned>(splits);
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    int n = 0;
+    B200W_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_decode_kernel<MPAD>, &lc));
+    slot = n > 0 ? n : -1;
+  }
+  return slot;
+}
+
 template <int MPAD>
 void launch_decode(const void* X, int ldx, const void* W, int ldw, const void* w_tiled, const DecodeEpi& epi,
                    bool allow_split, int M, int N, int K, cudaStream_t stream) {
@@ -755,13 +807,28 @@ void launch_decode(const void* X, int ldx, const void* W, int ldw, const void* w
   const int n_tiles = (N + BLOCK_M - 1) / BLOCK_M;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
   // split K until two CTAs per SM are in flight, keeping at least 8 K-blocks per split; the splits of a tile
-  // are one cluster (portable size limit 8)
+  // are one cluster (portable size limit 8). A cluster lives inside one GPC (16-20 SMs): 8-CTA clusters at 2
+  // CTAs per SM do not tile every GPC, and when the clusters of a launch exceed what the chip holds at once the
+  // stragglers run as a second wave on a nearly idle machine (ncu, profiles/r02_ncu_decode_tiled.txt: the
+  // 36 x 8 launch of Falcon's [dense | 4h_to_h] took 55.5 us against 43 us for the same bytes unsplit). So
+  // the split is the LARGEST one whose clusters are all co-resident (cudaOccupancyMaxActiveClusters).
   int splits = 1;
   if (allow_split) {
-    splits = 2 * sm_count() / n_tiles;
-    if (splits > num_kb / 8) splits = num_kb / 8;
-    if (splits > 8) splits = 8;
-    if (splits < 1) splits = 1;
+    int want = 2 * sm_count() / n_tiles;
+    if (want > num_kb / 8) want = num_kb / 8;
+    if (want > 8) want = 8;
+    if (want < 1) want = 1;
+    splits = want;                                           // nothing fits in one wave: keep the widest
+    static const bool fit = [] { const char* v = getenv("B200W_DECODE_SPLIT_FIT"); return !(v && v[0] == '0'); }();
+    for (int sp = want; fit && sp >= 2; --sp) {
+      const int per_sp = (num_kb + sp - 1) / sp;
+      if ((num_kb + per_sp - 1) / per_sp != sp) continue;    // this split count collapses to a smaller one
+      if (max_active_decode_clusters<MPAD>(sp) >= n_tiles) { splits = sp; break; }
+    }
+    static const bool dbg = getenv("B200W_DEBUG_SPLITS") != nullptr;
+    if (dbg)
+      fprintf(stderr, "b200w: decode GEMM N=%d K=%d: %d tiles x %d splits (wanted %d; %d clusters of that size fit)\n", N, K,
+              n_tiles, splits, want, splits > 1 ? max_active_decode_clusters<MPAD>(splits) : 0);
   }
   const int per = (num_kb + splits - 1) / splits;
   splits = (num_kb + per - 1) / per;
@@ -858,10 +925,12 @@ void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int 
 // nn.Linear(bias=True) (+ residual) (+ ReLU) in the epilogue. bf16 output only.
 void gemm_bf16_ex(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int ldb, void* D,
                   const void* C, bool out_fp32, int ldd, int M, int N, int K, int block_n, const void* bias,
-                  int act, cudaStream_t stream) {
+                  int act, cudaStream_t stream, void* d2_bf16) {
   B200W_CHECK(!(out_fp32 && (bias || act)), "bias / activation epilogue is built for bf16 outputs");
   B200W_CHECK((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "bias must be 16-byte aligned");
-  const EpiExtra ex{static_cast<const __nv_bfloat16*>(bias), act};
+  B200W_CHECK(!d2_bf16 || (out_fp32 && ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(d2_bf16) & 15) == 0),
+              "the bf16 copy exists for fp32 outputs with 16-byte aligned bf16 rows");
+  const EpiExtra ex{static_cast<const __nv_bfloat16*>(bias), act, static_cast<__nv_bfloat16*>(d2_bf16)};
   B200W_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
   B200W_CHECK(lda % 8 == 0 && ldb % 8 == 0, "TMA needs 16-byte aligned row strides");
   B200W_CHECK(ldd % (out_fp32 ? 4 : 8) == 0, "output rows must be 16-byte aligned");

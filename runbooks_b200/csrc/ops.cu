@@ -166,18 +166,41 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
     for (int j = 0; j < 8; ++j) dwp[p][j] = 0.f;
   }
   const float inv_d = 1.f / static_cast<float>(d);
+  // Software pipeline: the raw x / dy vectors of the NEXT row and the residual gradient of THIS row are
+  // requested before the block-wide reduction, so that three row streams are in flight across its two
+  // barriers (round 2 timeline: 0.48 of HBM peak with one row per block in flight). Same arithmetic, same
+  // order: results are bit-identical to the unpipelined kernel.
+  auto unpack8 = [](const uint4& u, float (&f)[8]) {
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = e.x; f[7] = e.y;
+  };
+  uint4 nx[P], ndy[P];
+  auto fetch = [&](int row) {
+    const size_t off = static_cast<size_t>(row) * d;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const int c = (p * NORM_THREADS + threadIdx.x) * 8;
+      if (c < d) {
+        nx[p] = *reinterpret_cast<const uint4*>(x + off + c);
+        ndy[p] = *reinterpret_cast<const uint4*>(dy + off + c);
+      }
+    }
+  };
+  if (static_cast<int>(blockIdx.x) < T) fetch(blockIdx.x);
   for (int row = blockIdx.x; row < T; row += gridDim.x) {
     const size_t off = static_cast<size_t>(row) * d;
     const float rs = rstd[row];
     float xh[P][8], g[P][8];
+    uint4 res[P];
     float dot = 0.f;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
       const int c = (p * NORM_THREADS + threadIdx.x) * 8;
       if (c < d) {
         float dyv[8];
-        load8(x + off + c, xh[p]);
-        load8(dy + off + c, dyv);
+        unpack8(nx[p], xh[p]);
+        unpack8(ndy[p], dyv);
+        if (dresid) res[p] = *reinterpret_cast<const uint4*>(dresid + off + c);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[p][j] *= rs;
@@ -187,13 +210,14 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
         }
       }
     }
+    if (row + static_cast<int>(gridDim.x) < T) fetch(row + gridDim.x);
     dot = block_sum(dot, red) * inv_d;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
       const int c = (p * NORM_THREADS + threadIdx.x) * 8;
       if (c < d) {
         float o[8];
-        if (dresid) load8(dresid + off + c, o);
+        if (dresid) unpack8(res[p], o);
         else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = 0.f;

@@ -14,9 +14,10 @@ void gemm_bf16(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int 
                cudaStream_t s);
 // D = act(A B^T + bias (+ C)): bias [N] bf16 (16-byte aligned) broadcast over the rows, act 0 none / 1 ReLU,
 // applied in the epilogue in fp32 before the single rounding to bf16 (OPT's biased projections).
+// d2_bf16 (fp32 outputs only): also write the output rounded to bf16 there, same row stride.
 void gemm_bf16_ex(const void* A, bool a_mn, int lda, const void* B, bool b_mn, int ldb, void* D,
                   const void* C, bool out_fp32, int ldd, int M, int N, int K, int block_n, const void* bias,
-                  int act, cudaStream_t s);
+                  int act, cudaStream_t s, void* d2_bf16 = nullptr);
 
 // out[M, N] = X[M, K] W[N, K]^T (+ C) for a decode batch (M <= 128): swap-AB + split-K streaming
 // kernel. ws / counters: zeroed scratch (M*N floats, ceil(N/128) unsigned), left zeroed; nullable.

@@ -22,7 +22,7 @@ def _gpus():
     return torch.cuda.device_count()
 
 
-def _rank_main(rank, world, uid, q, mode, steps):
+def _rank_main(rank, world, uid, q, mode, steps, comm1=False):
     try:
         shard = mode == "shard"
         if mode and not shard:
@@ -40,12 +40,13 @@ def _rank_main(rank, world, uid, q, mode, steps):
         oa = O.Arch(*v, rms_norm_eps=eps, rope_theta=theta)
         params = O.seeded_params(oa, int(fx["batch"][1]))
         e = Engine(rank)
-        if world > 1 and shard:
+        want_comm = world > 1 or comm1     # comm1: a ONE-rank communicator (the exchange path on a 1-GPU box)
+        if want_comm and shard:
             e.comm_init(rank, world, uid)          # sharded state: the communicator comes first
         e.init_model(LlamaArch(*v, rms_norm_eps=eps, rope_theta=theta), micro_batch=1, training=True,
                      shard_state=shard)
         e.load_state_dict(params)
-        if world > 1 and not shard:
+        if want_comm and not shard:
             e.comm_init(rank, world, uid)
         out = []
         for ids, labels, lr in ((fx["ids"], fx["labels"], 5e-5), (fx["ids2"], fx["labels2"], 2.5e-5))[:steps]:
@@ -64,17 +65,17 @@ def _rank_main(rank, world, uid, q, mode, steps):
         os._exit(1)
 
 
-def _run(world, mode=None, steps=2):
+def _run(world, mode=None, steps=2, comm1=False):
     import multiprocessing as mp
     from runbooks_b200.engine import Engine
     uid = b""
-    if world > 1:
+    if world > 1 or comm1:
         e = Engine(0)
         uid = e.comm_unique_id()
         e.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_rank_main, args=(r, world, uid, q, mode, steps)) for r in range(world)]
+    procs = [ctx.Process(target=_rank_main, args=(r, world, uid, q, mode, steps, comm1)) for r in range(world)]
     for p in procs:
         p.start()
     res = {}
@@ -101,6 +102,18 @@ def test_two_ranks_are_bit_identical_and_match_one_gpu():
     worst = max(float(np.linalg.norm(sd0[n] - sd_one[n]) / np.linalg.norm(sd_one[n])) for n in sd0)
     print(f"1-GPU vs 2-GPU updated weights: worst relative difference {worst:.3e}")
     assert worst < 1e-3
+
+
+def test_one_rank_communicator_overlap_equals_end_bit_for_bit():
+    """Runs on a 1-GPU box: a one-rank NCCL communicator drives the whole exchange path. In overlap mode the last
+    micro-step's wgrad GEMMs write the bf16 wire copy from their epilogue (gemm.cu EpiExtra::d2) and no cast
+    pass runs for those ranges; in `end` mode a cast kernel rounds the fp32 sum afterwards. Same rounding of the
+    same fp32 value: the updated weights must agree bit for bit (2 accumulation micro-steps per step)."""
+    a = _run(1, "overlap", steps=2, comm1=True)
+    b = _run(1, "end", steps=2, comm1=True)
+    assert a[0][0] == b[0][0]
+    for n in a[0][1]:
+        assert np.array_equal(a[0][1][n], b[0][1][n]), n
 
 
 @pytest.mark.skipif(_gpus() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")

@@ -395,7 +395,15 @@ def run_ours(args):
     e.profile_gemm(False)
     barrier()
 
+    per_rank = None
     if dist:
+        # every rank's own GEMM rate in the bracketed steps: the ranks move in lock-step (each all-reduce waits
+        # for the slowest), so the spread of these rates is what a data-parallel step loses to the slowest GPU
+        mine = torch.tensor([gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0, ms], dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = dict(gemm_tflops=[round(float(x[0]), 1) for x in allr],
+                        resident_ms_per_step=[round(float(x[1]) / args.steps, 2) for x in allr])
         t = torch.tensor([ms, ms_e2e], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
@@ -432,6 +440,8 @@ def run_ours(args):
         clocks=clocks, loss=round(float(loss), 4), grad_norm=round(float(gn), 4),
         device_gb=round(e.device_bytes() / 1e9, 1),
     )
+    if per_rank:
+        line["per_rank"] = per_rank
     e.close()
     if decode_obj is not None:
         line["decode"] = decode_obj

@@ -788,6 +788,17 @@ int max_active_decode_clusters(int splits) {
     lc.numAttrs = 1;
     int n = 0;
     B200W_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_decode_kernel<MPAD>, &lc));
+    // The occupancy queries answer for ONE CTA of this kernel per SM (measured on B200: 74 / 45 / 33 / 26 / 22 /
+    // 15 / 15 clusters of 2..8 CTAs, i.e. 148 CTAs at size 2; cudaOccupancyMaxActiveBlocksPerMultiprocessor = 1),
+    // although two 101 KB CTAs fit the 228 KB of an SM and ncu reports two resident
+    // (launch__occupancy_limit_shared_mem = 2, profiles/r02_ncu_decode.txt). Same-box sweeps agree with TWICE the
+    // figure: 36 clusters of 4, 5 or 6 CTAs run as one wave (3.21-3.50 ms per decode step on two boxes), 36
+    // clusters of 7 or 8 do not (3.55-3.78 ms) -- profiles/r02_decode_split_sweep.txt.
+    int smem_sm = 0, dev2 = 0;
+    B200W_CUDA(cudaGetDevice(&dev2));
+    B200W_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev2));
+    const int fit = smem_sm / (cfg::SMEM_BYTES + 1024);   // 1 KB per CTA is reserved by the system
+    if (splits * n <= sm_count() && fit >= 2) n *= 2;
     slot = n > 0 ? n : -1;
   }
   return slot;
@@ -803,6 +814,9 @@ void launch_decode(const void* X, int ldx, const void* W, int ldw, const void* w
   static PerDeviceOnce once;
   once.run([&] {
     B200W_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    // two CTAs per SM is the design (the next launch's CTAs prefetch weights while this one drains): ask for
+    // the whole shared-memory carve-out instead of leaving the choice to the driver
+    B200W_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   });
   const int n_tiles = (N + BLOCK_M - 1) / BLOCK_M;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
@@ -825,10 +839,20 @@ void launch_decode(const void* X, int ldx, const void* W, int ldw, const void* w
       if ((num_kb + per_sp - 1) / per_sp != sp) continue;    // this split count collapses to a smaller one
       if (max_active_decode_clusters<MPAD>(sp) >= n_tiles) { splits = sp; break; }
     }
+    static const int forced = [] { const char* v = getenv("B200W_DECODE_SPLITS"); return v ? atoi(v) : 0; }();
+    if (forced >= 1 && forced <= 8 && want > 1) splits = forced;   // development: same-box sweeps
     static const bool dbg = getenv("B200W_DEBUG_SPLITS") != nullptr;
-    if (dbg)
-      fprintf(stderr, "b200w: decode GEMM N=%d K=%d: %d tiles x %d splits (wanted %d; %d clusters of that size fit)\n", N, K,
-              n_tiles, splits, want, splits > 1 ? max_active_decode_clusters<MPAD>(splits) : 0);
+    if (dbg) {
+      fprintf(stderr, "b200w: decode GEMM N=%d K=%d: %d tiles x %d splits (wanted %d); co-resident clusters by size:", N, K,
+              n_tiles, splits, want);
+      for (int sp = 2; sp <= 8; ++sp) fprintf(stderr, " %d:%d", sp, max_active_decode_clusters<MPAD>(sp));
+      int per_sm = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemm_decode_kernel<MPAD>, GEMM_THREADS, cfg::SMEM_BYTES);
+      cudaFuncAttributes fa{};
+      cudaFuncGetAttributes(&fa, gemm_decode_kernel<MPAD>);
+      fprintf(stderr, "; CTAs per SM %d (dynamic smem %d B, static %zu B, regs %d)\n", per_sm, cfg::SMEM_BYTES,
+              fa.sharedSizeBytes, fa.numRegs);
+    }
   }
   const int per = (num_kb + splits - 1) / splits;
   splits = (num_kb + per - 1) / per;

@@ -1050,9 +1050,16 @@ void fwd_bwd_device(b200w_ctx* c, const int32_t* ids_dev, const int32_t* labels_
   for (int mi = 0; mi < n_micro; ++mi) {
     const int32_t* mids = ids_dev + static_cast<size_t>(mi) * mb * S;
     const int32_t* mlab = labels_dev + static_cast<size_t>(mi) * mb * S;
-    forward_micro(c, mids, mb);
-    loss_micro(c, mlab, mb);
+    {
+      NvtxRange r("b200w forward");
+      forward_micro(c, mids, mb);
+    }
+    {
+      NvtxRange r("b200w loss");
+      loss_micro(c, mlab, mb);
+    }
     const bool ar = allow_overlap && c->comm && mi == n_micro - 1;
+    NvtxRange r(ar ? "b200w backward + gradient exchange" : "b200w backward");
     backward_micro(c, mids, mb, mi == 0, ar);
   }
   if (c->comm) {
@@ -1079,6 +1086,7 @@ void fwd_bwd_all(b200w_ctx* c, const int32_t* ids, const int32_t* labels, int n_
 // all-reduce is complete on c->stream; global-norm clip + AdamW over the flat parameter space.
 // Gradient source: the fp32 accumulation buffer, or with a communicator the reduced bf16 wire copy.
 void optimizer_step(b200w_ctx* c, float lr) {
+  NvtxRange nvtx_range("b200w clip + AdamW");
   cudaStream_t s = c->stream;
   const bool wire = c->comm != nullptr;
   B200W_CUDA(cudaMemsetAsync(c->sumsq, 0, sizeof(double), s));

@@ -9,6 +9,8 @@
 #include <string>
 #include <utility>
 
+#include <nvtx3/nvToolsExt.h>
+
 namespace b200w {
 
 struct Error : std::runtime_error {
@@ -91,6 +93,15 @@ template <typename... KArgs, typename... Args>
 void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   launch_pdl_cluster(kern, grid, block, smem, s, 1, std::forward<Args>(args)...);
 }
+
+// NVTX range for the phases of a step (header-only NVTX v3: a no-op costing one predictable branch unless a tool
+// such as nsys / ncu --nvtx is attached). SURVEY.md 5, tracing row.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // gemm_bf16 leaves this many SMs free (grid = SMs - reserve): set around the backward that runs
 // concurrently with the NCCL gradient all-reduce, so that NCCL's CTAs find SMs without waiting for a

@@ -1202,6 +1202,7 @@ int b200w_infer_init_random(b200w_ctx* ctx, uint64_t seed, float std) {
 int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* positions,
                      const int32_t* slots, int n, int32_t* next_tokens, float* logits_out) {
   return iguard(ctx, [&] {
+    NvtxRange nvtx_range("b200w decode step");
     Infer* m = model(ctx);
     const auto& a = m->a;
     B200W_CHECK(tokens && positions && slots && n >= 1 && n <= m->max_batch, "bad batch");
@@ -1268,6 +1269,7 @@ int b200w_infer_step(b200w_ctx* ctx, const int32_t* tokens, const int32_t* posit
 int b200w_infer_prefill(b200w_ctx* ctx, const int32_t* tokens, const int32_t* lengths, const int32_t* slots,
                         int n_seqs, int padded_len, int32_t* next_tokens, float* logits_out) {
   return iguard(ctx, [&] {
+    NvtxRange nvtx_range("b200w prefill");
     Infer* m = model(ctx);
     const auto& a = m->a;
     B200W_CHECK(tokens && lengths && slots && n_seqs >= 1 && n_seqs <= m->max_batch, "bad prefill batch");

@@ -43,4 +43,40 @@ call(e, "b200w_op_attention_bwd", qkv, ld, H * dh, (H + Hkv) * dh, o, do, H * dh
 torch.cuda.synchronize()
 assert torch.isfinite(dqkv.float()).all() and torch.isfinite(o.float()).all()
 print("attention ok", flush=True)
+# round-2 additions: GeLU, the software-pipelined rmsnorm_bwd, a whole tiny Falcon fine-tune step (multi-query
+# attention backward, padded heads, RoPE with a head stride) and the Server path (prefill + cluster split-K decode)
+n = 64 * 1024
+x = torch.randn(n, generator=g).bfloat16().cuda()
+y = torch.empty_like(x)
+call(e, "b200w_op_gelu_fwd", x, y, n)
+call(e, "b200w_op_gelu_bwd", y, x, y, n)
+T, d = 300, 4096
+xx = torch.randn(T, d, generator=g).bfloat16().cuda()
+dy = torch.randn(T, d, generator=g).bfloat16().cuda()
+w = torch.randn(d, generator=g).bfloat16().cuda()
+rstd = torch.empty(T, device="cuda", dtype=torch.float32)
+yy = torch.empty_like(xx)
+dw = torch.zeros(d, device="cuda", dtype=torch.float32)
+call(e, "b200w_op_rmsnorm_fwd", xx, w, yy, rstd, T, d, 1e-5)
+call(e, "b200w_op_rmsnorm_bwd", dy, xx, w, rstd, xx, yy, dw, T, d)
+print("gelu / rmsnorm_bwd ok", flush=True)
 e.close()
+
+import numpy as np  # noqa: E402
+from runbooks_b200.engine import FalconArch  # noqa: E402
+from runbooks_b200.infer import Generator, InferEngine, ServeArch  # noqa: E402
+
+e = Engine(0)
+e.init_model(FalconArch(512, 256, 1024, 2, 4, max_seq_len=128), micro_batch=1, training=True)
+e.init_random(0, 0.05)
+ids = np.random.default_rng(0).integers(0, 512, size=(2, 128))
+loss, gn = e.train_step(ids, ids, lr=1e-4)
+assert np.isfinite(loss) and np.isfinite(gn)
+print(f"falcon train step ok: loss {loss:.4f}", flush=True)
+e.close()
+ie = InferEngine(0)
+ie.init_infer(ServeArch("falcon", 512, 256, 1024, 2, 4, 1, 64, 256, 1e-5, 10000.0, True), max_batch=4)
+ie.infer_init_random(0, 0.05)
+out = Generator(ie).generate([[1, 2, 3, 4, 5, 6, 7], [9, 8, 7]], 4)
+print("falcon serve ok:", out, flush=True)
+ie.close()

@@ -1,4 +1,5 @@
-"""One FULL fine-tune step (Llama-2-7B, 8 micro-steps of 4096 tokens, clip, AdamW) for an ncu launch list:
+"""One FULL fine-tune step (Llama-2-7B, per-device batch 8 x 4096 tokens as MICRO_BATCH-sequence micro-steps --
+default 2, what bench.py runs --, clip, AdamW) for an ncu launch list:
 
     ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
         --log-file gpurun_out/r2_step_launches.csv python tools/step_timeline.py
@@ -19,7 +20,8 @@ layers = int(os.environ.get("LAYERS", "32"))
 arch = LlamaArch.llama2_7b(4096)
 arch.num_layers = layers
 e = Engine(0)
-e.init_model(arch, micro_batch=1, training=True)
+micro = int(os.environ.get("MICRO_BATCH", "2"))
+e.init_model(arch, micro_batch=micro, training=True)
 e.init_random(0, 0.02)
 S, nseq = 4096, 8
 g = torch.Generator().manual_seed(1)

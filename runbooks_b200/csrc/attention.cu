@@ -45,10 +45,16 @@ __device__ __forceinline__ void require_1024_aligned(const void* p) {
     __trap();
   }
 }
+// B200W_WHATIF_* macros build TIMING-ONLY variants (wrong numerics) for same-box what-if experiments
+// (tools/build_variant.sh, tools/ab_variants.sh); none is defined in the product build.
 __device__ __forceinline__ float ex2(float x) {  // one MUFU.EX2
+#ifdef B200W_WHATIF_NOEXP
+  return fmaf(x, 1e-3f, 1.f);   // what if the exponentials were free
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 __device__ __forceinline__ void compute_bar_sync() {  // the 256 compute threads only (forward)
   asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -216,7 +222,12 @@ __device__ __forceinline__ void tmem_row64_to_global(uint32_t taddr, bf16* dst, 
 // forward
 // ==========================================================================================
 constexpr int FWD_BQ = 128, FWD_BKV = 64;
-constexpr int FWD_SMEM = 2 * ATOM128 /*Q*/ + 2 * 2 * ATOM64 /*K x2*/ + 2 * 2 * ATOM64 /*V x2*/ +
+#ifdef B200W_WHATIF_1CTA
+constexpr int FWD_WHATIF_PAD = 100 * 1024;   // what if only one forward CTA were resident per SM
+#else
+constexpr int FWD_WHATIF_PAD = 0;
+#endif
+constexpr int FWD_SMEM = FWD_WHATIF_PAD + 2 * ATOM128 /*Q*/ + 2 * 2 * ATOM64 /*K x2*/ + 2 * 2 * ATOM64 /*V x2*/ +
                          ATOM128 /*P*/ + 256 /*barriers*/;
 constexpr int FWD_TMEM_COLS = 256;  // S[2]: [0,64) [64,128)   O: [128,256)
 
@@ -355,7 +366,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
       // in registers (round 1 indexed sr[hc] dynamically, which ptxas put in local memory: 44 B of spills)
       uint32_t mine[32], other[32];
       tmem_ld32(tmem_base + buf * 64 + lane_base + hc * 32, mine);
+#ifdef B200W_WHATIF_NOOTHER
+#pragma unroll
+      for (int c = 0; c < 32; ++c) other[c] = 0u;   // what if the row maximum needed only this thread's half
+#else
       tmem_ld32(tmem_base + buf * 64 + lane_base + (hc ^ 1) * 32, other);
+#endif
       tmem_ld_wait();
 
       const int col0 = j * FWD_BKV;
@@ -636,8 +652,14 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       tc_fence_after();
       uint32_t s_r[16], dp_r[16];
       tmem_ld16(tmem_base + tb * 64 + lane_base + hc * 16, s_r);
+#ifdef B200W_WHATIF_NODP
+      tmem_ld_wait();   // what if dP^T did not have to be read from TMEM
+#pragma unroll
+      for (int c = 0; c < 16; ++c) dp_r[c] = s_r[c];
+#else
       tmem_ld16(tmem_base + 128 + tb * 64 + lane_base + hc * 16, dp_r);
       tmem_ld_wait();
+#endif
       // staging buffer tb was last read by the dV/dK MMAs of block it-2
       if (it >= 2) mbar_wait(&bar_d[tb], ((it >> 1) - 1) & 1);
       const float4* st_lse = reinterpret_cast<const float4*>(sStat + tb * 128 + hc * 16);

@@ -152,3 +152,34 @@ def test_opt_head_padding_stays_zero():
     logits2, _, _ = e2.forward(fx["ids"], fx["labels"])
     assert np.array_equal(logits, logits2)
     e.close(); e2.close()
+
+
+def test_opt_125m_true_size_step_matches_oracle():
+    """facebook/opt-125m at its TRUE size (BASELINE.json configs[0]: V 50272, d 768, ffn 3072, 12 layers x 12 heads of
+    64, 2048 learned positions; 125 M parameters), one fine-tune step on 2 x 128 tokens against the fp32 oracle
+    (itself pinned to HF at toy size): loss, grad-norm, logits, and the updated weights of one tensor per kind."""
+    from runbooks_b200.engine import OptArch
+    oa = OO.OPT_125M
+    params = OO.seeded_params(oa, 5, std=0.02)
+    rng = np.random.default_rng(6)
+    ids = rng.integers(0, oa.vocab_size, size=(2, 128)).astype(np.int64)
+    labels = ids.copy()
+    labels[0, :5] = -100
+    arch = OptArch(oa.vocab_size, oa.hidden_size, oa.ffn_dim, oa.num_layers, oa.num_heads,
+                   max_positions=oa.max_position_embeddings, max_seq_len=128, pad_token_id=oa.pad_token_id)
+    e = _engine(arch, params, 2)
+    assert sum(int(np.prod(s)) for _, s in e.params()) == 125_239_296      # HF: OPTForCausalLM(opt-125m).num_parameters()
+    logits, _, _ = e.forward(ids, labels)
+    ref = OO.train_step(params, ids, labels, oa, lr=5e-5)
+    err = rel_err(logits, ref["logits"].reshape(-1, oa.vocab_size))
+    loss, gn = e.train_step(ids, labels, lr=5e-5)
+    print(f"opt-125m true size: logits rel_err {err:.3e}, loss {loss:.5f} (oracle {ref['loss']:.5f}), "
+          f"gnorm {gn:.4f} (oracle {ref['gnorm']:.4f})")
+    assert err < 1.5e-2
+    assert abs(loss - ref["loss"]) < 1e-3 * ref["loss"] and abs(gn - ref["gnorm"]) < 5e-3 * ref["gnorm"]
+    for name in ("model.decoder.embed_tokens.weight", "model.decoder.embed_positions.weight",
+                 "model.decoder.layers.0.self_attn.q_proj.weight", "model.decoder.layers.11.fc2.weight",
+                 "model.decoder.layers.5.fc1.bias", "model.decoder.final_layer_norm.weight"):
+        w = e.read_state(name, params[name].shape, "master")
+        assert rel_err(w, ref["params"][name]) < 1e-3, name
+    e.close()

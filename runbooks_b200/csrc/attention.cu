@@ -635,9 +635,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       const size_t base = static_cast<size_t>(p.h) * Ttot + tok0 + (qb_base + p.qb) * BWD_BQ;
       return (tid < 64) ? lse2[base + tid] : delta[base + tid - 64];
     };
-    const float stat_mul = (tid < 64) ? 1.f : scale;  // delta is kept pre-multiplied by the scale
+    // (delta arrives pre-multiplied by the scale: attn_bwd_delta)
     IterPos cur{hk * G, 0};
-    if (tid < 128) sStat[tid] = fetch_stat(cur) * stat_mul;
+    if (tid < 128) sStat[tid] = fetch_stat(cur);
     bwd_compute_bar_sync();
 
     for (int it = 0; it < n_iter; ++it) {
@@ -691,7 +691,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_p[tb]);  // one arrival per compute warp
-      if (have_next) sStat[(tb ^ 1) * 128 + tid] = stat_next * stat_mul;
+      if (have_next) sStat[(tb ^ 1) * 128 + tid] = stat_next;
       // stats(it+1) visible; stats(it) no longer read. With one bar_p per stage the protocol no longer NEEDS
       // this block-wide barrier, and a variant with warp-private statistics rows and no barrier was built
       // and measured in round 2: 4 % SLOWER (303.9 vs 292.6 us, same-box ncu A/B,
@@ -869,7 +869,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __res
     }
     const size_t stat_idx = static_cast<size_t>(h) * (static_cast<size_t>(B) * S) + tok0 + row_seq;
     const float my_lse = lse2[stat_idx];
-    const float my_dl = delta[stat_idx] * scale;
+    const float my_dl = delta[stat_idx];   // pre-multiplied by the scale (attn_bwd_delta)
 
     for (int j = 0; j < njb; ++j) {
       const int tb = j & 1;
@@ -952,7 +952,7 @@ void attention_bwd(const void* qkv, int ld_qkv, int k_off, int v_off, const void
   B200W_CHECK(S % 128 == 0, "sequence length must be a multiple of 128");
   B200W_CHECK(H % Hkv == 0, "bad head configuration");
   const size_t T = static_cast<size_t>(B) * S;
-  attn_bwd_delta(out, dout, ld_out, delta, static_cast<int>(T), H, s);
+  attn_bwd_delta(out, dout, ld_out, delta, static_cast<int>(T), H, scale, s);
   CUtensorMap tm_qkv = make_tmap_bf16_2d(qkv, T, ld_qkv, ld_qkv, 64, 64);
   CUtensorMap tm_do = make_tmap_bf16_2d(dout, T, ld_out, ld_out, 64, 64);
   static PerDeviceOnce once;

@@ -521,7 +521,7 @@ __global__ void adamw_kernel(float* __restrict__ master, float* __restrict__ m,
 // attention backward helper: delta[h, t] = sum_c out[t, h*128+c] * dout[t, h*128+c]
 // ------------------------------------------------------------------------------------------
 __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout,
-                                  int ld, float* __restrict__ delta, int T, int H) {
+                                  int ld, float* __restrict__ delta, int T, int H, float scale) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= T * H) return;
@@ -533,7 +533,7 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
                b1 = unpack_bf16x2(b.y);
   float acc = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y;
   acc = warp_sum(acc);
-  if (lane == 0) delta[static_cast<size_t>(h) * T + t] = acc;
+  if (lane == 0) delta[static_cast<size_t>(h) * T + t] = acc * scale;
 }
 
 __global__ void cast_f32_bf16_2d_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
@@ -1005,11 +1005,11 @@ void colsum_add(const void* dy, float* db, float* part, int T, int N, int ld, cu
   B200W_CUDA(cudaGetLastError());
 }
 
-void attn_bwd_delta(const void* out, const void* dout, int ld, float* delta, int T, int H,
+void attn_bwd_delta(const void* out, const void* dout, int ld, float* delta, int T, int H, float scale,
                     cudaStream_t s) {
   const long long threads = static_cast<long long>(T) * H * 32;
   attn_delta_kernel<<<blocks_for(threads, 256), 256, 0, s>>>(
-      static_cast<const bf16*>(out), static_cast<const bf16*>(dout), ld, delta, T, H);
+      static_cast<const bf16*>(out), static_cast<const bf16*>(dout), ld, delta, T, H, scale);
   B200W_CUDA(cudaGetLastError());
 }
 void cast_f32_to_bf16_2d(const float* src, void* dst, int ld_dst, int T, int ncols,

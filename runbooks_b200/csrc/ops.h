@@ -133,7 +133,10 @@ void gelu_bwd(const void* dy, const void* x, void* dx, size_t n, cudaStream_t s)
 int colsum_blocks(int T);
 void colsum_add(const void* dy, float* db, float* part, int T, int N, int ld, cudaStream_t s);
 
-void attn_bwd_delta(const void* out, const void* dout, int ld, float* delta, int T, int H,
+// delta[h, t] = scale * sum_c out[t, h, c] * dout[t, h, c] (fp32): the softmax-backward row term, pre-multiplied
+// by the score scale so that neither backward kernel multiplies it again (in the dK/dV kernel that multiply sat
+// right behind the global load of the next block's statistics: 15 % of its stall samples)
+void attn_bwd_delta(const void* out, const void* dout, int ld, float* delta, int T, int H, float scale,
                     cudaStream_t s);
 // dst[t, c] (bf16, row stride ld_dst) = src[t, c] (fp32, dense [T, ncols])
 void cast_f32_to_bf16_2d(const float* src, void* dst, int ld_dst, int T, int ncols, cudaStream_t s);

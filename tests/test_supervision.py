@@ -36,7 +36,20 @@ def _stuck_in_collective(rank, q):
 
 def _ignores_sigterm(rank, q):
     signal.signal(signal.SIGTERM, signal.SIG_IGN)   # blocked in a driver call
+    ready = os.environ.get("B200W_TEST_READY_FILE")
+    if ready:
+        open(ready, "w").close()                    # the handler is installed: the peer may die now
     time.sleep(600)
+
+
+def _dies_silently_once_the_peer_ignores_sigterm(rank, q):
+    # a spawned child needs a second or more to import its modules; a SIGTERM that arrives before the peer has
+    # installed SIG_IGN would kill it the ordinary way and the grace-period path would not be exercised
+    ready = os.environ["B200W_TEST_READY_FILE"]
+    t0 = time.time()
+    while not os.path.exists(ready) and time.time() - t0 < 60:
+        time.sleep(0.05)
+    os._exit(3)
 
 
 def _run(targets, grace=2.0):
@@ -65,9 +78,10 @@ def test_silent_death_is_detected_by_exit_code():
     assert code == 1 and secs < 5 and not any(p.is_alive() for p in procs)
 
 
-def test_rank_that_ignores_sigterm_is_killed_after_the_grace_period():
-    code, secs, procs = _run([_ignores_sigterm, _dies_silently], grace=1.0)
-    assert code == 1 and secs < 8 and not any(p.is_alive() for p in procs)
+def test_rank_that_ignores_sigterm_is_killed_after_the_grace_period(tmp_path, monkeypatch):
+    monkeypatch.setenv("B200W_TEST_READY_FILE", str(tmp_path / "ready"))
+    code, secs, procs = _run([_ignores_sigterm, _dies_silently_once_the_peer_ignores_sigterm], grace=1.0)
+    assert code == 1 and secs < 60 and not any(p.is_alive() for p in procs)
     assert procs[0].exitcode == -signal.SIGKILL
 
 

@@ -22,6 +22,30 @@
 namespace b200w {
 
 static int pick_n_fast(int M, int N, int K);
+static int pick_raster(int M, int N, int K, int tile_m, int tile_n);
+
+// Tile raster: `raster` = n_fast | (group << 1). Tiles run along the fast dimension (N when n_fast, else M), but
+// only `group` tiles wide; a band of `group` fast-dimension tiles is swept across the whole slow dimension
+// before the next band starts (group 0 = the whole extent). The band's operand panels (group x 256 x K x 2 bytes,
+// chosen <= 34 MB by pick_raster) are what every wave of tiles re-reads, and they stay in L2; the other operand
+// is streamed once per band.
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int raster, int& mi, int& ni) {
+  const int n_fast = raster & 1, group = raster >> 1;
+  const int fast_total = n_fast ? num_n : num_m, slow_total = n_fast ? num_m : num_n;
+  int fast, slow;
+  if (group <= 0 || group >= fast_total) {
+    fast = tile % fast_total;
+    slow = tile / fast_total;
+  } else {
+    const int per_band = group * slow_total;
+    const int band = tile / per_band, r = tile - band * per_band;
+    const int width = min(group, fast_total - band * group);   // the last band may be narrower
+    slow = r / width;
+    fast = band * group + (r - slow * width);
+  }
+  mi = n_fast ? slow : fast;
+  ni = n_fast ? fast : slow;
+}
 
 namespace {
 
@@ -244,8 +268,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         // raster order: the operand that does NOT fit in L2 is made the slow index (launch())
-        const int m0 = (n_fast ? tile / num_n : tile % num_m) * BLOCK_M;
-        const int n0 = (n_fast ? tile % num_n : tile / num_m) * BLOCK_N;
+        int mi, ni;
+        tile_coords(tile, num_m, num_n, n_fast, mi, ni);
+        const int m0 = mi * BLOCK_M, n0 = ni * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * cfg::STAGE_BYTES;
@@ -309,8 +334,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (n_fast ? tile / num_n : tile % num_m) * BLOCK_M;
-      const int n0 = (n_fast ? tile % num_n : tile / num_m) * BLOCK_N;
+      int mi, ni;
+      tile_coords(tile, num_m, num_n, n_fast, mi, ni);
+      const int m0 = mi * BLOCK_M, n0 = ni * BLOCK_N;
       mbar_wait(&tfull_bar[acc], acc_phase);
       __syncwarp();
       tc_fence_after();
@@ -400,8 +426,10 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (n_fast ? tile / num_n : tile % num_m) * 256 + rank * 128;  // my 128 rows of A
-        const int n0 = (n_fast ? tile % num_n : tile / num_m) * PAIR_N + rank * (PAIR_N / 2);  // my B half
+        int mi, ni;
+        tile_coords(tile, num_m, num_n, n_fast, mi, ni);
+        const int m0 = mi * 256 + rank * 128;                 // my 128 rows of A
+        const int n0 = ni * PAIR_N + rank * (PAIR_N / 2);     // my B half
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * PAIR_STAGE_BYTES;
@@ -462,8 +490,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m0 = (n_fast ? tile / num_n : tile % num_m) * 256 + rank * 128;
-      const int n0 = (n_fast ? tile % num_n : tile / num_m) * PAIR_N;
+      int mi, ni;
+      tile_coords(tile, num_m, num_n, n_fast, mi, ni);
+      const int m0 = mi * 256 + rank * 128, n0 = ni * PAIR_N;
       mbar_wait(&tfull_bar[acc], acc_phase);
       __syncwarp();
       tc_fence_after();
@@ -506,7 +535,7 @@ void launch_pair(const void* A, const void* B, OutT* D, const OutT* C, int M, in
   const int max_clusters = (sm_count() - gemm_sm_reserve()) / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
   kern<<<clusters * 2, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(tmA, tmB, D, C, M, N, K, ldd,
-                                                                pick_n_fast(M, N, K), ex);
+                                                                pick_raster(M, N, K, 256, PAIR_N), ex);
   B200W_CUDA(cudaGetLastError());
 }
 
@@ -538,7 +567,7 @@ void launch(const void* A, const void* B, OutT* D, const OutT* C, int M, int N, 
   const int sms = sm_count() - gemm_sm_reserve();
   const int grid = num_tiles < sms ? num_tiles : sms;
   kern<<<grid, GEMM_THREADS, cfg::SMEM_BYTES, stream>>>(tmA, tmB, D, C, M, N, K, ldd,
-                                                        pick_n_fast(M, N, K), ex);
+                                                        pick_raster(M, N, K, BLOCK_M, BLOCK_N), ex);
   B200W_CUDA(cudaGetLastError());
 }
 
@@ -903,6 +932,31 @@ static int pick_n_fast(int M, int N, int K) {
   if (a_bytes <= l2_budget) return 0;
   if (b_bytes <= l2_budget) return 1;
   return b_bytes < a_bytes ? 1 : 0;
+}
+
+// Raster for tile_coords. An operand that every wave of tiles re-reads stays in L2 only up to ~34 MB: B200's 126 MB
+// L2 is two partitions, and at micro-batch 2 the 67 MB operands of the Llama-2-7B GEMMs (M = 8192 x K = 4096 bf16)
+// were re-fetched wave after wave -- ncu --set full at M = 8192 before this: 2.76x / 2.06x the algorithmic DRAM bytes
+// for the gate|up forward / accumulating wgrad against 1.04x / 1.07x at M = 4096 (profiles/r02_ncu_gemm_mb2.json,
+// r02_ncu_gemm.json). Cost model: the fast-dimension operand is read once, the other once per band.
+static int pick_raster(int M, int N, int K, int tile_m, int tile_n) {
+  static const bool grouped = [] { const char* v = getenv("B200W_GEMM_RASTER_BANDS"); return !(v && v[0] == '0'); }();
+  static const double budget = [] { const char* v = getenv("B200W_GEMM_BAND_MB"); return (v ? atof(v) : 34.0) * 1e6; }();
+  const double a = 2.0 * M * K, b = 2.0 * N * K, resident = 40e6, max_panel = 8.5e6;
+  const double pa = 2.0 * tile_m * K, pb = 2.0 * tile_n * K;
+  auto bands = [&](double fast, double panel) -> double {
+    if (fast <= resident) return 1.0;
+    if (panel > max_panel) return -1.0;                       // one panel is most of the budget: banding cannot help
+    const double per_band = floor(budget / panel) * panel;
+    return ceil(fast / per_band);
+  };
+  const double ga = bands(a, pa), gb = bands(b, pb);
+  if (!grouped || (ga < 0 && gb < 0)) return pick_n_fast(M, N, K);
+  const double cost_m = ga < 0 ? 1e30 : a + b * ga, cost_n = gb < 0 ? 1e30 : b + a * gb;
+  const int n_fast = cost_n < cost_m ? 1 : 0;
+  const double fast = n_fast ? b : a, panel = n_fast ? pb : pa;
+  const int group = fast <= resident ? 0 : static_cast<int>(floor(budget / panel));
+  return n_fast | (group << 1);
 }
 
 // out[M, N] = act(X[M, K] W[N, K]^T (+ bias) (+ C)), M <= 128: the decode-time projection. ws: zeroed

@@ -165,3 +165,28 @@ def test_gemm_bias_relu_epilogue(engine, M, N, K, bn, act, resid):
     assert err < 3e-3
     if act:
         assert float(D.float().min()) >= 0.0
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,f32", [
+    (8192, 4352, 4096, 0, 0, 0),    # forward at micro-batch 2: A = 67 MB -> M-fastest in bands of 16 tiles (2 bands)
+    (5120, 4352, 8192, 1, 1, 1),    # accumulating wgrad: B = 71 MB -> N-fastest in bands of 8 + 8 + 1 tiles
+])
+def test_gemm_banded_raster_at_shapes_that_exceed_l2(engine, M, N, K, a_mn, b_mn, f32):
+    """Operands larger than what stays in L2 switch the tile raster to bands (gemm.cu pick_raster / tile_coords);
+    every output tile must still be written exactly once -- NaN-filled output, fp32 reference computed on the GPU by
+    torch from the same bf16 operands. The fp32 case also accumulates in place a second time."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+    ref = A.float() @ B.float().T
+    Ad = A.T.contiguous() if a_mn else A
+    Bd = B.T.contiguous() if b_mn else B
+    D = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+    call(engine, "b200w_op_gemm", Ad, a_mn, Ad.shape[1], Bd, b_mn, Bd.shape[1], D, None, f32, N, M, N, K, 0)
+    assert bool(torch.isfinite(D.float()).all())
+    err = rel_err(D.float(), ref)
+    print(f"banded raster M{M} N{N} K{K}: rel_err {err:.3e}")
+    assert err < (2e-5 if f32 else 3e-3)
+    if f32:
+        call(engine, "b200w_op_gemm", Ad, a_mn, Ad.shape[1], Bd, b_mn, Bd.shape[1], D, D, 1, N, M, N, K, 0)
+        assert rel_err(D, 2 * ref) < 2e-5

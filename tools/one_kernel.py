@@ -15,7 +15,7 @@ from util import call  # noqa: E402
 which = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 e = Engine(0)
-T, d, f = 4096, 4096, 11008
+T, d, f = int(os.environ.get("TOKENS", "4096")), 4096, 11008   # TOKENS=8192: the micro-batch-2 launches
 if which.startswith("gemm"):
     M, N, K, a_mn, b_mn, f32 = {
         "gemm_fwd": (T, 2 * f, d, 0, 0, 0), "gemm_dgrad": (T, d, 2 * f, 0, 1, 0),

@@ -243,20 +243,23 @@ PER_DEVICE_BATCH = 8
 MICRO_BATCH = 2   # sequences per accumulation micro-step: T = 8192 rows per GEMM (see workload_config)
 SHARD_STATE = False
 def gemm_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of THIS
-    kernel family (profiles/r02_ncu_gemm.json, written by the round's profiling call from the .ncu-rep):
-    the forward gate|up GEMM, with the dgrad and accumulating-wgrad captures beside it."""
-    path = os.path.join(ROOT, "profiles", "r02_ncu_gemm.json")
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of THIS kernel
+    family at THIS micro-batch's shape (profiles/r02_ncu_gemm_mb2_banded.json for M = 8192 tokens, r02_ncu_gemm.json
+    for M = 4096; written from the .ncu-rep by tools/ncu_gemm_json.py): the forward gate|up GEMM, with the dgrad and
+    accumulating-wgrad captures beside it."""
+    name = "r02_ncu_gemm_mb2_banded.json" if MICRO_BATCH == 2 else "r02_ncu_gemm.json"
+    path = os.path.join(ROOT, "profiles", name)
     try:
-        d = json.load(open(path))["kernels"]
+        j = json.load(open(path))
+        d = j["kernels"]
         f = d["fwd_gateup"]
         return dict(bytes=f["dram_read_bytes"] + f["dram_write_bytes"],
-                    note=(f"dram__bytes_read+write of one forward gate|up GEMM launch (M4096 N22016 K4096) = "
+                    note=(f"dram__bytes_read+write of one forward gate|up GEMM launch (M{j.get('tokens', 4096)} N22016 K4096) = "
                           f"{f['traffic_over_algorithmic']}x its {f['algorithmic_bytes'] / 1e6:.0f} MB algorithmic; dgrad "
                           f"{d['dgrad_gateup']['traffic_over_algorithmic']}x, accumulating wgrad "
-                          f"{d['wgrad_gateup_acc']['traffic_over_algorithmic']}x (profiles/r02_ncu_gemm.json, ncu --set full)"))
+                          f"{d['wgrad_gateup_acc']['traffic_over_algorithmic']}x (profiles/{name}, ncu --set full)"))
     except Exception:  # noqa: BLE001
-        return dict(bytes=None, note="profiles/r02_ncu_gemm.json missing")
+        return dict(bytes=None, note=f"profiles/{name} missing")
 
 
 def workload_config(n_gpus: int):

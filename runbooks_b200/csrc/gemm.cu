@@ -951,6 +951,15 @@ static int pick_raster(int M, int N, int K, int tile_m, int tile_n) {
     return ceil(fast / per_band);
   };
   const double ga = bands(a, pa), gb = bands(b, pb);
+  static const bool square = [] { const char* v = getenv("B200W_GEMM_LONGK_SQUARE"); return !(v && v[0] == '0'); }();
+  if (grouped && square && ga < 0 && gb < 0) {
+    // long K: no band of panels can stay resident, but the ~74 tiles in flight march through K together and share
+    // the k-slices they are on, so a wave costs (rows + columns of tiles it spans) panels: make the wave square
+    // (8 x ~9 tiles) instead of a 16 x 4.6 strip -- 17 panels per wave instead of 20.6
+    const int n_fast = pick_n_fast(M, N, K);
+    const int fast_tiles = n_fast ? (N + tile_n - 1) / tile_n : (M + tile_m - 1) / tile_m;
+    return n_fast | ((fast_tiles >= 12 ? 8 : 0) << 1);
+  }
   if (!grouped || (ga < 0 && gb < 0)) return pick_n_fast(M, N, K);
   const double cost_m = ga < 0 ? 1e30 : a + b * ga, cost_n = gb < 0 ? 1e30 : b + a * gb;
   const int n_fast = cost_n < cost_m ? 1 : 0;

@@ -87,6 +87,10 @@ typedef struct b200w_ctx b200w_ctx;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
 B200W_API int b200w_abi_version(void);
+/* Test aid, needs no device: the tile raster gemm.cu chooses for an [M, N, K] GEMM with tile_m x tile_n output tiles
+ * (bit 0: N is the fast dimension; bits 1..: band width in tiles, 0 = whole extent) and, when coords != NULL, the
+ * (m, n) tile index of every tile in launch order ([tiles][2] int32). Returns -1 on bad arguments. */
+B200W_API int b200w_debug_gemm_raster(int M, int N, int K, int tile_m, int tile_n, int32_t* coords);
 B200W_API int b200w_create(int device, b200w_ctx** out);
 B200W_API void b200w_destroy(b200w_ctx* ctx);
 B200W_API const char* b200w_last_error(const b200w_ctx* ctx); /* ctx may be NULL: last create() error */

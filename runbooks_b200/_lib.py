@@ -50,6 +50,7 @@ class HParams(C.Structure):
 # name -> (restype, argtypes); mirrors include/b200w.h one to one (tests check the symbol list)
 PROTOTYPES = {
     "b200w_abi_version": (C.c_int, []),
+    "b200w_debug_gemm_raster": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "b200w_create": (C.c_int, [C.c_int, C.POINTER(c_ctx)]),
     "b200w_destroy": (None, [c_ctx]),
     "b200w_last_error": (C.c_char_p, [c_ctx]),

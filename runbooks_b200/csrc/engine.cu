@@ -1183,6 +1183,10 @@ void ctx_fill_const(b200w_ctx* c, void* w_bf16, size_t n, float value) {
 extern "C" {
 
 int b200w_abi_version(void) { return B200W_ABI_VERSION; }
+int b200w_debug_gemm_raster(int M, int N, int K, int tile_m, int tile_n, int32_t* coords) {
+  if (M <= 0 || N <= 0 || K <= 0 || tile_m <= 0 || tile_n <= 0) return -1;
+  return b200w::gemm_debug_raster(M, N, K, tile_m, tile_n, coords);
+}
 
 int b200w_create(int device, b200w_ctx** out) {
   if (!out) return B200W_ERR_INVALID;

@@ -29,7 +29,7 @@ static int pick_raster(int M, int N, int K, int tile_m, int tile_n);
 // before the next band starts (group 0 = the whole extent). The band's operand panels (group x 256 x K x 2 bytes,
 // chosen <= 34 MB by pick_raster) are what every wave of tiles re-reads, and they stay in L2; the other operand
 // is streamed once per band.
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int raster, int& mi, int& ni) {
+__host__ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int raster, int& mi, int& ni) {
   const int n_fast = raster & 1, group = raster >> 1;
   const int fast_total = n_fast ? num_n : num_m, slow_total = n_fast ? num_m : num_n;
   int fast, slow;
@@ -39,7 +39,8 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
   } else {
     const int per_band = group * slow_total;
     const int band = tile / per_band, r = tile - band * per_band;
-    const int width = min(group, fast_total - band * group);   // the last band may be narrower
+    const int rest = fast_total - band * group;
+    const int width = group < rest ? group : rest;            // the last band may be narrower
     slow = r / width;
     fast = band * group + (r - slow * width);
   }
@@ -1078,6 +1079,22 @@ void gemm_bf16_ex(const void* A, bool a_mn, int lda, const void* B, bool b_mn, i
                                          static_cast<const __nv_bfloat16*>(C), M, N, K, lda, ldb,
                                          ldd, ex, stream);
   }
+}
+
+// Host-side view of the tile raster for tests (no device needed): the raster word pick_raster chooses for a shape and,
+// optionally, the (m, n) tile index of every tile in launch order.
+int gemm_debug_raster(int M, int N, int K, int tile_m, int tile_n, int32_t* coords) {
+  const int raster = pick_raster(M, N, K, tile_m, tile_n);
+  if (coords) {
+    const int num_m = (M + tile_m - 1) / tile_m, num_n = (N + tile_n - 1) / tile_n;
+    for (int t = 0; t < num_m * num_n; ++t) {
+      int mi, ni;
+      tile_coords(t, num_m, num_n, raster, mi, ni);
+      coords[2 * t] = mi;
+      coords[2 * t + 1] = ni;
+    }
+  }
+  return raster;
 }
 
 }  // namespace b200w

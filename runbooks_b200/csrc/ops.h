@@ -19,6 +19,10 @@ void gemm_bf16_ex(const void* A, bool a_mn, int lda, const void* B, bool b_mn, i
                   const void* C, bool out_fp32, int ldd, int M, int N, int K, int block_n, const void* bias,
                   int act, cudaStream_t s, void* d2_bf16 = nullptr);
 
+// raster word (n_fast | band << 1) gemm_bf16 uses for a shape and tile size; coords (nullable): [tiles][2] = (m, n)
+// tile index of every tile in launch order. Host only.
+int gemm_debug_raster(int M, int N, int K, int tile_m, int tile_n, int32_t* coords);
+
 // out[M, N] = X[M, K] W[N, K]^T (+ C) for a decode batch (M <= 128): swap-AB + split-K streaming
 // kernel. ws / counters: zeroed scratch (M*N floats, ceil(N/128) unsigned), left zeroed; nullable.
 // act: 0 none, 1 exact GeLU applied to (acc + C).

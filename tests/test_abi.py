@@ -89,7 +89,10 @@ int main(void) {
   b200w_ctx* ctx = NULL;
   int st = b200w_create(0, &ctx);
   if (st != B200W_OK) { printf("create failed as documented: %d %s\n", st, b200w_last_error(NULL)); return 3; }
-  b200w_arch a = {32000, 4096, 11008, 32, 32, 32, 128, 4096, 1e-5f, 10000.0f};
+  b200w_arch a = {.vocab_size = 32000, .hidden_size = 4096, .intermediate_size = 11008, .num_layers = 32,
+                  .num_heads = 32, .num_kv_heads = 32, .head_dim = 128, .max_seq_len = 4096, .rms_norm_eps = 1e-5f,
+                  .rope_theta = 10000.0f, .family = B200W_FAMILY_LLAMA,
+                  .pad_token_id = 0 /* Llama-2-7b-hf config.json; -1 when the checkpoint has none */};
   st = b200w_model_init(ctx, &a, NULL, 1, 1);
   float loss = 0, gnorm = 0;
   int32_t ids[1] = {0};

@@ -106,7 +106,12 @@ B200W_API void b200w_default_hparams(b200w_hparams* hp);
  * bytes per parameter), the gradient exchange is a reduce-scatter, AdamW runs on the owned slices
  * and the bf16 compute copy is all-gathered -- the wire bytes of one all-reduce. Same results as
  * mode 1 (bit-identical at 2 ranks). b200w_read_state then serves kind 0 from the compute copy and
- * refuses kinds 1-3. */
+ * refuses kinds 1-3.
+ * Either training mode may be OR-ed with B200W_TRAIN_RECOMPUTE (Llama family): only every layer's INPUT is kept
+ * through the forward; the backward re-runs each layer's forward from it (gradient checkpointing, the other half
+ * of the config #5 memory plan: 34.5 GB -> 3.2 GB of saved activations for Llama-2-7B at 2 x 4096 tokens) for
+ * about a quarter more forward time. Same kernels on the same operands: results are bit-identical. */
+#define B200W_TRAIN_RECOMPUTE 4
 B200W_API int b200w_model_init(b200w_ctx* ctx, const b200w_arch* arch, const b200w_hparams* hp,
                      int micro_batch, int training);
 /* Parameter names follow the HF checkpoint keys ("model.embed_tokens.weight",

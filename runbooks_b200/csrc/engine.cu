@@ -221,6 +221,7 @@ struct b200w_ctx {
   struct Range { size_t off, cnt; bool decay; };
   std::vector<Range> ranges;
   bool shard = false;
+  bool recompute = false;   // keep only every layer's input; the backward re-runs the layer's forward (B200W_TRAIN_RECOMPUTE)
   float2* rope_tab = nullptr;
 
   struct LayerP { size_t ln1, ln1b, ln2, ln2b, wqkv, bqkv, wo, bo, wgu, b1, wd, b2; };
@@ -489,7 +490,8 @@ void alloc_activations(b200w_ctx* c) {
                H = a.num_heads;
   const int L = a.num_layers;
   c->la.resize(L);
-  const int Lsave = c->training ? L : 1;  // forward-only: every layer reuses one set
+  // forward-only: every layer reuses one set. Recompute: one set too, but every layer keeps its own input
+  const int Lsave = (c->training && !c->recompute) ? L : 1;
   for (int l = 0; l < L; ++l) {
     if (l < Lsave) {
       auto& x = c->la[l];
@@ -508,6 +510,7 @@ void alloc_activations(b200w_ctx* c) {
       x.lse = c->alloc<float>(H * T);
     } else {
       c->la[l] = c->la[0];
+      if (c->training && c->recompute) c->la[l].h_in = c->alloc<bf16>(T * d);
     }
   }
   c->h_final = c->alloc<bf16>(T * d);
@@ -570,12 +573,31 @@ void egemm(b200w_ctx* c, const void* A, bool a_mn, int lda, const void* B, bool 
 }
 
 // ---- forward of one micro-batch (ids already on device): Llama family ------------------------
-void forward_micro_llama(b200w_ctx* c, const int32_t* ids, int nseq) {
+// One Llama decoder layer: x's buffers receive the activations the backward needs, h_next the layer's output
+// (nullptr in the recompute pass of the backward, which stops before the down projection).
+void forward_layer_llama(b200w_ctx* c, int l, const bf16* h_in, bf16* h_next, b200w_ctx::LayerA& x, int nseq) {
   const b200w_arch& a = c->arch;
   const int S = a.max_seq_len, T = nseq * S, d = a.hidden_size, f = a.intermediate_size;
   const int H = a.num_heads, Hkv = a.num_kv_heads, dh = a.head_dim;
   const int qd = H * dh, kd = Hkv * dh, qkvd = qkv_dim(c);
   const float scale = 1.f / sqrtf(static_cast<float>(dh));
+  cudaStream_t s = c->stream;
+  int64_t& n = c->launches;
+  const auto& p = c->lp[l];
+  rmsnorm_fwd(h_in, c->w + p.ln1, x.n1, x.rstd1, T, d, a.rms_norm_eps, s); ++n;
+  egemm(c, x.n1, false, d, c->w + p.wqkv, false, d, x.qkv, nullptr, false, qkvd, T, qkvd, d);
+  rope_apply(x.qkv, qkvd, c->rope_tab, T, S, H + Hkv, dh, false, s); ++n;
+  attention_fwd(x.qkv, qkvd, qd, qd + kd, x.attn, qd, x.lse, nseq, S, H, Hkv, scale, s); ++n;
+  egemm(c, x.attn, false, qd, c->w + p.wo, false, qd, x.h_mid, h_in, false, d, T, d, qd);
+  rmsnorm_fwd(x.h_mid, c->w + p.ln2, x.n2, x.rstd2, T, d, a.rms_norm_eps, s); ++n;
+  egemm(c, x.n2, false, d, c->w + p.wgu, false, d, x.gu, nullptr, false, 2 * f, T, 2 * f, d);
+  swiglu_fwd(x.gu, x.act, T, f, s); ++n;
+  if (h_next) egemm(c, x.act, false, f, c->w + p.wd, false, f, h_next, x.h_mid, false, d, T, d, f);
+}
+
+void forward_micro_llama(b200w_ctx* c, const int32_t* ids, int nseq) {
+  const b200w_arch& a = c->arch;
+  const int S = a.max_seq_len, T = nseq * S, d = a.hidden_size;
   cudaStream_t s = c->stream;
   int64_t& n = c->launches;
   const int L = a.num_layers;
@@ -584,19 +606,10 @@ void forward_micro_llama(b200w_ctx* c, const int32_t* ids, int nseq) {
   embed_fwd(ids, c->w + c->p_embed, nullptr, h, T, d, a.vocab_size, S, 0, s); ++n;
   for (int l = 0; l < L; ++l) {
     auto& x = c->la[l];
-    const auto& p = c->lp[l];
     bf16* h_in = c->training ? x.h_in : h;
     bf16* h_next = c->training ? (l + 1 < L ? c->la[l + 1].h_in : c->h_final)
                                : (h == c->la[0].h_in ? c->h_final : c->la[0].h_in);
-    rmsnorm_fwd(h_in, c->w + p.ln1, x.n1, x.rstd1, T, d, a.rms_norm_eps, s); ++n;
-    egemm(c, x.n1, false, d, c->w + p.wqkv, false, d, x.qkv, nullptr, false, qkvd, T, qkvd, d);
-    rope_apply(x.qkv, qkvd, c->rope_tab, T, S, H + Hkv, dh, false, s); ++n;
-    attention_fwd(x.qkv, qkvd, qd, qd + kd, x.attn, qd, x.lse, nseq, S, H, Hkv, scale, s); ++n;
-    egemm(c, x.attn, false, qd, c->w + p.wo, false, qd, x.h_mid, h_in, false, d, T, d, qd);
-    rmsnorm_fwd(x.h_mid, c->w + p.ln2, x.n2, x.rstd2, T, d, a.rms_norm_eps, s); ++n;
-    egemm(c, x.n2, false, d, c->w + p.wgu, false, d, x.gu, nullptr, false, 2 * f, T, 2 * f, d);
-    swiglu_fwd(x.gu, x.act, T, f, s); ++n;
-    egemm(c, x.act, false, f, c->w + p.wd, false, f, h_next, x.h_mid, false, d, T, d, f);
+    forward_layer_llama(c, l, h_in, h_next, x, nseq);
     h = h_next;
   }
   // in training mode h == h_final; in forward-only mode h is whichever buffer came last
@@ -790,6 +803,9 @@ void backward_micro_llama(b200w_ctx* c, const int32_t* ids, int nseq, bool first
     auto& x = c->la[l];
     const auto& p = c->lp[l];
     const size_t o_q = p.wqkv, o_o = p.wo, o_gu = p.wgu, o_d = p.wd;
+    // activation recomputation: the layer's forward again, from its saved input into the shared buffers (the same
+    // kernels on the same operands: bit-identical activations, hence bit-identical gradients)
+    if (c->recompute) forward_layer_llama(c, l, x.h_in, nullptr, x, nseq);
     // h_next = h_mid + act Wd^T
     egemm(c, dh_cur, false, d, c->w + o_d, true, f, c->dact, nullptr, false, f, T, f, d);
     egemm(c, dh_cur, true, d, x.act, true, f, g + o_d, acc(o_d), true, f, d, f, T, nullptr, 0, wire(o_d));
@@ -1297,8 +1313,14 @@ int b200w_model_init(b200w_ctx* ctx, const b200w_arch* arch, const b200w_hparams
     ctx->arch = *arch;
     if (hp) ctx->hp = *hp; else b200w_default_hparams(&ctx->hp);
     ctx->micro_batch = micro_batch;
+    B200W_CHECK(training >= 0 && (training & ~B200W_TRAIN_RECOMPUTE) <= 2, "training: 0, 1 or 2, optionally | B200W_TRAIN_RECOMPUTE");
+    const bool recompute = (training & B200W_TRAIN_RECOMPUTE) != 0;
+    training &= ~B200W_TRAIN_RECOMPUTE;
+    B200W_CHECK(!recompute || (training != 0 && !opt && !falcon),
+                "activation recomputation is built for fine-tuning the Llama family");
     ctx->training = training != 0;
     ctx->shard = training == 2;
+    ctx->recompute = recompute;
     B200W_CHECK(!(training == 2 && arch->head_dim != 128), "sharded optimiser state is built for head_dim 128 models");
     B200W_CHECK(!ctx->shard || (ctx->comm && ctx->nranks > 1),
                 "sharded optimiser state needs the communicator first: b200w_comm_init before b200w_model_init(training = 2)");

@@ -235,3 +235,35 @@ def test_real_width_layer_at_full_sequence_length():
         assert err < 3e-2, (name, err)
     print(f"real-width layer: worst gradient rel_err {worst:.3e}")
     e.close()
+
+
+@pytest.mark.parametrize("case,micro", [("llama_tiny_gqa", 1), ("llama_tiny_mha", 2)])
+def test_activation_recompute_is_bit_identical_and_smaller(case, micro):
+    """B200W_TRAIN_RECOMPUTE: only every layer's input survives the forward, the backward re-runs the layer. The same
+    kernels on the same operands: loss, grad-norm and every fp32 master weight after two steps are BIT-identical
+    to the mode that keeps all activations, with less device memory."""
+    fx, oa, arch, B, seed = _load(case)
+    params = O.seeded_params(oa, seed)
+    out = {}
+    for rec in (False, True):
+        e = Engine(0)
+        e.init_model(arch, micro_batch=micro, training=True, recompute=rec)
+        e.load_state_dict(params)
+        s1 = e.train_step(fx["ids"], fx["labels"], lr=5e-5)
+        s2 = e.train_step(fx["ids2"], fx["labels2"], lr=2.5e-5)
+        out[rec] = (s1, s2, {n: e.read_state(n, s, "master") for n, s in e.params()}, e.device_bytes())
+        e.close()
+    assert out[True][0] == out[False][0] and out[True][1] == out[False][1]
+    for n in out[False][2]:
+        assert np.array_equal(out[True][2][n], out[False][2][n]), n
+    print(f"{case}: device bytes {out[False][3]} -> {out[True][3]} with recomputation")
+    assert out[True][3] < out[False][3] if arch.num_layers > 1 else out[True][3] == out[False][3]
+
+
+def test_activation_recompute_is_refused_where_it_is_not_built():
+    from runbooks_b200._lib import B200WError
+    from runbooks_b200.engine import OptArch
+    e = Engine(0)
+    with pytest.raises(B200WError):
+        e.init_model(OptArch(192, 128, 256, 2, 2, 128, 128), micro_batch=1, training=True, recompute=True)
+    e.close()

@@ -240,6 +240,7 @@ def run_reference(args):
 PER_DEVICE_BATCH = 8
 
 
+RECOMPUTE = False
 MICRO_BATCH = 2   # sequences per accumulation micro-step: T = 8192 rows per GEMM (see workload_config)
 SHARD_STATE = False
 def gemm_traffic():
@@ -266,7 +267,7 @@ def workload_config(n_gpus: int):
     return dict(workload="Llama-2-7B bf16 causal-LM fine-tune, seq 4096 (BASELINE.json configs[1])",
                 global_batch=PER_DEVICE_BATCH * n_gpus, seq_len=4096, per_device_batch=PER_DEVICE_BATCH,
                 micro_batch=MICRO_BATCH, parallelism=f"dp{n_gpus}" + ("-sharded-state" if SHARD_STATE and n_gpus > 1 else ""),
-                optimizer="AdamW fp32 master, clip 1.0",
+                optimizer="AdamW fp32 master, clip 1.0" + (", activation recomputation" if RECOMPUTE else ""),
                 l2="working set (13.5 GB bf16 weights + activations per micro-step) >> 126 MB L2; no flush needed",
                 micro_batch_note=("the per-device batch of 8 sequences runs as 4 accumulation micro-steps of 2: the N = 4096 "
                                   "GEMMs then have 512 instead of 256 output tiles for 74 CTA pairs (98.8 % instead of 86.5 % wave "
@@ -320,7 +321,7 @@ def run_ours(args):
         uid = bytes(uid.numpy().tobytes())
     if shard:                                # sharded optimiser state: the communicator comes first
         e.comm_init(rank, world, uid)
-    e.init_model(arch, micro_batch=args.micro_batch, training=True, shard_state=shard)
+    e.init_model(arch, micro_batch=args.micro_batch, training=True, shard_state=shard, recompute=bool(args.recompute))
     e.init_random(seed=0, std=0.02)          # identical replicas: same seed on every rank
     if world > 1 and not shard:
         e.comm_init(rank, world, uid)
@@ -541,7 +542,7 @@ def emit(line: dict):
 
 
 def main():
-    global MICRO_BATCH, SHARD_STATE
+    global MICRO_BATCH, SHARD_STATE, RECOMPUTE
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -554,12 +555,16 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="development only: fewer layers")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-decode", action="store_true", help="skip the Falcon-7B decode leg (N=1 only)")
+    ap.add_argument("--recompute", action="store_true",
+                    help="activation recomputation (NOT the benchmark default: the extra forward work is real work "
+                         "but not algorithmic FLOPs; the line is labelled)")
     ap.add_argument("--shard-state", action="store_true", default=bool(os.environ.get("B200W_SHARD_STATE")),
                     help="N>1: fp32 master / Adam moments sharded over the ranks (reduce-scatter + all-gather)")
     ap.add_argument("--decode-only", action="store_true", help="run only the decode leg and print its object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     MICRO_BATCH = args.micro_batch
+    RECOMPUTE = bool(args.recompute)
     SHARD_STATE = bool(args.shard_state)
     # A rank that fails must EXIT, at once: its peers are inside a collective that can no longer
     # complete, and the launcher only tears the job down when a worker process ends. Interpreter

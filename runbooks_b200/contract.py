@@ -47,6 +47,7 @@ class TrainParams:
     optim: str = "adamw_torch_fused"   # the default with torch >= 2.8 (training_args.py:797-806); same AdamW formula as adamw_torch
     label_smoothing_factor: float = 0.0
     average_tokens_across_devices: str = "true"
+    gradient_checkpointing: str = "false"   # TrainingArguments.gradient_checkpointing: activation recomputation (same results)
     save_steps: int = 500
     logging_steps: int = 1
     seed: int = 42
@@ -107,11 +108,17 @@ def load_params(path: Optional[str] = None, environ: Optional[Dict[str, str]] = 
     if str(p.average_tokens_across_devices).strip().lower() not in ("true", "1"):
         raise ValueError("average_tokens_across_devices=false is not implemented: the N-rank step always "
                          "normalises by the global target count (the TrainingArguments default)")
+    if str(p.gradient_checkpointing).strip().lower() not in ("true", "false", "1", "0"):
+        raise ValueError(f"gradient_checkpointing={p.gradient_checkpointing!r}: expected true or false")
     if p.warmup_steps < 0:
         raise ValueError("warmup_steps must be >= 0")
     if p.gradient_accumulation_steps < 1 or p.per_device_train_batch_size < 1:
         raise ValueError("batch sizes must be >= 1")
     return p
+
+
+def wants_recompute(p: TrainParams) -> bool:
+    return str(p.gradient_checkpointing).strip().lower() in ("true", "1")
 
 
 def warmup_steps_for(total_steps: int, warmup_steps: float) -> int:

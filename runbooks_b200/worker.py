@@ -76,7 +76,7 @@ def train_rank(rank: int, world: int, uid: bytes, content: str) -> None:
     eng = Engine(rank)
     eng.init_model(arch, micro_batch=1, training=True, max_grad_norm=params.max_grad_norm,
                    weight_decay=params.weight_decay, betas=(params.adam_beta1, params.adam_beta2),
-                   eps=params.adam_epsilon)
+                   eps=params.adam_epsilon, recompute=contract.wants_recompute(params))   # Llama family; others raise
     wanted = {n for n, _ in eng.params()}
     seen, unused = set(), []
     t_load, load_bytes = time.time(), 0

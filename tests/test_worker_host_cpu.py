@@ -100,6 +100,21 @@ def test_two_ranks_plan_the_same_steps_and_partition_every_global_batch(content,
     assert (lab == -100).any() and (lab != -100).any()
 
 
+def test_gradient_checkpointing_param_selects_activation_recomputation(content, capsys):
+    """TrainingArguments.gradient_checkpointing (string or bool in params.json) reaches the engine as recompute."""
+    for value, want in (("true", True), (True, True), ("false", False), (None, False)):
+        CALLS.clear()
+        kw = dict(max_steps=1, per_device_train_batch_size=2, max_seq_length=128, save_steps=0)
+        if value is not None:
+            kw["gradient_checkpointing"] = value
+        _write_params(content, **kw)
+        worker.train_rank(0, 1, b"", str(content))
+        assert CALLS[0]["hparams"]["recompute"] is want, (value, CALLS[0]["hparams"])
+    _write_params(content, max_steps=1, gradient_checkpointing="sometimes")
+    with pytest.raises(ValueError):
+        worker.train_rank(0, 1, b"", str(content))
+
+
 def test_checkpoints_final_artifacts_and_log_lines(content, capsys):
     _write_params(content, max_steps=5, per_device_train_batch_size=2, max_seq_length=128, save_steps=2, logging_steps=1)
     worker.train_rank(0, 1, b"", str(content))

@@ -198,7 +198,9 @@ def cpu_measure(repeats: int, budget_s: float):
     n = max(3, min(repeats, int(budget_s / max(t_one, 1e-3))))
     if t_one > budget_s:
         n = 1
+    t_runs = time.perf_counter()
     runs = [smp.run() for _ in range(n)]
+    timed_wall = time.perf_counter() - t_runs
     a = smp.a
     per_seq = sorted(a.num_layers * tl + th for tl, th in runs)
     med = per_seq[len(per_seq) // 2]
@@ -210,7 +212,8 @@ def cpu_measure(repeats: int, budget_s: float):
                         f"median of {n} repeats after 1 warm-up"),
                 repeats=n, spread_max_over_min=round(per_seq[-1] / per_seq[0], 3),
                 layer_s=round(sorted(r[0] for r in runs)[n // 2], 3), head_s=round(sorted(r[1] for r in runs)[n // 2], 3),
-                threads_sweep_ms=sweep, host_threads_available=avail)
+                threads_sweep_ms=sweep, host_threads_available=avail,
+                timed_wall_s=round(timed_wall, 2), warmup_wall_s=round(t_one, 2))
     return value, med, desc
 
 
@@ -233,7 +236,12 @@ def run_reference(args):
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=workload_config(args.gpus), cpu_baseline=desc,
                 e2e=dict(value=round(value, 3), unit="tokens/s", h2d_bytes_per_step=0,
-                         d2h_bytes_per_step=0))
+                         d2h_bytes_per_step=0),
+                # what a wall clock around this process sees is cpu_baseline.timed_wall_s (+ warm-up and imports), NOT
+                # steps x ms_per_step: a step of this arm is a bounded SAMPLE (one of the 32 layers + the head, one of
+                # the 8 sequences); ms_per_step is the full workload step that sample implies
+                ms_per_step_is="32 x layer_s + head_s per sequence, x 8 sequences (cpu_baseline.layer_s / head_s); "
+                               "wall time actually spent: cpu_baseline.timed_wall_s")
     emit(line)
 
 

@@ -125,7 +125,9 @@ def cpu_pick_threads():
 
 class CpuSample:
     """Holds the tensors of the sample so that repeats time arithmetic, not allocation / RNG."""
-    TOKENS = 4096
+    # 4096 = the workload's sequence length. The variable exists for the contract test of this arm (tests/
+    # test_bench_reference_cpu.py); any other value is stated in the line's `sample` text.
+    TOKENS = int(os.environ.get("B200W_BENCH_CPU_SAMPLE_TOKENS", "4096"))
 
     def __init__(self):
         import torch
@@ -207,7 +209,7 @@ def cpu_measure(repeats: int, budget_s: float):
     value = CpuSample.TOKENS / med
     desc = dict(value=round(value, 3), unit="tokens/s", cores=threads, kind="port",
                 sample=(f"oracle port (fp32 torch, HF semantics): 1 of 32 true-width Llama-2-7B decoder layers "
-                        f"fwd + bwd + AdamW on a full 4096-token sequence, plus final norm + lm_head + CE fwd/bwd "
+                        f"fwd + bwd + AdamW on a full {CpuSample.TOKENS}-token sequence, plus final norm + lm_head + CE fwd/bwd "
                         f"(the real loss); step = 32 x layer + head per sequence, no extrapolation in tokens; "
                         f"median of {n} repeats after 1 warm-up"),
                 repeats=n, spread_max_over_min=round(per_seq[-1] / per_seq[0], 3),
